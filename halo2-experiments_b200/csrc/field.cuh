@@ -1,0 +1,209 @@
+// bn256 Fr / Fq on the sm_100a integer pipe: 8 x u32 little-endian limbs in
+// Montgomery form (R = 2^256) — bit-identical in memory to halo2curves'
+// `Fr([u64; 4])` / `Fq([u64; 4])` (halo2curves 0.3.1 src/bn256/{fr,fq}.rs, reached
+// from /root/reference/src/circuits/utils.rs:2), so Rust `Vec<Fr>` buffers are
+// consumed zero-copy.  All results are fully reduced to [0, p): every value that
+// leaves a kernel is the canonical Montgomery representative, which is what
+// makes device results bit-exact against the CPU path.
+//
+// The multiplier is an even/odd-column CIOS: products a[j]*b_i with even j land
+// on 64-bit aligned limb pairs of one accumulator, odd j on the other, so each
+// (lo,hi) pair is one IMAD.WIDE.U32 with carry-in/out and the two carry chains
+// never collide.  8 rounds x (16 + 16 wide halves + 1 mul.lo) = 264 mul32 halves
+// = 132 IMAD.WIDE + 8 IMAD per field multiplication.
+#pragma once
+#include "ptx_chain.cuh"
+
+namespace b200zk {
+
+struct alignas(32) fe_t { uint32_t l[8]; };   // 32-byte aligned -> LDG.E.256 / STG.E.256 on sm_100a
+
+struct FrCfg {
+    static constexpr uint32_t INV = 0xefffffffu;         // -r^-1 mod 2^32
+    ZK_D static constexpr uint32_t p(int i) {
+        constexpr uint32_t t[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                                   0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return t[i];
+    }
+    ZK_D static constexpr uint32_t one(int i) {          // R mod r
+        constexpr uint32_t t[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                                   0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return t[i];
+    }
+    ZK_D static constexpr uint32_t r2(int i) {           // R^2 mod r
+        constexpr uint32_t t[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                                   0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+        return t[i];
+    }
+};
+
+struct FqCfg {
+    static constexpr uint32_t INV = 0xe4866389u;         // -q^-1 mod 2^32
+    ZK_D static constexpr uint32_t p(int i) {
+        constexpr uint32_t t[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u,
+                                   0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return t[i];
+    }
+    ZK_D static constexpr uint32_t one(int i) {          // R mod q
+        constexpr uint32_t t[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                                   0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return t[i];
+    }
+    ZK_D static constexpr uint32_t r2(int i) {           // R^2 mod q
+        constexpr uint32_t t[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
+                                   0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+        return t[i];
+    }
+};
+
+template <class C> struct Field {
+    typedef fe_t T;
+
+    ZK_D static T zero() { T r; for (int i = 0; i < 8; ++i) r.l[i] = 0; return r; }
+    ZK_D static T one() { T r; for (int i = 0; i < 8; ++i) r.l[i] = C::one(i); return r; }
+    ZK_D static T r2() { T r; for (int i = 0; i < 8; ++i) r.l[i] = C::r2(i); return r; }
+    ZK_D static bool is_zero(const T& a) {
+        uint32_t o = 0; for (int i = 0; i < 8; ++i) o |= a.l[i]; return o == 0;
+    }
+    ZK_D static bool eq(const T& a, const T& b) {
+        uint32_t o = 0; for (int i = 0; i < 8; ++i) o |= a.l[i] ^ b.l[i]; return o == 0;
+    }
+
+    // r = a - p if a >= p else a          (a < 2p)
+    ZK_D static void reduce_once(T& a) {
+        uint32_t t[8];
+        t[0] = ptx::sub_cc(a.l[0], C::p(0));
+#pragma unroll
+        for (int i = 1; i < 8; ++i) t[i] = ptx::subc_cc(a.l[i], C::p(i));
+        uint32_t borrow = ptx::subc(0, 0);               // 0xffffffff if a < p
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a.l[i] = borrow ? a.l[i] : t[i];
+    }
+
+    ZK_D static T add(const T& a, const T& b) {
+        T r;
+        r.l[0] = ptx::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) r.l[i] = ptx::addc_cc(a.l[i], b.l[i]);
+        r.l[7] = ptx::addc(a.l[7], b.l[7]);              // p < 2^254: no carry out
+        reduce_once(r);
+        return r;
+    }
+    ZK_D static T sub(const T& a, const T& b) {
+        T r;
+        r.l[0] = ptx::sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < 8; ++i) r.l[i] = ptx::subc_cc(a.l[i], b.l[i]);
+        uint32_t borrow = ptx::subc(0, 0);               // all-ones if a < b
+        r.l[0] = ptx::add_cc(r.l[0], C::p(0) & borrow);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) r.l[i] = ptx::addc_cc(r.l[i], C::p(i) & borrow);
+        r.l[7] = ptx::addc(r.l[7], C::p(7) & borrow);
+        return r;
+    }
+    ZK_D static T neg(const T& a) { return sub(zero(), a); }
+    ZK_D static T dbl(const T& a) { return add(a, a); }
+
+    // acc[0..7] += a[even limbs 0,2,4,6 starting at `a`] * b as one carry chain; the
+    // carry out of acc[7] is left in CC.
+    ZK_D static void cmad_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
+        acc[0] = ptx::mad_lo_cc(a[0], b, acc[0]);
+        acc[1] = ptx::madc_hi_cc(a[0], b, acc[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            acc[j] = ptx::madc_lo_cc(a[j], b, acc[j]);
+            acc[j + 1] = ptx::madc_hi_cc(a[j], b, acc[j + 1]);
+        }
+    }
+    // same, consuming the incoming CC carry and reading the addend two limbs up:
+    // acc[j] = acc[j+2] + a[j]*b  (j < 6),  acc[6..7] = a[6]*b  — the "shift right by 64 bits"
+    // that re-aligns the accumulator which just lost its low limb.
+    ZK_D static void madc_row_rshift(uint32_t* acc, const uint32_t* a, uint32_t b) {
+#pragma unroll
+        for (int j = 0; j < 6; j += 2) {
+            acc[j] = ptx::madc_lo_cc(a[j], b, acc[j + 2]);
+            acc[j + 1] = ptx::madc_hi_cc(a[j], b, acc[j + 3]);
+        }
+        acc[6] = ptx::madc_lo_cc(a[6], b, 0);
+        acc[7] = ptx::madc_hi(a[6], b, 0);
+    }
+    ZK_D static void mul_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) { acc[j] = ptx::mul_lo(a[j], b); acc[j + 1] = ptx::mul_hi(a[j], b); }
+    }
+
+    // One CIOS round.  `ev` holds limb positions 0..7, `od` positions 1..8 on exit;
+    // on entry (not first) `od` is the previous round's even accumulator, i.e. it is
+    // positioned at -1..6 with od[0] == 0 already consumed.
+    ZK_D static void round(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t bi, bool first) {
+        const uint32_t P[8] = {C::p(0), C::p(1), C::p(2), C::p(3), C::p(4), C::p(5), C::p(6), C::p(7)};
+        if (first) {
+            mul_row(od, a + 1, bi);
+            mul_row(ev, a, bi);
+        } else {
+            ev[0] = ptx::add_cc(ev[0], od[1]);           // position 0 of the shifted accumulator
+            madc_row_rshift(od, a + 1, bi);              // carry continues into position 1
+            cmad_row(ev, a, bi);
+            od[7] = ptx::addc(od[7], 0);                 // carry out of position 7 -> position 8
+        }
+        uint32_t m = ptx::mul_lo(ev[0], C::INV);
+        cmad_row(od, P + 1, m);                          // total < 2^288, so no carry out of od[7]
+        cmad_row(ev, P, m);
+        od[7] = ptx::addc(od[7], 0);
+        // now ev[0] == 0; dividing by 2^32 swaps the roles of the two accumulators
+    }
+
+    ZK_D static T mul(const T& a, const T& b) {
+        uint32_t ev[8], od[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            round(ev, od, a.l, b.l[i], i == 0);
+            round(od, ev, a.l, b.l[i + 1], false);
+        }
+        // result = ev (positions 0..7) + od>>32 (od[1..7] at positions 0..6)
+        T r;
+        r.l[0] = ptx::add_cc(ev[0], od[1]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) r.l[i] = ptx::addc_cc(ev[i], od[i + 1]);
+        r.l[7] = ptx::addc(ev[7], 0);
+        reduce_once(r);
+        return r;
+    }
+    ZK_D static T sqr(const T& a) { return mul(a, a); }
+
+    ZK_D static T from_mont(const T& a) {                // a * 1 * R^-1 : canonical integer
+        T o = zero(); o.l[0] = 1; return mul(a, o);
+    }
+    ZK_D static T to_mont(const T& a) { return mul(a, r2()); }
+
+    // a^e, e given as canonical 256-bit LE limbs (variable time)
+    ZK_D static T pow(const T& a, const uint32_t e[8]) {
+        T acc = one();
+        for (int i = 255; i >= 0; --i) {
+            acc = sqr(acc);
+            if ((e[i >> 5] >> (i & 31)) & 1) acc = mul(acc, a);
+        }
+        return acc;
+    }
+    ZK_D static T pow_u64(const T& a, unsigned long long e) {
+        T acc = one();
+        bool started = false;
+        for (int i = 63; i >= 0; --i) {
+            if (started) acc = sqr(acc);
+            if ((e >> i) & 1) { acc = started ? mul(acc, a) : a; started = true; }
+        }
+        return acc;
+    }
+    ZK_D static T inv(const T& a) {                      // Fermat; inv(0) = 0
+        uint32_t e[8];
+        e[0] = C::p(0) - 2;                              // p is odd and p(0) >= 2 for both fields
+#pragma unroll
+        for (int i = 1; i < 8; ++i) e[i] = C::p(i);
+        return pow(a, e);
+    }
+};
+
+typedef Field<FrCfg> Fr;
+typedef Field<FqCfg> Fq;
+
+}  // namespace b200zk

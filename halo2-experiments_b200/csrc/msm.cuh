@@ -1,0 +1,151 @@
+// Signed-digit Pippenger multi-scalar multiplication over bn256 G1, replacing
+// halo2_proofs `arithmetic::best_multiexp` (PSE v2023_02_02 src/arithmetic.rs),
+// which the reference reaches through ParamsKZG::commit / commit_lagrange inside
+// keygen_vk / create_proof (/root/reference/src/circuits/utils.rs:31,40-48).
+// The group element returned is independent of the bucket method, so parity with
+// the CPU path is bit-exact after affine normalisation.
+//
+// Device pipeline (all state in HBM, one launch each):
+//   1. digits+count : scalar -> canonical (one Montgomery mul by 1), W signed
+//                     c-bit digits, histogram of (window, |digit|) keys
+//   2. scan         : exclusive prefix sum of the histogram
+//   3. scatter      : counting sort of (point index, sign) entries by key
+//   4. accumulate   : one thread per bucket, XYZZ mixed additions (the IMAD-bound
+//                     kernel; N*W additions of 8M+2S)
+//   5. reduce       : per window, chunked running sums  sum_v v*B_v
+//   6. fold         : per window tree sum of the chunk results
+// The W window sums (W*128 B) go back to the host, which does the last W*c
+// doublings — a strictly serial chain that a CPU core finishes ~10x sooner than
+// one GPU thread — and the affine normalisation for the transcript.
+#pragma once
+#include "curve.cuh"
+#include "blockexec.cuh"
+
+namespace b200zk {
+
+#if defined(__CUDACC__)
+ZK_D uint32_t zk_atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+#else
+inline uint32_t zk_atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+#endif
+
+struct MsmArgs {
+    const fe_t* scalars;        // n Montgomery-form Fr
+    const affine_t* bases;      // n affine points
+    uint32_t n;
+    uint32_t c;                 // window bits
+    uint32_t nwin;              // W = ceil(255 / c)
+    uint32_t log_t;             // reduce: 2^log_t chunks per window
+    uint32_t* counts;           // [W << (c-1)]
+    uint32_t* offsets;          // [(W << (c-1)) + 1]
+    uint32_t* cursor;           // [W << (c-1)]
+    uint32_t* entries;          // [n * W]   (index << 1) | sign
+    xyzz_t* buckets;            // [W << (c-1)]
+    xyzz_t* partials;           // [W << log_t]
+    xyzz_t* window_sums;        // [W]
+};
+
+ZK_D uint32_t msm_window_bits(const fe_t& s, uint32_t bit, uint32_t c) {
+    uint32_t idx = bit >> 5, sh = bit & 31;
+    if (idx >= 8) return 0;
+    uint32_t v = s.l[idx] >> sh;
+    if (sh + c > 32 && idx + 1 < 8) v |= s.l[idx + 1] << (32 - sh);
+    return v & ((1u << c) - 1);
+}
+
+// Calls f(key, sign) for every non-zero signed digit of scalar i.
+// Digits d_j in [-2^(c-1), 2^(c-1)]; key = j * 2^(c-1) + |d_j| - 1.
+template <class F> ZK_D void msm_for_each_digit(const MsmArgs& a, uint32_t i, F f) {
+    fe_t s = Fr::from_mont(a.scalars[i]);
+    uint32_t carry = 0, half = 1u << (a.c - 1);
+    for (uint32_t j = 0; j < a.nwin; ++j) {
+        uint32_t d = msm_window_bits(s, j * a.c, a.c) + carry;
+        uint32_t sign = 0;
+        if (d > half) { d = (1u << a.c) - d; sign = 1; carry = 1; } else carry = 0;
+        if (d != 0) f(j * half + d - 1, sign);
+    }
+}
+
+ZK_D void msm_count_thread(const MsmArgs& a, uint32_t i) {
+    if (i >= a.n) return;
+    msm_for_each_digit(a, i, [&](uint32_t key, uint32_t) { zk_atomic_add(&a.counts[key], 1u); });
+}
+
+ZK_D void msm_scatter_thread(const MsmArgs& a, uint32_t i) {
+    if (i >= a.n) return;
+    msm_for_each_digit(a, i, [&](uint32_t key, uint32_t sign) {
+        uint32_t pos = zk_atomic_add(&a.cursor[key], 1u);
+        a.entries[pos] = (i << 1) | sign;
+    });
+}
+
+// Single-block exclusive scan of counts[0..total) into offsets[0..total] and cursor.
+// sm: nthreads + 1 words.
+ZK_D void msm_scan_block(const MsmArgs& a, uint32_t nthreads, uint32_t* sm) {
+    const uint32_t total = a.nwin << (a.c - 1);
+    const uint32_t per = (total + nthreads - 1) / nthreads;
+    ZK_PHASE_BEGIN(tid, nthreads)
+    uint32_t s = 0, b = tid * per, e = b + per < total ? b + per : total;
+    for (uint32_t k = b; k < e; ++k) s += a.counts[k];
+    sm[tid] = s;
+    ZK_PHASE_END
+    ZK_PHASE_BEGIN(tid, nthreads)
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (uint32_t t = 0; t < nthreads; ++t) { uint32_t v = sm[t]; sm[t] = run; run += v; }
+        sm[nthreads] = run;
+    }
+    ZK_PHASE_END
+    ZK_PHASE_BEGIN(tid, nthreads)
+    uint32_t run = sm[tid], b = tid * per, e = b + per < total ? b + per : total;
+    for (uint32_t k = b; k < e; ++k) { a.offsets[k] = run; a.cursor[k] = run; run += a.counts[k]; }
+    if (tid == 0) a.offsets[total] = sm[nthreads];
+    ZK_PHASE_END
+}
+
+ZK_D void msm_accumulate_thread(const MsmArgs& a, uint32_t key) {
+    if (key >= (a.nwin << (a.c - 1))) return;
+    uint32_t b = a.offsets[key], e = a.offsets[key + 1];
+    xyzz_t acc = xyzz_identity();
+    for (uint32_t k = b; k < e; ++k) {
+        uint32_t en = a.entries[k];
+        xyzz_madd(acc, a.bases[en >> 1], en & 1);
+    }
+    a.buckets[key] = acc;
+}
+
+// gid -> (window j, chunk t).  Chunk covers bucket indices [b0, b0 + m), bucket b has
+// multiplier b + 1:  sum (b+1) B_b = sum (b - b0 + 1) B_b  +  b0 * sum B_b.
+ZK_D void msm_reduce_thread(const MsmArgs& a, uint32_t gid) {
+    if (gid >= (a.nwin << a.log_t)) return;
+    uint32_t j = gid >> a.log_t, t = gid & ((1u << a.log_t) - 1);
+    uint32_t m = (1u << (a.c - 1)) >> a.log_t, b0 = t * m;
+    const xyzz_t* B = a.buckets + ((size_t)j << (a.c - 1));
+    xyzz_t running = xyzz_identity(), acc = xyzz_identity();
+    for (uint32_t b = b0 + m; b-- > b0;) {
+        xyzz_add(running, B[b]);
+        xyzz_add(acc, running);
+    }
+    if (b0 != 0) { xyzz_t s = xyzz_mul_small(running, b0); xyzz_add(acc, s); }
+    a.partials[gid] = acc;
+}
+
+// One block per window: sum the 2^log_t chunk results.  sm: nthreads xyzz_t.
+ZK_D void msm_fold_block(const MsmArgs& a, uint32_t j, uint32_t nthreads, xyzz_t* sm) {
+    const uint32_t T = 1u << a.log_t;
+    ZK_PHASE_BEGIN(tid, nthreads)
+    xyzz_t acc = xyzz_identity();
+    for (uint32_t t = tid; t < T; t += nthreads) xyzz_add(acc, a.partials[((size_t)j << a.log_t) + t]);
+    sm[tid] = acc;
+    ZK_PHASE_END
+    for (uint32_t s = nthreads >> 1; s > 0; s >>= 1) {
+        ZK_PHASE_BEGIN(tid, nthreads)
+        if (tid < s) { xyzz_t v = sm[tid]; xyzz_add(v, sm[tid + s]); sm[tid] = v; }
+        ZK_PHASE_END
+    }
+    ZK_PHASE_BEGIN(tid, nthreads)
+    if (tid == 0) a.window_sums[j] = sm[0];
+    ZK_PHASE_END
+}
+
+}  // namespace b200zk

@@ -1,0 +1,43 @@
+// Host-side planning and finishing for msm.cuh (pure C++, no CUDA types).
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include "host_field.hpp"
+
+namespace b200zk {
+
+struct MsmShape {
+    uint32_t c, nwin, log_t;
+    size_t nbuckets;         // nwin << (c-1)
+};
+
+// Window choice: accumulate does n*W mixed additions (10 muls each), reduce does
+// 2 * 2^(c-1) * W full additions (14 muls) at much lower parallel efficiency.
+inline MsmShape msm_plan_shape(size_t n, int force_c = 0) {
+    MsmShape s{};
+    uint32_t lg = 0; while (((size_t)1 << (lg + 1)) <= n) ++lg;
+    uint32_t c = lg > 4 ? lg - 4 : 2;
+    if (c < 4) c = 4;
+    if (c > 16) c = 16;
+    if (force_c > 0) c = (uint32_t)force_c;
+    s.c = c;
+    s.nwin = (255 + c - 1) / c;
+    uint32_t log_b = c - 1;
+    s.log_t = log_b > 5 ? log_b - 5 : 0;                // 32 buckets per reduce thread
+    s.nbuckets = (size_t)s.nwin << (c - 1);
+    return s;
+}
+
+// sum_j 2^(c j) * window_sums[j]  -> affine.  window_sums: nwin XYZZ points (device format).
+inline host::HAffine msm_finish(const void* window_sums, uint32_t nwin, uint32_t c) {
+    using namespace host;
+    const HXyzz* w = (const HXyzz*)window_sums;
+    HXyzz acc = hx_identity();
+    for (uint32_t j = nwin; j-- > 0;) {
+        for (uint32_t i = 0; i < c; ++i) acc = hx_dbl(acc);
+        acc = hx_add(acc, w[j]);
+    }
+    return hx_to_affine(acc);
+}
+
+}  // namespace b200zk

@@ -1,0 +1,75 @@
+"""ctypes binding for the host-emulation build of the device headers (test aid)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "libemu.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+        _lib = ctypes.CDLL(_LIB)
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+OPS = {"add": 0, "sub": 1, "mul": 2, "sqr": 3, "inv": 4, "from_mont": 5, "to_mont": 6}
+
+
+def field_op(which, op, a, b=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    b = a if b is None else np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros_like(a)
+    lib().emu_field_op(which, OPS[op], _p(a), _p(b), _p(out), ctypes.c_size_t(a.shape[0]))
+    return out
+
+
+def field_consts(which):
+    one = np.zeros((1, 4), dtype=np.uint64)
+    r2 = np.zeros((1, 4), dtype=np.uint64)
+    lib().emu_field_consts(which, _p(one), _p(r2))
+    return one[0], r2[0]
+
+
+def ntt(a, log_n, omega, n_in=None, max_log_m=10, max_log_tw=2, tile_cap_log=12, nthreads=64, pre=None, post=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    n_in = a.shape[0] if n_in is None else n_in
+    out = np.zeros((1 << log_n, 4), dtype=np.uint64)
+    pre = None if pre is None else np.ascontiguousarray(pre, dtype=np.uint64)
+    post = None if post is None else np.ascontiguousarray(post, dtype=np.uint64)
+    lib().emu_ntt(_p(a), ctypes.c_uint32(n_in), _p(out), ctypes.c_uint32(log_n), _p(np.ascontiguousarray(omega)),
+                  ctypes.c_uint32(max_log_m), ctypes.c_uint32(max_log_tw), ctypes.c_uint32(tile_cap_log),
+                  ctypes.c_uint32(nthreads), _p(pre), _p(post))
+    return out
+
+
+def msm(scalars, bases, force_c=0):
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+    out = np.zeros(8, dtype=np.uint64)
+    lib().emu_msm(_p(scalars), _p(bases), ctypes.c_uint32(scalars.shape[0]), ctypes.c_int(force_c), _p(out))
+    return out
+
+
+def host_field_op(which, op, a, b=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    b = a if b is None else np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros_like(a)
+    lib().emu_host_field_op(which, {"add": 0, "sub": 1, "mul": 2, "inv": 3}[op], _p(a), _p(b), _p(out), ctypes.c_size_t(a.shape[0]))
+    return out
+
+
+def host_fr_consts(wide):
+    r, z, d, w = (np.zeros(4, dtype=np.uint64) for _ in range(4))
+    wide = np.ascontiguousarray(wide, dtype=np.uint64)
+    lib().emu_host_fr_consts(_p(r), _p(z), _p(d), _p(wide), _p(w))
+    return r, z, d, w

@@ -1,0 +1,123 @@
+// TEST AID: compiles the product's device headers with a host compiler (carry flag
+// and block phases emulated, see csrc/ptx_chain.cuh and csrc/blockexec.cuh) so the
+// limb algorithms and kernel index logic can be checked against the oracle on a box
+// without a GPU.  Never linked into the product library.
+#include <vector>
+#include <cstring>
+#include "../../halo2-experiments_b200/csrc/field.cuh"
+#include "../../halo2-experiments_b200/csrc/ntt.cuh"
+#include "../../halo2-experiments_b200/csrc/ntt_plan.hpp"
+#include "../../halo2-experiments_b200/csrc/msm.cuh"
+#include "../../halo2-experiments_b200/csrc/msm_plan.hpp"
+
+using namespace b200zk;
+
+extern "C" {
+
+// op: 0 add 1 sub 2 mul 3 sqr 4 inv 5 from_mont 6 to_mont ; which: 0 Fr 1 Fq
+void emu_field_op(int which, int op, const fe_t* a, const fe_t* b, fe_t* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        if (which == 0) {
+            switch (op) {
+                case 0: out[i] = Fr::add(a[i], b[i]); break;
+                case 1: out[i] = Fr::sub(a[i], b[i]); break;
+                case 2: out[i] = Fr::mul(a[i], b[i]); break;
+                case 3: out[i] = Fr::sqr(a[i]); break;
+                case 4: out[i] = Fr::inv(a[i]); break;
+                case 5: out[i] = Fr::from_mont(a[i]); break;
+                case 6: out[i] = Fr::to_mont(a[i]); break;
+            }
+        } else {
+            switch (op) {
+                case 0: out[i] = Fq::add(a[i], b[i]); break;
+                case 1: out[i] = Fq::sub(a[i], b[i]); break;
+                case 2: out[i] = Fq::mul(a[i], b[i]); break;
+                case 3: out[i] = Fq::sqr(a[i]); break;
+                case 4: out[i] = Fq::inv(a[i]); break;
+                case 5: out[i] = Fq::from_mont(a[i]); break;
+                case 6: out[i] = Fq::to_mont(a[i]); break;
+            }
+        }
+    }
+}
+
+void emu_field_consts(int which, fe_t* one, fe_t* r2) {
+    if (which == 0) { *one = Fr::one(); *r2 = Fr::r2(); } else { *one = Fq::one(); *r2 = Fq::r2(); }
+}
+
+// Full multi-pass NTT through ntt_pass_block, mirroring the launch sequence of ntt.cu.
+// pre/post: 3 elements each or null.
+void emu_ntt(const fe_t* in, uint32_t n_in, fe_t* out, uint32_t log_n, const fe_t* omega,
+             uint32_t max_log_m, uint32_t max_log_tw, uint32_t tile_cap_log, uint32_t nthreads,
+             const fe_t* pre, const fe_t* post) {
+    NttShape s = ntt_plan_shape(log_n, max_log_m, max_log_tw, tile_cap_log);
+    size_t N = (size_t)1 << log_n;
+    std::vector<fe_t> roots((size_t)1 << (s.log_roots ? s.log_roots - 1 : 0));
+    std::vector<fe_t> lo((size_t)1 << s.tw_lo_bits), hi(N >> s.tw_lo_bits ? N >> s.tw_lo_bits : 1);
+    fe_t w_r = Fr::pow_u64(*omega, 1ull << (log_n - s.log_roots));
+    for (uint32_t i = 0; i < roots.size(); ++i) ntt_pow_table_thread(roots.data(), w_r, i, 0);
+    for (uint32_t i = 0; i < lo.size(); ++i) ntt_pow_table_thread(lo.data(), *omega, i, 0);
+    for (uint32_t i = 0; i < hi.size(); ++i) ntt_pow_table_thread(hi.data(), *omega, i, s.tw_lo_bits);
+    std::vector<fe_t> scratch(N);
+    for (uint32_t p = 0; p < s.npass; ++p) {
+        const NttPassShape& q = s.pass[p];
+        NttPassArgs a{};
+        a.in = p == 0 ? in : scratch.data();
+        a.out = q.is_last ? out : scratch.data();
+        a.log_n = log_n; a.log_m = q.log_m; a.log_l = q.log_l; a.log_tw = q.log_tw; a.is_last = q.is_last;
+        a.log_m1 = q.log_m1; a.log_mid = q.log_mid;
+        a.n_in = p == 0 ? n_in : (uint32_t)N;
+        a.use_pre = (p == 0 && pre) ? 1 : 0; a.use_post = (q.is_last && post) ? 1 : 0;
+        if (pre) memcpy(a.pre, pre, 96);
+        if (post) memcpy(a.post, post, 96);
+        a.roots = roots.data(); a.log_roots = s.log_roots;
+        a.tw_lo = lo.data(); a.tw_hi = hi.data(); a.tw_lo_bits = s.tw_lo_bits;
+        std::vector<half_t> sm((size_t)2 << (q.log_m + q.log_tw));
+        for (uint32_t b = 0; b < q.blocks; ++b) ntt_pass_block(a, b, nthreads, sm.data());
+    }
+}
+
+
+// Full MSM through the block programs of msm.cuh + the host finish of msm_plan.hpp.
+// out_affine: 64 bytes (x, y Montgomery).
+void emu_msm(const fe_t* scalars, const affine_t* bases, uint32_t n, int force_c, uint32_t* out_affine64) {
+    MsmShape s = msm_plan_shape(n, force_c);
+    std::vector<uint32_t> counts(s.nbuckets, 0), offsets(s.nbuckets + 1), cursor(s.nbuckets), entries((size_t)n * s.nwin + 1);
+    std::vector<xyzz_t> buckets(s.nbuckets), partials((size_t)s.nwin << s.log_t), wsum(s.nwin);
+    MsmArgs a{};
+    a.scalars = scalars; a.bases = bases; a.n = n; a.c = s.c; a.nwin = s.nwin; a.log_t = s.log_t;
+    a.counts = counts.data(); a.offsets = offsets.data(); a.cursor = cursor.data(); a.entries = entries.data();
+    a.buckets = buckets.data(); a.partials = partials.data(); a.window_sums = wsum.data();
+    for (uint32_t i = 0; i < n; ++i) msm_count_thread(a, i);
+    std::vector<uint32_t> sm(65);
+    msm_scan_block(a, 64, sm.data());
+    for (uint32_t i = 0; i < n; ++i) msm_scatter_thread(a, i);
+    for (uint32_t k = 0; k < s.nbuckets; ++k) msm_accumulate_thread(a, k);
+    for (uint32_t g = 0; g < (s.nwin << s.log_t); ++g) msm_reduce_thread(a, g);
+    std::vector<xyzz_t> smx(8);
+    for (uint32_t j = 0; j < s.nwin; ++j) msm_fold_block(a, j, 8, smx.data());
+    host::HAffine r = msm_finish(wsum.data(), s.nwin, s.c);
+    memcpy(out_affine64, &r, 64);
+}
+
+// host field self-check hooks: op 0 add 1 sub 2 mul 3 inv ; which 0 Fr 1 Fq
+void emu_host_field_op(int which, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    using namespace host;
+    for (size_t i = 0; i < n; ++i) {
+        if (which == 0) {
+            HFr x = HFr::from_limbs(a + 4 * i), y = HFr::from_limbs(b + 4 * i);
+            HFr r = op == 0 ? x + y : op == 1 ? x - y : op == 2 ? x * y : x.inv();
+            r.store(out + 4 * i);
+        } else {
+            HFq x = HFq::from_limbs(a + 4 * i), y = HFq::from_limbs(b + 4 * i);
+            HFq r = op == 0 ? x + y : op == 1 ? x - y : op == 2 ? x * y : x.inv();
+            r.store(out + 4 * i);
+        }
+    }
+}
+void emu_host_fr_consts(uint64_t* root, uint64_t* zeta, uint64_t* delta, uint64_t* wide_in8, uint64_t* wide_out) {
+    host::fr_root_of_unity().store(root); host::fr_zeta().store(zeta); host::fr_delta().store(delta);
+    host::HFr::from_u512(wide_in8).store(wide_out);
+}
+
+}  // extern "C"

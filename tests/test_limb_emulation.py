@@ -1,0 +1,123 @@
+"""Checks the product's 8x32-bit limb algorithms and kernel index logic, compiled for the
+host with the PTX carry flag / block phases emulated, against the CPU oracle.  CPU only."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import pyref as P
+from tests.emu import binding as emu
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_field_limbs_match_oracle(orc, which):
+    p = P.R_MOD if which == 0 else P.Q_MOD
+    rnd = random.Random(10 + which)
+    edge = [0, 1, 2, p - 1, p - 2, p >> 1, (1 << 253) % p, (1 << 32) - 1, (1 << 64) - 1, 1 << 224]
+    a = edge + [rnd.randrange(p) for _ in range(300)]
+    b = list(reversed(edge)) + [rnd.randrange(p) for _ in range(300)]
+    A, B = orc.ints_to_mont(a, which), orc.ints_to_mont(b, which)
+    one, r2 = emu.field_consts(which)
+    assert orc.mont_to_ints(one, which) == [1]
+    assert orc.raw_to_ints(r2) == orc.raw_to_ints(orc.field_params(which)["r2"])
+    for op in ("add", "sub", "mul"):
+        assert np.array_equal(emu.field_op(which, op, A, B), orc.binop(op, A, B, which)), op
+    assert np.array_equal(emu.field_op(which, "sqr", A), orc.binop("mul", A, A, which))
+    assert np.array_equal(emu.field_op(which, "from_mont", A), orc.to_raw(A, which))
+    assert np.array_equal(emu.field_op(which, "to_mont", orc.ints_to_raw(a)), A)
+    nz = orc.ints_to_mont([x for x in a[:40] if x], which)
+    assert np.array_equal(emu.field_op(which, "inv", nz), orc.inv(nz, which))
+    # worst-case carries: all limbs 0xffffffff is not a field element, but p-1 squared etc. are
+    m = orc.ints_to_mont([p - 1] * 4, which)
+    assert orc.mont_to_ints(emu.field_op(which, "mul", m, m), which) == [1] * 4
+
+
+@pytest.mark.parametrize("log_n,max_log_m,max_log_tw,cap", [
+    (0, 10, 2, 12), (1, 10, 2, 12), (3, 10, 2, 12), (6, 10, 2, 12),      # single pass
+    (6, 3, 1, 12), (7, 4, 2, 12), (8, 4, 3, 5),                           # two passes, tile cap binding
+    (6, 2, 1, 12), (9, 3, 2, 12), (8, 3, 0, 12), (10, 4, 2, 5),          # three passes
+])
+def test_ntt_pass_structure(orc, log_n, max_log_m, max_log_tw, cap):
+    rnd = random.Random(100 + log_n)
+    n = 1 << log_n
+    a = orc.ints_to_mont([rnd.randrange(P.R_MOD) for _ in range(n)])
+    w = orc.ints_to_mont([P.omega_for_k(log_n)])[0]
+    got = emu.ntt(a, log_n, w, max_log_m=max_log_m, max_log_tw=max_log_tw, tile_cap_log=cap, nthreads=7)
+    assert np.array_equal(got, orc.best_fft(a, w, log_n))
+
+
+def test_ntt_fused_domain_hooks(orc):
+    """coeff_to_extended / extended_to_coeff / lagrange_to_coeff as pre/post hooks."""
+    rnd = random.Random(77)
+    k, j = 5, 6
+    d = orc.Domain(j, k)
+    n, ext_k = 1 << k, d.extended_k
+    a = orc.ints_to_mont([rnd.randrange(P.R_MOD) for _ in range(n)])
+    one = orc.ints_to_mont([1])[0]
+    # lagrange_to_coeff: iNTT with post = ifft_divisor
+    post = np.stack([d.ifft_divisor] * 3)
+    got = emu.ntt(a, k, d.omega_inv, max_log_m=3, max_log_tw=1, post=post)
+    coeff = d.lagrange_to_coeff(a)
+    assert np.array_equal(got, coeff)
+    # coeff_to_extended: pre = [1, zeta, zeta^2], zero padded
+    pre = np.stack([one, d.g_coset, d.g_coset_inv])
+    ext = emu.ntt(coeff, ext_k, d.extended_omega, n_in=n, max_log_m=3, max_log_tw=2, pre=pre)
+    assert np.array_equal(ext, d.coeff_to_extended(coeff))
+    # extended_to_coeff: post = ext^-1 * [1, zeta^-1, zeta^-2] = ext^-1 * [1, zeta^2, zeta]
+    div = d.extended_ifft_divisor
+    post = np.stack([div, orc.binop("mul", div, d.g_coset_inv)[0], orc.binop("mul", div, d.g_coset)[0]])
+    back = emu.ntt(ext, ext_k, d.extended_omega_inv, max_log_m=4, max_log_tw=2, post=post)
+    assert np.array_equal(back[: n * (j - 1)], d.extended_to_coeff(ext))
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_host_field_matches_oracle(orc, which):
+    p = P.R_MOD if which == 0 else P.Q_MOD
+    rnd = random.Random(20 + which)
+    a = [0, 1, p - 1, p - 2] + [rnd.randrange(p) for _ in range(200)]
+    b = [p - 1, 0, p - 1, 1] + [rnd.randrange(p) for _ in range(200)]
+    A, B = orc.ints_to_mont(a, which), orc.ints_to_mont(b, which)
+    for op in ("add", "sub", "mul"):
+        assert np.array_equal(emu.host_field_op(which, op, A, B), orc.binop(op, A, B, which)), op
+    nz = orc.ints_to_mont([x for x in a[:30] if x], which)
+    assert np.array_equal(emu.host_field_op(which, "inv", nz), orc.inv(nz, which))
+
+
+def test_host_fr_constants(orc):
+    wide = np.arange(1, 9, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    r, z, d, w = emu.host_fr_consts(wide)
+    R, D, Z = orc.fr_constants()
+    assert np.array_equal(r, R) and np.array_equal(z, Z) and np.array_equal(d, D)
+    assert np.array_equal(w, orc.from_u512(wide.reshape(1, 8))[0])
+
+
+@pytest.mark.parametrize("n,c", [(1, 0), (2, 0), (37, 4), (200, 0), (200, 7), (64, 16), (300, 5)])
+def test_msm_pipeline_structure(orc, n, c):
+    rnd = random.Random(200 + n + c)
+    ks = [rnd.randrange(P.R_MOD) for _ in range(n)]
+    ss = [rnd.randrange(P.R_MOD) for _ in range(n)]
+    if n >= 37:
+        ss[0], ss[1], ss[2], ss[3] = 0, 1, P.R_MOD - 1, (1 << 253)       # edge scalars
+        ks[5] = ks[4]                                                     # repeated base (P + P inside a bucket)
+        ss[5] = ss[4]
+        ks[7] = P.R_MOD - ks[6]                                           # P + (-P)
+        ss[7] = ss[6]
+    bases = orc.g1_fixed_base_mul(orc.ints_to_mont(ks))
+    if n >= 37:
+        bases[9] = 0                                                      # identity base
+    S = orc.ints_to_mont(ss)
+    got = emu.msm(S, bases, c)
+    want = orc.g1_batch_normalize(orc.best_multiexp(S, bases))[0]
+    assert np.array_equal(got, want)
+
+
+def test_msm_all_same_small_scalars(orc):
+    """Skewed digit distribution: every point lands in one bucket."""
+    n = 100
+    ks = list(range(1, n + 1))
+    bases = orc.g1_fixed_base_mul(orc.ints_to_mont(ks))
+    for s in (1, 3, 255):
+        S = orc.ints_to_mont([s] * n)
+        assert np.array_equal(emu.msm(S, bases, 6), orc.g1_batch_normalize(orc.best_multiexp(S, bases))[0])
+    Z = orc.ints_to_mont([0] * n)
+    assert np.array_equal(emu.msm(Z, bases, 0), np.zeros(8, dtype=np.uint64))
