@@ -1,0 +1,286 @@
+"""Host-side mirror of the halo2_proofs back-end interface over libb200zk.so (ctypes).
+
+Names and argument meaning follow halo2_proofs v2023_02_02 (the crate the reference
+pins at /root/reference/Cargo.toml:10 and calls from
+/root/reference/src/circuits/utils.rs:22-70):
+
+    best_multiexp(coeffs, bases) -> G1            arithmetic.rs
+    best_fft(a, omega, log_n)                     arithmetic.rs
+    EvaluationDomain(j, k).lagrange_to_coeff / coeff_to_extended /
+        extended_to_coeff / divide_by_vanishing_poly      poly/domain.rs
+    ParamsKZG.load / setup, .commit, .commit_lagrange      poly/kzg/commitment.rs
+
+Arrays are numpy uint64, shape (n, 4) for Fr (Montgomery limbs, the memory layout of
+halo2curves' Fr), (n, 8) for G1Affine, (12,) for a G1 result.  Everything computes on
+the GPU through the C ABI declared in include/b200zk.h; there is no CPU fallback —
+importing works anywhere, but creating a Backend without a CUDA device raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200zk.so")
+
+OK, EINVAL, ENODEV, ECUDA, ENOMEM = 0, -1, -2, -3, -4
+
+
+class B200zkError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libb200zk.so (fails loudly if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200zkError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = ctypes.CDLL(LIB_PATH)
+        L.b200zk_last_error.restype = ctypes.c_char_p
+        L.b200zk_launch_count.restype = ctypes.c_uint64
+        L.b200zk_domain_k.restype = ctypes.c_uint32
+        L.b200zk_domain_extended_k.restype = ctypes.c_uint32
+        L.b200zk_domain_quotient_poly_degree.restype = ctypes.c_uint32
+        L.b200zk_domain_destroy.restype = None
+        L.b200zk_params_destroy.restype = None
+        L.b200zk_ctx_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(ctypes.c_void_p)
+    return a
+
+
+def _fr(a, n=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    a = a.reshape(-1, 4)
+    if n is not None and a.shape[0] != n:
+        raise B200zkError(f"expected {n} field elements, got {a.shape[0]}")
+    return a
+
+
+class DeviceBuffer:
+    """Device memory owned by a Backend (b200zk_malloc)."""
+
+    def __init__(self, backend, nbytes):
+        self.backend, self.nbytes = backend, int(nbytes)
+        ptr = ctypes.c_void_p()
+        backend._check(lib().b200zk_malloc(backend._ctx, ctypes.c_size_t(self.nbytes), ctypes.byref(ptr)))
+        self.ptr = ptr
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        self.backend._check(lib().b200zk_upload(self.backend._ctx, self.ptr, _p(arr), ctypes.c_size_t(arr.nbytes)))
+        return self
+
+    def download(self, shape, dtype=np.uint64):
+        out = np.empty(shape, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        self.backend._check(lib().b200zk_download(self.backend._ctx, _p(out), self.ptr, ctypes.c_size_t(out.nbytes)))
+        return out
+
+    def free(self):
+        if self.ptr is not None:
+            lib().b200zk_free(self.backend._ctx, self.ptr)
+            self.ptr = None
+
+
+class Backend:
+    """One CUDA device + stream + scratch (b200zk_ctx)."""
+
+    def __init__(self, device=0):
+        self._ctx = ctypes.c_void_p()
+        rc = lib().b200zk_ctx_create(ctypes.c_int32(device), ctypes.byref(self._ctx))
+        if rc != OK:
+            self._ctx = None
+            raise B200zkError(f"b200zk_ctx_create(device={device}) failed with code {rc}: no usable sm_100 CUDA device "
+                              "(this backend has no CPU fallback)")
+
+    def close(self):
+        if self._ctx:
+            lib().b200zk_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def _check(self, rc):
+        if rc != OK:
+            raise B200zkError(f"b200zk error {rc}: {lib().b200zk_last_error(self._ctx).decode()}")
+
+    # -- plumbing --
+    def sync(self):
+        self._check(lib().b200zk_sync(self._ctx))
+
+    def launch_count(self):
+        return int(lib().b200zk_launch_count(self._ctx))
+
+    def event_record(self, slot):
+        self._check(lib().b200zk_event_record(self._ctx, ctypes.c_uint32(slot)))
+
+    def event_elapsed_ms(self, a, b):
+        ms = ctypes.c_float()
+        self._check(lib().b200zk_event_elapsed_ms(self._ctx, ctypes.c_uint32(a), ctypes.c_uint32(b), ctypes.byref(ms)))
+        return float(ms.value)
+
+    def alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        return DeviceBuffer(self, arr.nbytes).upload(arr)
+
+    def pinned_empty(self, shape, dtype=np.uint64):
+        """numpy view over cudaHostAlloc'ed memory (kept alive by the returned array's base)."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = ctypes.c_void_p()
+        self._check(lib().b200zk_host_alloc(self._ctx, ctypes.c_size_t(nbytes), ctypes.byref(ptr)))
+        buf = (ctypes.c_uint8 * nbytes).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def set_msm_window(self, c):
+        self._check(lib().b200zk_msm_set_window(self._ctx, ctypes.c_int32(c)))
+
+    # -- arithmetic.rs --
+    def best_multiexp(self, coeffs, bases):
+        """sum coeffs[i] * bases[i]; panics upstream on length mismatch -> raises here."""
+        coeffs = _fr(coeffs)
+        bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+        if coeffs.shape[0] != bases.shape[0]:
+            raise B200zkError("best_multiexp: coeffs.len() != bases.len()")
+        out = np.zeros(12, dtype=np.uint64)
+        self._check(lib().b200zk_msm(self._ctx, _p(coeffs), _p(bases), ctypes.c_size_t(coeffs.shape[0]), _p(out)))
+        return out
+
+    def best_multiexp_dev(self, d_coeffs, d_bases, n):
+        out = np.zeros(12, dtype=np.uint64)
+        self._check(lib().b200zk_msm_dev(self._ctx, d_coeffs.ptr, d_bases.ptr, ctypes.c_size_t(n), _p(out)))
+        return out
+
+    def best_fft(self, a, omega, log_n):
+        """In-place on a copy; returns the transformed array (natural order, unscaled)."""
+        a = np.array(_fr(a, 1 << log_n))
+        self._check(lib().b200zk_fft(self._ctx, _p(a), _p(_fr(omega, 1)), ctypes.c_uint32(log_n)))
+        return a
+
+    def best_fft_dev(self, d_a, omega, log_n):
+        self._check(lib().b200zk_fft_dev(self._ctx, d_a.ptr, _p(_fr(omega, 1)), ctypes.c_uint32(log_n)))
+
+
+class EvaluationDomain:
+    """poly::EvaluationDomain<Fr>::new(j, k) on a Backend."""
+    _CONSTS = ["omega", "omega_inv", "extended_omega", "extended_omega_inv", "g_coset", "g_coset_inv",
+               "ifft_divisor", "extended_ifft_divisor", "barycentric_weight"]
+
+    def __init__(self, backend, j, k):
+        self.backend = backend
+        self._h = ctypes.c_void_p()
+        backend._check(lib().b200zk_domain_create(backend._ctx, ctypes.c_uint32(j), ctypes.c_uint32(k), ctypes.byref(self._h)))
+        self.k = int(lib().b200zk_domain_k(self._h))
+        self.n = 1 << self.k
+        self.extended_k = int(lib().b200zk_domain_extended_k(self._h))
+        self.quotient_poly_degree = int(lib().b200zk_domain_quotient_poly_degree(self._h))
+        for i, name in enumerate(self._CONSTS):
+            v = np.zeros(4, dtype=np.uint64)
+            backend._check(lib().b200zk_domain_constant(self._h, ctypes.c_uint32(i), _p(v)))
+            setattr(self, name, v)
+
+    def close(self):
+        if self._h:
+            lib().b200zk_domain_destroy(self._h)
+            self._h = None
+
+    def extended_len(self):
+        return 1 << self.extended_k
+
+    def lagrange_to_coeff(self, a):
+        a = np.array(_fr(a, self.n))
+        self.backend._check(lib().b200zk_lagrange_to_coeff(self._h, _p(a)))
+        return a
+
+    def coeff_to_extended(self, a):
+        a = _fr(a, self.n)
+        out = np.empty((self.extended_len(), 4), dtype=np.uint64)
+        self.backend._check(lib().b200zk_coeff_to_extended(self._h, _p(a), _p(out)))
+        return out
+
+    def extended_to_coeff(self, a):
+        a = _fr(a, self.extended_len())
+        out = np.empty((self.n * self.quotient_poly_degree, 4), dtype=np.uint64)
+        self.backend._check(lib().b200zk_extended_to_coeff(self._h, _p(a), _p(out)))
+        return out
+
+    def divide_by_vanishing_poly(self, a):
+        a = np.array(_fr(a, self.extended_len()))
+        self.backend._check(lib().b200zk_divide_by_vanishing_poly(self._h, _p(a)))
+        return a
+
+    # device-resident variants (DeviceBuffer in, DeviceBuffer out)
+    def lagrange_to_coeff_dev(self, d_a):
+        self.backend._check(lib().b200zk_lagrange_to_coeff_dev(self._h, d_a.ptr))
+
+    def coeff_to_extended_dev(self, d_coeffs, d_out):
+        self.backend._check(lib().b200zk_coeff_to_extended_dev(self._h, d_coeffs.ptr, d_out.ptr))
+
+    def extended_to_coeff_dev(self, d_ext, d_out):
+        self.backend._check(lib().b200zk_extended_to_coeff_dev(self._h, d_ext.ptr, d_out.ptr))
+
+    def divide_by_vanishing_poly_dev(self, d_ext):
+        self.backend._check(lib().b200zk_divide_by_vanishing_poly_dev(self._h, d_ext.ptr))
+
+
+class ParamsKZG:
+    """poly::kzg::commitment::ParamsKZG<Bn256> with the SRS resident in HBM."""
+
+    def __init__(self, backend, handle, k):
+        self.backend, self._h, self.k, self.n = backend, handle, k, 1 << k
+
+    @classmethod
+    def load(cls, backend, k, g, g_lagrange=None):
+        g = np.ascontiguousarray(g, dtype=np.uint64).reshape(1 << k, 8)
+        gl = None if g_lagrange is None else np.ascontiguousarray(g_lagrange, dtype=np.uint64).reshape(1 << k, 8)
+        h = ctypes.c_void_p()
+        backend._check(lib().b200zk_params_load(backend._ctx, ctypes.c_uint32(k), _p(g), _p(gl), ctypes.byref(h)))
+        return cls(backend, h, k)
+
+    @classmethod
+    def setup(cls, backend, k, s):
+        """ParamsKZG::setup(k, rng) with s = Fr::random(rng) drawn by the caller."""
+        h = ctypes.c_void_p()
+        backend._check(lib().b200zk_params_setup(backend._ctx, ctypes.c_uint32(k), _p(_fr(s, 1)), ctypes.byref(h)))
+        return cls(backend, h, k)
+
+    def close(self):
+        if self._h:
+            lib().b200zk_params_destroy(self._h)
+            self._h = None
+
+    def read(self, lagrange=True):
+        g = np.empty((self.n, 8), dtype=np.uint64)
+        gl = np.empty((self.n, 8), dtype=np.uint64) if lagrange else None
+        self.backend._check(lib().b200zk_params_read(self._h, _p(g), _p(gl)))
+        return g, gl
+
+    def commit(self, poly):
+        poly = _fr(poly)
+        out = np.zeros(12, dtype=np.uint64)
+        self.backend._check(lib().b200zk_commit(self._h, _p(poly), ctypes.c_size_t(poly.shape[0]), _p(out)))
+        return out
+
+    def commit_lagrange(self, poly):
+        poly = _fr(poly)
+        out = np.zeros(12, dtype=np.uint64)
+        self.backend._check(lib().b200zk_commit_lagrange(self._h, _p(poly), ctypes.c_size_t(poly.shape[0]), _p(out)))
+        return out
+
+    def commit_dev(self, d_poly, n, lagrange):
+        out = np.zeros(12, dtype=np.uint64)
+        self.backend._check(lib().b200zk_commit_dev(self._h, d_poly.ptr, ctypes.c_size_t(n), ctypes.c_int32(1 if lagrange else 0), _p(out)))
+        return out

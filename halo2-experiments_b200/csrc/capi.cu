@@ -1,0 +1,410 @@
+// C ABI of libb200zk.so (declarations and reference mapping: include/b200zk.h).
+#include "context.hpp"
+#include <new>
+
+using namespace b200zk;
+using host::HFr;
+using host::HFq;
+
+namespace b200zk {
+
+int32_t fail(b200zk_ctx* ctx, int32_t code, const char* what, const char* detail) {
+    if (ctx) {
+        ctx->err = std::string(what) + ": " + (detail ? detail : "");
+    }
+    return code;
+}
+
+int32_t ws_reserve(b200zk_ctx* ctx, Workspace& w, size_t bytes) {
+    if (bytes <= w.cap) return B200ZK_OK;
+    if (w.p) { ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ZK_CUDA(ctx, cudaFree(w.p)); w.p = nullptr; w.cap = 0; }
+    size_t cap = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&w.p, cap);
+    if (e != cudaSuccess) { cap = bytes; e = cudaMalloc(&w.p, cap); }
+    if (e != cudaSuccess) { w.p = nullptr; return fail(ctx, B200ZK_ENOMEM, "cudaMalloc(workspace)", cudaGetErrorString(e)); }
+    w.cap = cap;
+    return B200ZK_OK;
+}
+
+}  // namespace b200zk
+
+struct b200zk_domain {
+    b200zk_ctx* ctx;
+    uint32_t k, extended_k, quotient_poly_degree;
+    HFr omega, omega_inv, extended_omega, extended_omega_inv, g_coset, g_coset_inv;
+    HFr ifft_divisor, extended_ifft_divisor, barycentric_weight;
+    fe_t* d_t_evaluations;           // 2^(extended_k - k), already inverted
+};
+
+struct b200zk_params {
+    b200zk_ctx* ctx;
+    uint32_t k;
+    affine_t* d_g;
+    affine_t* d_g_lagrange;
+};
+
+static void write_g1(const host::HAffine& a, void* out_g1) {
+    uint64_t* o = (uint64_t*)out_g1;
+    if (a.x.is_zero() && a.y.is_zero()) {           // G1::identity() = (0, 1, 0)
+        memset(o, 0, 96);
+        HFq::one().store(o + 4);
+        return;
+    }
+    a.x.store(o); a.y.store(o + 4); HFq::one().store(o + 8);
+}
+
+extern "C" {
+
+int32_t b200zk_ctx_create(int32_t device, b200zk_ctx** out) {
+    if (!out) return B200ZK_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return B200ZK_ENODEV;
+    if (cudaSetDevice(device) != cudaSuccess) return B200ZK_ENODEV;
+    b200zk_ctx* ctx = new (std::nothrow) b200zk_ctx();
+    if (!ctx) return B200ZK_ENOMEM;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return B200ZK_ENODEV; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) { delete ctx; return B200ZK_ENODEV; }     // sm_100a code only
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200ZK_ECUDA; }
+    for (auto& e : ctx->events) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return B200ZK_ECUDA; }
+    if (cudaHostAlloc(&ctx->pinned, 1 << 16, cudaHostAllocDefault) != cudaSuccess) { delete ctx; return B200ZK_ECUDA; }
+    *out = ctx;
+    return B200ZK_OK;
+}
+
+void b200zk_ctx_destroy(b200zk_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->ntt_plans) { cudaFree(kv.second.roots); cudaFree(kv.second.tw_lo); cudaFree(kv.second.tw_hi); }
+    for (Workspace* w : {&ctx->ntt_scratch, &ctx->msm_ws, &ctx->io_a, &ctx->io_b}) if (w->p) cudaFree(w->p);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto& e : ctx->events) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* b200zk_last_error(const b200zk_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int32_t b200zk_sync(b200zk_ctx* ctx) {
+    if (!ctx) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+uint64_t b200zk_launch_count(const b200zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t b200zk_event_record(b200zk_ctx* ctx, uint32_t slot) {
+    if (!ctx || slot >= 64) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaEventRecord(ctx->events[slot], ctx->stream));
+    return B200ZK_OK;
+}
+
+int32_t b200zk_event_elapsed_ms(b200zk_ctx* ctx, uint32_t from_slot, uint32_t to_slot, float* ms) {
+    if (!ctx || from_slot >= 64 || to_slot >= 64 || !ms) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaEventSynchronize(ctx->events[to_slot]));
+    ZK_CUDA(ctx, cudaEventElapsedTime(ms, ctx->events[from_slot], ctx->events[to_slot]));
+    return B200ZK_OK;
+}
+
+// ---- memory ------------------------------------------------------------------
+int32_t b200zk_malloc(b200zk_ctx* ctx, size_t bytes, void** dptr) {
+    if (!ctx || !dptr) return B200ZK_EINVAL;
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(ctx, B200ZK_ENOMEM, "cudaMalloc", cudaGetErrorString(e));
+    return B200ZK_OK;
+}
+int32_t b200zk_free(b200zk_ctx* ctx, void* dptr) {
+    if (!ctx) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, cudaFree(dptr));
+    return B200ZK_OK;
+}
+int32_t b200zk_upload(b200zk_ctx* ctx, void* dptr, const void* hostp, size_t bytes) {
+    if (!ctx) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaMemcpyAsync(dptr, hostp, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+int32_t b200zk_download(b200zk_ctx* ctx, void* hostp, const void* dptr, size_t bytes) {
+    if (!ctx) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaMemcpyAsync(hostp, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+int32_t b200zk_memset_zero(b200zk_ctx* ctx, void* dptr, size_t bytes) {
+    if (!ctx) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaMemsetAsync(dptr, 0, bytes, ctx->stream));
+    return B200ZK_OK;
+}
+int32_t b200zk_host_alloc(b200zk_ctx* ctx, size_t bytes, void** hptr) {
+    if (!ctx || !hptr) return B200ZK_EINVAL;
+    cudaError_t e = cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(ctx, B200ZK_ENOMEM, "cudaHostAlloc", cudaGetErrorString(e));
+    return B200ZK_OK;
+}
+int32_t b200zk_host_free(b200zk_ctx* ctx, void* hptr) {
+    if (!ctx) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaFreeHost(hptr));
+    return B200ZK_OK;
+}
+
+// ---- best_multiexp --------------------------------------------------------------
+int32_t b200zk_msm_set_window(b200zk_ctx* ctx, int32_t c) {
+    if (!ctx || c < 0 || c > 20 || c == 1) return B200ZK_EINVAL;
+    ctx->msm_force_c = c;
+    return B200ZK_OK;
+}
+
+int32_t b200zk_msm_dev(b200zk_ctx* ctx, const void* d_coeffs, const void* d_bases, size_t len, void* out_g1_host) {
+    if (!ctx || !out_g1_host || (len && (!d_coeffs || !d_bases))) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    host::HAffine r;
+    ZK_TRY(msm_run(ctx, (const fe_t*)d_coeffs, (const affine_t*)d_bases, len, &r));
+    write_g1(r, out_g1_host);
+    return B200ZK_OK;
+}
+
+int32_t b200zk_msm(b200zk_ctx* ctx, const void* coeffs, const void* bases, size_t len, void* out_g1) {
+    if (!ctx || !out_g1 || (len && (!coeffs || !bases))) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZK_TRY(ws_reserve(ctx, ctx->io_a, len * sizeof(fe_t)));
+    ZK_TRY(ws_reserve(ctx, ctx->io_b, len * sizeof(affine_t)));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, coeffs, len * sizeof(fe_t), cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->io_b.p, bases, len * sizeof(affine_t), cudaMemcpyHostToDevice, ctx->stream));
+    return b200zk_msm_dev(ctx, ctx->io_a.p, ctx->io_b.p, len, out_g1);
+}
+
+// ---- best_fft ---------------------------------------------------------------------
+int32_t b200zk_fft_dev(b200zk_ctx* ctx, void* d_a, const void* omega_host, uint32_t log_n) {
+    if (!ctx || !d_a || !omega_host || log_n > 30) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    HFr omega = HFr::from_limbs(omega_host);
+    return ntt_run(ctx, (const fe_t*)d_a, 1u << log_n, (fe_t*)d_a, log_n, omega, nullptr, nullptr);
+}
+
+int32_t b200zk_fft(b200zk_ctx* ctx, void* a, const void* omega, uint32_t log_n) {
+    if (!ctx || !a || !omega || log_n > 30) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t bytes = sizeof(fe_t) << log_n;
+    ZK_TRY(ws_reserve(ctx, ctx->io_a, bytes));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_TRY(b200zk_fft_dev(ctx, ctx->io_a.p, omega, log_n));
+    ZK_CUDA(ctx, cudaMemcpyAsync(a, ctx->io_a.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+// ---- EvaluationDomain ---------------------------------------------------------------
+int32_t b200zk_domain_create(b200zk_ctx* ctx, uint32_t j, uint32_t k, b200zk_domain** out) {
+    if (!ctx || !out || j < 2 || k > host::FR_TWO_ADICITY) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    b200zk_domain* d = new (std::nothrow) b200zk_domain();
+    if (!d) return B200ZK_ENOMEM;
+    d->ctx = ctx; d->k = k;
+    d->quotient_poly_degree = j - 1;
+    uint64_t n = 1ull << k;
+    d->extended_k = k;
+    while ((1ull << d->extended_k) < n * d->quotient_poly_degree) d->extended_k++;
+    if (d->extended_k > host::FR_TWO_ADICITY) { delete d; return fail(ctx, B200ZK_EINVAL, "domain_create", "extended_k exceeds Fr two-adicity"); }
+    d->extended_omega = host::fr_root_of_unity();
+    for (uint32_t i = d->extended_k; i < host::FR_TWO_ADICITY; ++i) d->extended_omega = d->extended_omega.sqr();
+    d->omega = d->extended_omega;
+    for (uint32_t i = k; i < d->extended_k; ++i) d->omega = d->omega.sqr();
+    d->omega_inv = d->omega.inv();
+    d->extended_omega_inv = d->extended_omega.inv();
+    d->g_coset = host::fr_zeta();
+    d->g_coset_inv = d->g_coset.sqr();
+    d->ifft_divisor = HFr::from_u64(n).inv();
+    d->extended_ifft_divisor = HFr::from_u64(1ull << d->extended_k).inv();
+    d->barycentric_weight = d->ifft_divisor;
+    // t_evaluations[i] = 1 / (zeta^n * (extended_omega^n)^i - 1)
+    size_t m = (size_t)1 << (d->extended_k - k);
+    std::vector<HFr> t(m);
+    HFr cur = d->g_coset.pow_u64(n), step = d->extended_omega.pow_u64(n);
+    for (size_t i = 0; i < m; ++i) { t[i] = (cur - HFr::one()).inv(); cur = cur * step; }
+    cudaError_t e = cudaMalloc(&d->d_t_evaluations, m * sizeof(fe_t));
+    if (e != cudaSuccess) { delete d; return fail(ctx, B200ZK_ENOMEM, "cudaMalloc", cudaGetErrorString(e)); }
+    e = cudaMemcpy(d->d_t_evaluations, t.data(), m * sizeof(fe_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d->d_t_evaluations); delete d; return fail(ctx, B200ZK_ECUDA, "cudaMemcpy", cudaGetErrorString(e)); }
+    *out = d;
+    return B200ZK_OK;
+}
+
+void b200zk_domain_destroy(b200zk_domain* d) {
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    cudaStreamSynchronize(d->ctx->stream);
+    cudaFree(d->d_t_evaluations);
+    delete d;
+}
+
+uint32_t b200zk_domain_k(const b200zk_domain* d) { return d ? d->k : 0; }
+uint32_t b200zk_domain_extended_k(const b200zk_domain* d) { return d ? d->extended_k : 0; }
+uint32_t b200zk_domain_quotient_poly_degree(const b200zk_domain* d) { return d ? d->quotient_poly_degree : 0; }
+
+int32_t b200zk_domain_constant(const b200zk_domain* d, uint32_t which, void* out_fr) {
+    if (!d || !out_fr || which > 8) return B200ZK_EINVAL;
+    const HFr* f[] = {&d->omega, &d->omega_inv, &d->extended_omega, &d->extended_omega_inv, &d->g_coset, &d->g_coset_inv,
+                      &d->ifft_divisor, &d->extended_ifft_divisor, &d->barycentric_weight};
+    f[which]->store(out_fr);
+    return B200ZK_OK;
+}
+
+int32_t b200zk_lagrange_to_coeff_dev(b200zk_domain* d, void* d_a) {
+    if (!d || !d_a) return B200ZK_EINVAL;
+    ZK_CUDA(d->ctx, cudaSetDevice(d->ctx->device));
+    HFr post[3] = {d->ifft_divisor, d->ifft_divisor, d->ifft_divisor};
+    return ntt_run(d->ctx, (const fe_t*)d_a, 1u << d->k, (fe_t*)d_a, d->k, d->omega_inv, nullptr, post);
+}
+
+int32_t b200zk_coeff_to_extended_dev(b200zk_domain* d, const void* d_coeffs, void* d_out_ext) {
+    if (!d || !d_coeffs || !d_out_ext) return B200ZK_EINVAL;
+    ZK_CUDA(d->ctx, cudaSetDevice(d->ctx->device));
+    HFr pre[3] = {HFr::one(), d->g_coset, d->g_coset_inv};
+    return ntt_run(d->ctx, (const fe_t*)d_coeffs, 1u << d->k, (fe_t*)d_out_ext, d->extended_k, d->extended_omega, pre, nullptr);
+}
+
+int32_t b200zk_extended_to_coeff_dev(b200zk_domain* d, void* d_ext, void* d_out_coeffs) {
+    if (!d || !d_ext || !d_out_coeffs) return B200ZK_EINVAL;
+    b200zk_ctx* ctx = d->ctx;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    HFr dv = d->extended_ifft_divisor;
+    HFr post[3] = {dv, dv * d->g_coset_inv, dv * d->g_coset};
+    ZK_TRY(ntt_run(ctx, (const fe_t*)d_ext, 1u << d->extended_k, (fe_t*)d_ext, d->extended_k, d->extended_omega_inv, nullptr, post));
+    size_t bytes = (sizeof(fe_t) << d->k) * d->quotient_poly_degree;
+    if (d_out_coeffs != d_ext) ZK_CUDA(ctx, cudaMemcpyAsync(d_out_coeffs, d_ext, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return B200ZK_OK;
+}
+
+int32_t b200zk_divide_by_vanishing_poly_dev(b200zk_domain* d, void* d_ext) {
+    if (!d || !d_ext) return B200ZK_EINVAL;
+    ZK_CUDA(d->ctx, cudaSetDevice(d->ctx->device));
+    return fr_scale_periodic(d->ctx, (fe_t*)d_ext, (size_t)1 << d->extended_k, d->d_t_evaluations, 1u << (d->extended_k - d->k));
+}
+
+int32_t b200zk_lagrange_to_coeff(b200zk_domain* d, void* a) {
+    if (!d || !a) return B200ZK_EINVAL;
+    b200zk_ctx* ctx = d->ctx;
+    size_t bytes = sizeof(fe_t) << d->k;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZK_TRY(ws_reserve(ctx, ctx->io_a, bytes));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_TRY(b200zk_lagrange_to_coeff_dev(d, ctx->io_a.p));
+    ZK_CUDA(ctx, cudaMemcpyAsync(a, ctx->io_a.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+int32_t b200zk_coeff_to_extended(b200zk_domain* d, const void* coeffs, void* out_ext) {
+    if (!d || !coeffs || !out_ext) return B200ZK_EINVAL;
+    b200zk_ctx* ctx = d->ctx;
+    size_t in_bytes = sizeof(fe_t) << d->k, out_bytes = sizeof(fe_t) << d->extended_k;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZK_TRY(ws_reserve(ctx, ctx->io_a, in_bytes));
+    ZK_TRY(ws_reserve(ctx, ctx->io_b, out_bytes));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, coeffs, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_TRY(b200zk_coeff_to_extended_dev(d, ctx->io_a.p, ctx->io_b.p));
+    ZK_CUDA(ctx, cudaMemcpyAsync(out_ext, ctx->io_b.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+int32_t b200zk_extended_to_coeff(b200zk_domain* d, const void* ext, void* out_coeffs) {
+    if (!d || !ext || !out_coeffs) return B200ZK_EINVAL;
+    b200zk_ctx* ctx = d->ctx;
+    size_t in_bytes = sizeof(fe_t) << d->extended_k, out_bytes = (sizeof(fe_t) << d->k) * d->quotient_poly_degree;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZK_TRY(ws_reserve(ctx, ctx->io_b, in_bytes));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->io_b.p, ext, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_TRY(b200zk_extended_to_coeff_dev(d, ctx->io_b.p, ctx->io_b.p));
+    ZK_CUDA(ctx, cudaMemcpyAsync(out_coeffs, ctx->io_b.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+int32_t b200zk_divide_by_vanishing_poly(b200zk_domain* d, void* ext) {
+    if (!d || !ext) return B200ZK_EINVAL;
+    b200zk_ctx* ctx = d->ctx;
+    size_t bytes = sizeof(fe_t) << d->extended_k;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZK_TRY(ws_reserve(ctx, ctx->io_b, bytes));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->io_b.p, ext, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_TRY(b200zk_divide_by_vanishing_poly_dev(d, ctx->io_b.p));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ext, ctx->io_b.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+// ---- ParamsKZG ------------------------------------------------------------------------
+int32_t b200zk_params_load(b200zk_ctx* ctx, uint32_t k, const void* g, const void* g_lagrange, b200zk_params** out) {
+    if (!ctx || !out || !g || k > host::FR_TWO_ADICITY) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    b200zk_params* p = new (std::nothrow) b200zk_params();
+    if (!p) return B200ZK_ENOMEM;
+    p->ctx = ctx; p->k = k; p->d_g = nullptr; p->d_g_lagrange = nullptr;
+    size_t bytes = sizeof(affine_t) << k;
+    cudaError_t e = cudaMalloc(&p->d_g, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_g, g, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && g_lagrange) {
+        e = cudaMalloc(&p->d_g_lagrange, bytes);
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_g_lagrange, g_lagrange, bytes, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(p->d_g); cudaFree(p->d_g_lagrange); delete p;
+        return fail(ctx, B200ZK_ECUDA, "params_load", cudaGetErrorString(e));
+    }
+    *out = p;
+    return B200ZK_OK;
+}
+
+void b200zk_params_destroy(b200zk_params* p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    cudaFree(p->d_g); cudaFree(p->d_g_lagrange);
+    delete p;
+}
+
+int32_t b200zk_params_read(b200zk_params* p, void* g_out, void* g_lagrange_out) {
+    if (!p) return B200ZK_EINVAL;
+    b200zk_ctx* ctx = p->ctx;
+    size_t bytes = sizeof(affine_t) << p->k;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (g_out) ZK_CUDA(ctx, cudaMemcpy(g_out, p->d_g, bytes, cudaMemcpyDeviceToHost));
+    if (g_lagrange_out) {
+        if (!p->d_g_lagrange) return fail(ctx, B200ZK_EINVAL, "params_read", "no lagrange basis loaded");
+        ZK_CUDA(ctx, cudaMemcpy(g_lagrange_out, p->d_g_lagrange, bytes, cudaMemcpyDeviceToHost));
+    }
+    return B200ZK_OK;
+}
+
+int32_t b200zk_commit_dev(b200zk_params* p, const void* d_poly, size_t len, int32_t lagrange, void* out_g1_host) {
+    if (!p || !out_g1_host || (len && !d_poly) || len > ((size_t)1 << p->k)) return B200ZK_EINVAL;
+    const affine_t* bases = lagrange ? p->d_g_lagrange : p->d_g;
+    if (!bases) return fail(p->ctx, B200ZK_EINVAL, "commit", "basis not loaded");
+    return b200zk_msm_dev(p->ctx, d_poly, bases, len, out_g1_host);
+}
+
+static int32_t commit_host(b200zk_params* p, const void* poly, size_t len, int32_t lagrange, void* out_g1) {
+    if (!p || !out_g1 || (len && !poly) || len > ((size_t)1 << p->k)) return B200ZK_EINVAL;
+    b200zk_ctx* ctx = p->ctx;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZK_TRY(ws_reserve(ctx, ctx->io_a, len * sizeof(fe_t)));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, poly, len * sizeof(fe_t), cudaMemcpyHostToDevice, ctx->stream));
+    return b200zk_commit_dev(p, ctx->io_a.p, len, lagrange, out_g1);
+}
+
+int32_t b200zk_commit(b200zk_params* p, const void* poly, size_t len, void* out_g1) { return commit_host(p, poly, len, 0, out_g1); }
+int32_t b200zk_commit_lagrange(b200zk_params* p, const void* poly, size_t len, void* out_g1) { return commit_host(p, poly, len, 1, out_g1); }
+
+int32_t b200zk_params_setup(b200zk_ctx* ctx, uint32_t k, const void* s_fr, b200zk_params** out) {
+    (void)k; (void)s_fr; (void)out;
+    return fail(ctx, B200ZK_EINVAL, "params_setup", "not built yet");
+}
+
+}  // extern "C"

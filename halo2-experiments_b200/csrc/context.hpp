@@ -1,0 +1,77 @@
+// Internal context shared by the translation units of libb200zk.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <array>
+#include <string>
+#include <vector>
+#include "../../include/b200zk.h"
+#include "host_field.hpp"
+#include "field.cuh"
+#include "curve.cuh"
+#include "ntt_plan.hpp"
+#include "msm_plan.hpp"
+
+namespace b200zk {
+
+struct NttPlan {
+    NttShape shape;
+    fe_t* roots = nullptr;
+    fe_t* tw_lo = nullptr;
+    fe_t* tw_hi = nullptr;
+};
+
+struct Workspace {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace b200zk
+
+struct b200zk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    cudaEvent_t events[64] = {};
+    int sm_count = 148;
+    int msm_force_c = 0;
+    std::map<std::array<uint64_t, 5>, b200zk::NttPlan> ntt_plans;     // key: log_n + omega limbs
+    b200zk::Workspace ntt_scratch, msm_ws, io_a, io_b;
+    void* pinned = nullptr;                                            // small pinned staging (results)
+};
+
+namespace b200zk {
+
+int32_t fail(b200zk_ctx* ctx, int32_t code, const char* what, const char* detail);
+
+#define ZK_CUDA(ctx, expr)                                                          \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) return fail((ctx), B200ZK_ECUDA, #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define ZK_TRY(expr)                      \
+    do {                                  \
+        int32_t _r = (expr);              \
+        if (_r != B200ZK_OK) return _r;   \
+    } while (0)
+
+// grow-only device workspace
+int32_t ws_reserve(b200zk_ctx* ctx, Workspace& w, size_t bytes);
+
+// ntt.cu ---------------------------------------------------------------------
+// out[i] = sum_j in[j] omega^(ij) over N = 2^log_n; in has n_in valid elements (rest
+// read as zero).  pre/post: three host Fr multipliers indexed by position mod 3, or null.
+// d_out may alias d_in.
+int32_t ntt_run(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, uint32_t log_n,
+                const host::HFr& omega, const host::HFr* pre, const host::HFr* post);
+// a[i] *= m[i mod period]  (divide_by_vanishing_poly), m on device
+int32_t fr_scale_periodic(b200zk_ctx* ctx, fe_t* d_a, size_t n, const fe_t* d_m, uint32_t period);
+
+// msm.cu ---------------------------------------------------------------------
+int32_t msm_run(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, host::HAffine* out);
+
+}  // namespace b200zk

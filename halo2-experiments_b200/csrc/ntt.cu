@@ -1,0 +1,109 @@
+// Launch side of the NTT (see ntt.cuh for the algorithm and the reference mapping).
+#include "context.hpp"
+#include "ntt.cuh"
+
+namespace b200zk {
+
+static constexpr uint32_t NTT_THREADS = 512;
+static constexpr uint32_t NTT_MAX_LOG_M = 10;      // <= 1024-point DFT per tile
+static constexpr uint32_t NTT_MAX_LOG_TW = 3;      // <= 8 columns = 256 B contiguous
+static constexpr uint32_t NTT_TILE_CAP_LOG = 12;   // 4096 elements = 128 KiB of shared memory
+
+__global__ void __launch_bounds__(NTT_THREADS, 1) ntt_pass_kernel(const NttPassArgs a) {
+    extern __shared__ half_t ntt_sm[];
+    ntt_pass_block(a, blockIdx.x, blockDim.x, ntt_sm);
+}
+
+__global__ void ntt_pow_table_kernel(fe_t* out, const fe_t base, uint32_t count, uint32_t shift) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) ntt_pow_table_thread(out, base, i, shift);
+}
+
+__global__ void fr_scale_periodic_kernel(fe_t* a, size_t n, const fe_t* m, uint32_t period) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) { fe_t x = a[i], y = m[i & (period - 1)]; a[i] = Fr::mul(x, y); }
+}
+
+static fe_t to_dev(const host::HFr& x) { fe_t r; memcpy(r.l, x.v, 32); return r; }
+
+static int32_t build_plan(b200zk_ctx* ctx, uint32_t log_n, const host::HFr& omega, NttPlan& plan) {
+    plan.shape = ntt_plan_shape(log_n, NTT_MAX_LOG_M, NTT_MAX_LOG_TW, NTT_TILE_CAP_LOG);
+    const NttShape& s = plan.shape;
+    size_t n_roots = (size_t)1 << (s.log_roots ? s.log_roots - 1 : 0);
+    size_t n_lo = (size_t)1 << s.tw_lo_bits, n_hi = ((size_t)1 << log_n) >> s.tw_lo_bits;
+    if (n_hi == 0) n_hi = 1;
+    ZK_CUDA(ctx, cudaMalloc(&plan.roots, n_roots * sizeof(fe_t)));
+    ZK_CUDA(ctx, cudaMalloc(&plan.tw_lo, n_lo * sizeof(fe_t)));
+    ZK_CUDA(ctx, cudaMalloc(&plan.tw_hi, n_hi * sizeof(fe_t)));
+    host::HFr w_r = omega.pow_u64(1ull << (log_n - s.log_roots));
+    auto launch = [&](fe_t* out, const host::HFr& base, size_t count, uint32_t shift) {
+        ntt_pow_table_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(out, to_dev(base), (uint32_t)count, shift);
+        ctx->launches++;
+    };
+    launch(plan.roots, w_r, n_roots, 0);
+    launch(plan.tw_lo, omega, n_lo, 0);
+    launch(plan.tw_hi, omega, n_hi, s.tw_lo_bits);
+    ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+int32_t ntt_run(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, uint32_t log_n,
+                const host::HFr& omega, const host::HFr* pre, const host::HFr* post) {
+    if (log_n > 3 * NTT_MAX_LOG_M) return fail(ctx, B200ZK_EINVAL, "ntt_run", "log_n too large");
+    std::array<uint64_t, 5> key = {log_n, omega.v[0], omega.v[1], omega.v[2], omega.v[3]};
+    auto it = ctx->ntt_plans.find(key);
+    if (it == ctx->ntt_plans.end()) {
+        NttPlan plan;
+        ZK_TRY(build_plan(ctx, log_n, omega, plan));
+        it = ctx->ntt_plans.emplace(key, plan).first;
+    }
+    const NttPlan& plan = it->second;
+    const NttShape& s = plan.shape;
+    size_t N = (size_t)1 << log_n;
+    fe_t* scratch = nullptr;
+    if (s.npass > 1) {
+        ZK_TRY(ws_reserve(ctx, ctx->ntt_scratch, N * sizeof(fe_t)));
+        scratch = (fe_t*)ctx->ntt_scratch.p;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZK_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(sizeof(fe_t) << NTT_TILE_CAP_LOG)));
+        attr_set = true;
+    }
+    for (uint32_t p = 0; p < s.npass; ++p) {
+        const NttPassShape& q = s.pass[p];
+        NttPassArgs a{};
+        a.in = p == 0 ? d_in : scratch;
+        a.out = q.is_last ? d_out : scratch;
+        a.log_n = log_n; a.log_m = q.log_m; a.log_l = q.log_l; a.log_tw = q.log_tw; a.is_last = q.is_last;
+        a.log_m1 = q.log_m1; a.log_mid = q.log_mid;
+        a.n_in = p == 0 ? n_in : (uint32_t)N;
+        a.use_pre = (p == 0 && pre) ? 1 : 0;
+        a.use_post = (q.is_last && post) ? 1 : 0;
+        for (int i = 0; i < 3; ++i) {
+            if (pre) a.pre[i] = to_dev(pre[i]);
+            if (post) a.post[i] = to_dev(post[i]);
+        }
+        a.roots = plan.roots; a.log_roots = s.log_roots;
+        a.tw_lo = plan.tw_lo; a.tw_hi = plan.tw_hi; a.tw_lo_bits = s.tw_lo_bits;
+        size_t smem = sizeof(fe_t) << (q.log_m + q.log_tw);
+        uint32_t tile = 1u << (q.log_m + q.log_tw);
+        uint32_t threads = tile / 2 < NTT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : NTT_THREADS;
+        ntt_pass_kernel<<<q.blocks, threads, smem, ctx->stream>>>(a);
+        ctx->launches++;
+    }
+    ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+int32_t fr_scale_periodic(b200zk_ctx* ctx, fe_t* d_a, size_t n, const fe_t* d_m, uint32_t period) {
+    unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
+    fr_scale_periodic_kernel<<<blocks, 256, 0, ctx->stream>>>(d_a, n, d_m, period);
+    ctx->launches++;
+    ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+}  // namespace b200zk

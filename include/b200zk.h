@@ -1,0 +1,121 @@
+/* b200zk — C ABI of the B200-native halo2 (PSE fork, bn256 KZG) proving backend.
+ *
+ * Every entry point replaces one function of halo2_proofs v2023_02_02 /
+ * halo2curves 0.3.1 (third-party crates pinned at /root/reference/Cargo.toml:10-11)
+ * that the reference reaches from its only prover call site,
+ * `full_prover` (/root/reference/src/circuits/utils.rs:22-70).  A patched
+ * halo2_proofs binds these symbols over Rust FFI; chips and
+ * circuits recompile unchanged.
+ *
+ * Conventions
+ *  - Field elements are 32-byte little-endian Montgomery limbs, exactly the
+ *    in-memory layout of halo2curves `Fr([u64;4])` / `Fq([u64;4])`, so `&[Fr]`
+ *    and `&[G1Affine]` are passed as plain pointers with no conversion.
+ *    G1Affine = {x, y} 64 B (identity (0,0)); G1 = {x, y, z} Jacobian 96 B.
+ *  - Every function returns 0 on success and a negative B200ZK_E* code on error;
+ *    nothing is thrown across the boundary.  b200zk_last_error() gives the text.
+ *    The Rust shim turns a non-zero code into the panic / plonk::Error the
+ *    upstream function would have raised (e.g. length mismatch in best_multiexp).
+ *  - A ctx owns one CUDA device, one stream and its scratch memory and is used by
+ *    one caller thread at a time.  There is no CPU fallback: if no CUDA device is
+ *    usable, ctx creation fails with B200ZK_ENODEV.
+ *  - "_dev" variants take device pointers obtained from b200zk_malloc() and leave
+ *    results on the device; the host variants copy in and out (H2D, kernel, D2H).
+ */
+#ifndef B200ZK_H
+#define B200ZK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ZK_OK 0
+#define B200ZK_EINVAL (-1)   /* bad argument (length mismatch, log_n out of range ...) */
+#define B200ZK_ENODEV (-2)   /* no usable CUDA device / extension unusable           */
+#define B200ZK_ECUDA (-3)    /* CUDA runtime error, see b200zk_last_error            */
+#define B200ZK_ENOMEM (-4)
+
+typedef struct b200zk_ctx b200zk_ctx;
+typedef struct b200zk_domain b200zk_domain;
+typedef struct b200zk_params b200zk_params;
+
+/* ---- context ------------------------------------------------------------ */
+int32_t b200zk_ctx_create(int32_t device, b200zk_ctx** out);
+void b200zk_ctx_destroy(b200zk_ctx* ctx);
+const char* b200zk_last_error(const b200zk_ctx* ctx);
+int32_t b200zk_sync(b200zk_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+uint64_t b200zk_launch_count(const b200zk_ctx* ctx);
+/* CUDA events on the ctx stream, for device-side timing of the calls in between */
+int32_t b200zk_event_record(b200zk_ctx* ctx, uint32_t slot /* < 64 */);
+int32_t b200zk_event_elapsed_ms(b200zk_ctx* ctx, uint32_t from_slot, uint32_t to_slot, float* ms);
+
+/* ---- device memory -------------------------------------------------------- */
+int32_t b200zk_malloc(b200zk_ctx* ctx, size_t bytes, void** dptr);
+int32_t b200zk_free(b200zk_ctx* ctx, void* dptr);
+int32_t b200zk_upload(b200zk_ctx* ctx, void* dptr, const void* host, size_t bytes);
+int32_t b200zk_download(b200zk_ctx* ctx, void* host, const void* dptr, size_t bytes);
+int32_t b200zk_memset_zero(b200zk_ctx* ctx, void* dptr, size_t bytes);
+/* pinned host staging buffers (cudaHostAlloc) for the end-to-end path */
+int32_t b200zk_host_alloc(b200zk_ctx* ctx, size_t bytes, void** hptr);
+int32_t b200zk_host_free(b200zk_ctx* ctx, void* hptr);
+
+/* ---- arithmetic::best_multiexp(coeffs: &[Fr], bases: &[G1Affine]) -> G1 ----
+ * halo2_proofs src/arithmetic.rs.  out = sum coeffs[i] * bases[i], returned as a
+ * Jacobian point with z = 1 (or the identity (0,1,0)): the same group element the
+ * CPU path returns, in normalised representation.  len == 0 gives the identity. */
+int32_t b200zk_msm(b200zk_ctx* ctx, const void* coeffs, const void* bases, size_t len, void* out_g1);
+int32_t b200zk_msm_dev(b200zk_ctx* ctx, const void* d_coeffs, const void* d_bases, size_t len, void* out_g1_host);
+/* window size override for tuning (0 = automatic) */
+int32_t b200zk_msm_set_window(b200zk_ctx* ctx, int32_t c);
+
+/* ---- arithmetic::best_fft(a: &mut [Fr], omega: Fr, log_n: u32) --------------
+ * In place, natural order in and out, unscaled:  a[i] <- sum_j a[j] omega^(ij). */
+int32_t b200zk_fft(b200zk_ctx* ctx, void* a, const void* omega, uint32_t log_n);
+int32_t b200zk_fft_dev(b200zk_ctx* ctx, void* d_a, const void* omega_host, uint32_t log_n);
+
+/* ---- poly::EvaluationDomain<Fr> (src/poly/domain.rs) ------------------------
+ * b200zk_domain_create(j, k) = EvaluationDomain::new(j, k). */
+int32_t b200zk_domain_create(b200zk_ctx* ctx, uint32_t j, uint32_t k, b200zk_domain** out);
+void b200zk_domain_destroy(b200zk_domain* dom);
+uint32_t b200zk_domain_k(const b200zk_domain* dom);
+uint32_t b200zk_domain_extended_k(const b200zk_domain* dom);
+uint32_t b200zk_domain_quotient_poly_degree(const b200zk_domain* dom);
+/* which: 0 omega, 1 omega_inv, 2 extended_omega, 3 extended_omega_inv, 4 g_coset,
+ *        5 g_coset_inv, 6 ifft_divisor, 7 extended_ifft_divisor, 8 barycentric_weight */
+int32_t b200zk_domain_constant(const b200zk_domain* dom, uint32_t which, void* out_fr);
+/* lagrange_to_coeff: n elements in place */
+int32_t b200zk_lagrange_to_coeff(b200zk_domain* dom, void* a);
+int32_t b200zk_lagrange_to_coeff_dev(b200zk_domain* dom, void* d_a);
+/* coeff_to_extended: n coefficients in, 2^extended_k evaluations out */
+int32_t b200zk_coeff_to_extended(b200zk_domain* dom, const void* coeffs, void* out_ext);
+int32_t b200zk_coeff_to_extended_dev(b200zk_domain* dom, const void* d_coeffs, void* d_out_ext);
+/* extended_to_coeff: 2^extended_k evaluations in (clobbered in the _dev variant),
+ * n * quotient_poly_degree coefficients out */
+int32_t b200zk_extended_to_coeff(b200zk_domain* dom, const void* ext, void* out_coeffs);
+int32_t b200zk_extended_to_coeff_dev(b200zk_domain* dom, void* d_ext, void* d_out_coeffs);
+/* divide_by_vanishing_poly: 2^extended_k evaluations in place */
+int32_t b200zk_divide_by_vanishing_poly(b200zk_domain* dom, void* ext);
+int32_t b200zk_divide_by_vanishing_poly_dev(b200zk_domain* dom, void* d_ext);
+
+/* ---- poly::kzg::commitment::ParamsKZG<Bn256> ---------------------------------
+ * load: upload an existing SRS (g, g_lagrange: n G1Affine each; g_lagrange may be
+ * NULL).  setup: ParamsKZG::setup(k, rng) with the secret s supplied by the caller
+ * (s = Fr::random(rng) on the Rust side); bases are generated on the device. */
+int32_t b200zk_params_load(b200zk_ctx* ctx, uint32_t k, const void* g, const void* g_lagrange, b200zk_params** out);
+int32_t b200zk_params_setup(b200zk_ctx* ctx, uint32_t k, const void* s_fr, b200zk_params** out);
+void b200zk_params_destroy(b200zk_params* p);
+/* copy the bases back (get_g / g_lagrange), n * 64 bytes each; either may be NULL */
+int32_t b200zk_params_read(b200zk_params* p, void* g_out, void* g_lagrange_out);
+/* commit(poly: Coeff) / commit_lagrange(poly: LagrangeCoeff); len <= n */
+int32_t b200zk_commit(b200zk_params* p, const void* poly, size_t len, void* out_g1);
+int32_t b200zk_commit_lagrange(b200zk_params* p, const void* poly, size_t len, void* out_g1);
+int32_t b200zk_commit_dev(b200zk_params* p, const void* d_poly, size_t len, int32_t lagrange, void* out_g1_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ZK_H */

@@ -19,3 +19,17 @@ def orc():
     binding.build()
     binding.lib()
     return binding
+
+
+@pytest.fixture(scope="session")
+def zk():
+    """The product package (halo2-experiments_b200/)."""
+    from __graft_entry__ import load_package
+    return load_package()
+
+
+@pytest.fixture(scope="session")
+def backend(zk):
+    be = zk.Backend(0)
+    yield be
+    be.close()

@@ -1,0 +1,159 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle on the same seeded
+inputs (bit-exact: everything here is integer arithmetic), plus size-independent properties
+at the sizes the oracle is too slow for."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(orc, k, seed=1):
+    s = orc.random_fr(1, 1000 + seed)[0]
+    return orc.params_setup(k, s)
+
+
+def _affine(out12):
+    return out12[:8]
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 5, 8, 10, 11, 13, 16])
+def test_best_fft_matches_oracle(backend, orc, k):
+    a = orc.random_fr(1 << k, 10 + k)
+    from oracle import pyref
+    w = orc.ints_to_mont([pyref.omega_for_k(k)])[0]
+    got = backend.best_fft(a, w, k)
+    assert np.array_equal(got, orc.best_fft(a, w, k))
+    # generic omega (not a root of unity of that order is still a valid best_fft input)
+    w2 = orc.random_fr(1, 99)[0]
+    if k <= 8:
+        assert np.array_equal(backend.best_fft(a, w2, k), orc.best_fft(a, w2, k))
+
+
+@pytest.mark.parametrize("k", [18, 20, 21])
+def test_best_fft_large_roundtrip_and_spot(backend, orc, k):
+    from oracle import pyref
+    n = 1 << k
+    a = orc.random_fr(n, 30 + k)
+    w = pyref.omega_for_k(k)
+    W, WI = orc.ints_to_mont([w])[0], orc.ints_to_mont([pow(w, -1, pyref.R_MOD)])[0]
+    f = backend.best_fft(a, W, k)
+    if k <= 20:
+        assert np.array_equal(f, orc.best_fft(a, W, k))
+    else:
+        # spot-check a few outputs by Horner: out[i] = a(omega^i)
+        for i in (0, 1, n // 2 + 3, n - 1):
+            x = orc.ints_to_mont([pow(w, i, pyref.R_MOD)])[0]
+            assert np.array_equal(f[i], orc.eval_polynomial(a, x))
+    back = backend.best_fft(f, WI, k)
+    ninv = orc.ints_to_mont([pow(n, -1, pyref.R_MOD)])[0]
+    assert np.array_equal(orc.binop("mul", back, np.tile(ninv, (n, 1))), a)
+
+
+@pytest.mark.parametrize("j,k", [(6, 4), (6, 9), (3, 10), (17, 6), (6, 14), (4, 12), (2, 7)])
+def test_domain_matches_oracle(zk, backend, orc, j, k):
+    d, od = zk.EvaluationDomain(backend, j, k), orc.Domain(j, k)
+    assert d.extended_k == od.extended_k and d.quotient_poly_degree == od.quotient_poly_degree
+    for name in d._CONSTS:
+        assert np.array_equal(getattr(d, name), getattr(od, name)), name
+    a = orc.random_fr(1 << k, 50 + k)
+    coeff = d.lagrange_to_coeff(a)
+    assert np.array_equal(coeff, od.lagrange_to_coeff(a))
+    ext = d.coeff_to_extended(coeff)
+    assert np.array_equal(ext, od.coeff_to_extended(coeff))
+    assert np.array_equal(d.divide_by_vanishing_poly(ext), od.divide_by_vanishing_poly(ext))
+    e2 = orc.random_fr(1 << od.extended_k, 60 + k)
+    assert np.array_equal(d.extended_to_coeff(e2), od.extended_to_coeff(e2))
+    # round trip: extended_to_coeff(coeff_to_extended(p)) = p || 0
+    back = d.extended_to_coeff(ext)
+    assert np.array_equal(back[: 1 << k], coeff) and not back[1 << k:].any()
+    d.close()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 32, 33, 255, 1000, 4096, 1 << 14, (1 << 16) + 7])
+def test_best_multiexp_matches_oracle(backend, orc, n):
+    k = max(1, (max(n, 1) - 1).bit_length())
+    g, _ = _setup(orc, k)
+    coeffs = orc.random_fr(n, 70 + (n % 97))
+    got = backend.best_multiexp(coeffs, g[:n])
+    if n == 0:
+        # G1::identity() = (0, 1, 0)
+        assert not got[:4].any() and not got[8:].any() and np.array_equal(got[4:8], orc.ints_to_mont([1], orc.FQ)[0])
+        return
+    want = orc.g1_batch_normalize(orc.best_multiexp(coeffs, g[:n]))[0]
+    assert np.array_equal(_affine(got), want)
+
+
+@pytest.mark.parametrize("c", [4, 7, 11, 13, 16])
+def test_best_multiexp_window_sizes(backend, orc, c):
+    n = 3000
+    g, _ = _setup(orc, 12)
+    coeffs = orc.random_fr(n, 5)
+    backend.set_msm_window(c)
+    try:
+        got = backend.best_multiexp(coeffs, g[:n])
+    finally:
+        backend.set_msm_window(0)
+    assert np.array_equal(_affine(got), orc.g1_batch_normalize(orc.best_multiexp(coeffs, g[:n]))[0])
+
+
+def test_best_multiexp_edge_inputs(backend, orc):
+    """zero / one / r-1 scalars, identity and repeated bases, P + (-P), witness-like sparse columns."""
+    from oracle import pyref
+    n = 2048
+    g, _ = _setup(orc, 11)
+    g = np.array(g)
+    ss = orc.mont_to_ints(orc.random_fr(n, 6))
+    ss[0], ss[1], ss[2], ss[3] = 0, 1, pyref.R_MOD - 1, 1 << 253
+    g[5] = g[4]; ss[5] = ss[4]                      # P + P inside one bucket
+    g[7, :4] = g[6, :4]                             # -P: same x, negated y
+    g[7, 4:] = orc.binop("sub", np.zeros((1, 4), dtype=np.uint64), g[6, 4:].reshape(1, 4), orc.FQ)[0]
+    ss[7] = ss[6]
+    g[9] = 0                                        # identity base
+    S = orc.ints_to_mont(ss)
+    assert np.array_equal(_affine(backend.best_multiexp(S, g)), orc.g1_batch_normalize(orc.best_multiexp(S, g))[0])
+    # 99.9 % zeros, the rest < 2^64 ("witness-like")
+    sparse = [0] * n
+    for i in range(0, n, 512):
+        sparse[i] = (i * 0x9E3779B97F4A7C15) & ((1 << 64) - 1)
+    S = orc.ints_to_mont(sparse)
+    assert np.array_equal(_affine(backend.best_multiexp(S, g)), orc.g1_batch_normalize(orc.best_multiexp(S, g))[0])
+    # all scalars equal and tiny: every point lands in one bucket
+    S = orc.ints_to_mont([3] * n)
+    assert np.array_equal(_affine(backend.best_multiexp(S, g)), orc.g1_batch_normalize(orc.best_multiexp(S, g))[0])
+    # all-zero column -> identity
+    out = backend.best_multiexp(orc.ints_to_mont([0] * n), g)
+    assert not out[:4].any() and not out[8:].any()
+    # length mismatch is an error, as upstream's assert_eq!
+    with pytest.raises(Exception):
+        backend.best_multiexp(S[:10], g[:11])
+
+
+def test_best_multiexp_linearity_large(backend, orc):
+    """2^20 points: MSM(a + b) == MSM(a) + MSM(b) and agreement with the oracle on a 2^18 prefix."""
+    k = 20
+    n = 1 << k
+    g, _ = _setup(orc, k)
+    a, b = orc.random_fr(n, 80), orc.random_fr(n, 81)
+    ra, rb = backend.best_multiexp(a, g), backend.best_multiexp(b, g)
+    rab = backend.best_multiexp(orc.binop("add", a, b), g)
+    s = orc.g1_add(orc.g1_from_affine(_affine(ra))[0], orc.g1_from_affine(_affine(rb))[0])
+    assert np.array_equal(orc.g1_batch_normalize(s)[0], _affine(rab))
+    m = 1 << 18
+    assert np.array_equal(_affine(backend.best_multiexp(a[:m], g[:m])), orc.g1_batch_normalize(orc.best_multiexp(a[:m], g[:m]))[0])
+
+
+def test_params_commit_matches_oracle(zk, backend, orc):
+    k = 10
+    g, gl = _setup(orc, k)
+    params = zk.ParamsKZG.load(backend, k, g, gl)
+    poly = orc.random_fr(1 << k, 90)
+    assert np.array_equal(_affine(params.commit(poly)), orc.g1_batch_normalize(orc.best_multiexp(poly, g))[0])
+    assert np.array_equal(_affine(params.commit_lagrange(poly)), orc.g1_batch_normalize(orc.best_multiexp(poly, gl))[0])
+    short = poly[:300]
+    assert np.array_equal(_affine(params.commit(short)), orc.g1_batch_normalize(orc.best_multiexp(short, g[:300]))[0])
+    # commit_lagrange(evals) == commit(lagrange_to_coeff(evals))
+    d = zk.EvaluationDomain(backend, 3, k)
+    assert np.array_equal(params.commit_lagrange(poly), params.commit(d.lagrange_to_coeff(poly)))
+    g2, gl2 = params.read()
+    assert np.array_equal(g2, g) and np.array_equal(gl2, gl)
+    d.close(); params.close()
