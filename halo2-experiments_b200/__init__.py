@@ -173,6 +173,47 @@ class Backend:
     def best_fft_dev(self, d_a, omega, log_n):
         self._check(lib().b200zk_fft_dev(self._ctx, d_a.ptr, _p(_fr(omega, 1)), ctypes.c_uint32(log_n)))
 
+    def eval_polynomial(self, poly, x):
+        poly = _fr(poly)
+        out = np.zeros(4, dtype=np.uint64)
+        self._check(lib().b200zk_eval_polynomial(self._ctx, _p(poly), ctypes.c_size_t(poly.shape[0]), _p(_fr(x, 1)), _p(out)))
+        return out
+
+    def eval_polynomial_dev(self, d_poly, n, x):
+        out = np.zeros(4, dtype=np.uint64)
+        self._check(lib().b200zk_eval_polynomial_dev(self._ctx, d_poly.ptr, ctypes.c_size_t(n), _p(_fr(x, 1)), _p(out)))
+        return out
+
+    def kate_division(self, a, b):
+        """Quotient of a(X) by (X - b): len(a) - 1 coefficients."""
+        a = _fr(a)
+        n = a.shape[0]
+        d_a, d_q = self.to_device(a), self.alloc(max(n - 1, 1) * 32)
+        try:
+            self._check(lib().b200zk_kate_division_dev(self._ctx, d_a.ptr, ctypes.c_size_t(n), _p(_fr(b, 1)), d_q.ptr))
+            return d_q.download((n - 1, 4))
+        finally:
+            d_a.free(); d_q.free()
+
+    def batch_invert(self, a, field=0):
+        a = _fr(a)
+        d = self.to_device(a)
+        try:
+            self._check(lib().b200zk_batch_invert_dev(self._ctx, d.ptr, ctypes.c_size_t(a.shape[0]), ctypes.c_int32(field)))
+            return d.download(a.shape)
+        finally:
+            d.free()
+
+    def prefix_product(self, p, z0):
+        """z[0] = z0, z[i] = z[i-1] * p[i-1]."""
+        p = _fr(p)
+        d = self.to_device(p)
+        try:
+            self._check(lib().b200zk_prefix_product_dev(self._ctx, d.ptr, d.ptr, ctypes.c_size_t(p.shape[0]), _p(_fr(z0, 1))))
+            return d.download(p.shape)
+        finally:
+            d.free()
+
 
 class EvaluationDomain:
     """poly::EvaluationDomain<Fr>::new(j, k) on a Backend."""

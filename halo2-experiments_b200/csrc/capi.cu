@@ -80,7 +80,8 @@ void b200zk_ctx_destroy(b200zk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->ntt_plans) { cudaFree(kv.second.roots); cudaFree(kv.second.tw_lo); cudaFree(kv.second.tw_hi); }
-    for (Workspace* w : {&ctx->ntt_scratch, &ctx->msm_ws, &ctx->io_a, &ctx->io_b}) if (w->p) cudaFree(w->p);
+    for (Workspace* w : {&ctx->ntt_scratch, &ctx->msm_ws, &ctx->io_a, &ctx->io_b, &ctx->poly_ws, &ctx->poly_heads, &ctx->setup_ws}) if (w->p) cudaFree(w->p);
+    if (ctx->d_gen_table) cudaFree(ctx->d_gen_table);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto& e : ctx->events) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -403,8 +404,58 @@ int32_t b200zk_commit(b200zk_params* p, const void* poly, size_t len, void* out_
 int32_t b200zk_commit_lagrange(b200zk_params* p, const void* poly, size_t len, void* out_g1) { return commit_host(p, poly, len, 1, out_g1); }
 
 int32_t b200zk_params_setup(b200zk_ctx* ctx, uint32_t k, const void* s_fr, b200zk_params** out) {
-    (void)k; (void)s_fr; (void)out;
-    return fail(ctx, B200ZK_EINVAL, "params_setup", "not built yet");
+    if (!ctx || !out || !s_fr || k > host::FR_TWO_ADICITY) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    b200zk_params* p = new (std::nothrow) b200zk_params();
+    if (!p) return B200ZK_ENOMEM;
+    p->ctx = ctx; p->k = k; p->d_g = nullptr; p->d_g_lagrange = nullptr;
+    size_t bytes = sizeof(affine_t) << k;
+    cudaError_t e = cudaMalloc(&p->d_g, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_g_lagrange, bytes);
+    int32_t rc = e == cudaSuccess ? params_setup_run(ctx, k, HFr::from_limbs(s_fr), p->d_g, p->d_g_lagrange)
+                                  : fail(ctx, B200ZK_ENOMEM, "params_setup", cudaGetErrorString(e));
+    if (rc == B200ZK_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, B200ZK_ECUDA, "params_setup", "sync failed");
+    if (rc != B200ZK_OK) { cudaFree(p->d_g); cudaFree(p->d_g_lagrange); delete p; return rc; }
+    *out = p;
+    return B200ZK_OK;
+}
+
+// ---- eval_polynomial / kate_division / BatchInvert / grand-product scan ---------------------
+int32_t b200zk_eval_polynomial_dev(b200zk_ctx* ctx, const void* d_poly, size_t len, const void* x_fr, void* out_fr_host) {
+    if (!ctx || !x_fr || !out_fr_host || (len && !d_poly)) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    HFr head;
+    ZK_TRY(recurrence_run(ctx, (const fe_t*)d_poly, nullptr, len, HFr::from_limbs(x_fr), &head));
+    head.store(out_fr_host);
+    return B200ZK_OK;
+}
+
+int32_t b200zk_eval_polynomial(b200zk_ctx* ctx, const void* poly, size_t len, const void* x_fr, void* out_fr) {
+    if (!ctx || !x_fr || !out_fr || (len && !poly)) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZK_TRY(ws_reserve(ctx, ctx->io_a, len * sizeof(fe_t)));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, poly, len * sizeof(fe_t), cudaMemcpyHostToDevice, ctx->stream));
+    return b200zk_eval_polynomial_dev(ctx, ctx->io_a.p, len, x_fr, out_fr);
+}
+
+int32_t b200zk_kate_division_dev(b200zk_ctx* ctx, const void* d_a, size_t len, const void* b_fr, void* d_q) {
+    if (!ctx || !d_a || !b_fr || !d_q || len < 1) return B200ZK_EINVAL;
+    if (len == 1) return B200ZK_OK;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    // q[i] = a[i+1] + b q[i+1]: the Horner recurrence on a[1..]
+    return recurrence_run(ctx, (const fe_t*)d_a + 1, (fe_t*)d_q, len - 1, HFr::from_limbs(b_fr), nullptr);
+}
+
+int32_t b200zk_batch_invert_dev(b200zk_ctx* ctx, void* d_a, size_t len, int32_t field) {
+    if (!ctx || (len && !d_a) || field < 0 || field > 1) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return batch_invert_run(ctx, (fe_t*)d_a, len, field);
+}
+
+int32_t b200zk_prefix_product_dev(b200zk_ctx* ctx, const void* d_p, void* d_z, size_t len, const void* z0_fr) {
+    if (!ctx || !z0_fr || (len && (!d_p || !d_z))) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return prefix_product_run(ctx, (const fe_t*)d_p, (fe_t*)d_z, len, HFr::from_limbs(z0_fr));
 }
 
 }  // extern "C"

@@ -1,0 +1,97 @@
+// Launch side of the O(n) field-vector primitives (poly.cuh).
+#include "context.hpp"
+#include "poly.cuh"
+
+namespace b200zk {
+
+static constexpr uint32_t POLY_THREADS = 128;
+static constexpr uint32_t SCAN_THREADS = 512;
+static constexpr size_t CHUNK = 64;
+
+template <class F> __global__ void __launch_bounds__(POLY_THREADS) batch_invert_kernel(fe_t* a, fe_t* scratch, size_t n, size_t lanes) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < lanes) batch_invert_lane<F>(a, scratch, n, t, lanes);
+}
+
+__global__ void __launch_bounds__(POLY_THREADS) recur_local_kernel(const fe_t* a, fe_t* y, size_t n, size_t m, const fe_t b, fe_t* heads) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    recur_local_chunk(a, y, n, m, c, b, heads);
+}
+__global__ void __launch_bounds__(SCAN_THREADS) recur_carries_kernel(fe_t* heads, fe_t* carries, size_t n, size_t m, const fe_t b) {
+    __shared__ fe_t sm[2 * SCAN_THREADS];
+    recur_carries_block(heads, carries, n, m, b, blockDim.x, sm);
+}
+__global__ void __launch_bounds__(POLY_THREADS) recur_apply_kernel(fe_t* y, size_t n, size_t m, const fe_t b, const fe_t* carries) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    recur_apply_chunk(y, n, m, c, b, carries);
+}
+
+__global__ void __launch_bounds__(POLY_THREADS) prodscan_product_kernel(const fe_t* p, size_t n, size_t m, fe_t* prods) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    prodscan_chunk_product(p, n, m, c, prods);
+}
+__global__ void __launch_bounds__(SCAN_THREADS) prodscan_carries_kernel(fe_t* prods, size_t C, const fe_t z0) {
+    __shared__ fe_t sm[2 * SCAN_THREADS];
+    prodscan_carries_block(prods, C, z0, blockDim.x, sm);
+}
+__global__ void __launch_bounds__(POLY_THREADS) prodscan_write_kernel(const fe_t* p, fe_t* z, size_t n, size_t m, const fe_t* prods) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    prodscan_write_chunk(p, z, n, m, c, prods);
+}
+
+static fe_t to_dev(const host::HFr& x) { fe_t r; memcpy(r.l, x.v, 32); return r; }
+static unsigned nblocks(size_t work, unsigned threads) { return (unsigned)((work + threads - 1) / threads); }
+
+int32_t batch_invert_run(b200zk_ctx* ctx, fe_t* d_a, size_t n, int field) {
+    if (n == 0) return B200ZK_OK;
+    ZK_TRY(ws_reserve(ctx, ctx->poly_ws, n * sizeof(fe_t)));
+    // enough lanes to fill the machine, at least ~32 elements per lane to amortise the inversion
+    size_t lanes = std::min<size_t>((n + 31) / 32, (size_t)ctx->sm_count * 1024);
+    if (lanes == 0) lanes = 1;
+    if (field == 0) batch_invert_kernel<Fr><<<nblocks(lanes, POLY_THREADS), POLY_THREADS, 0, ctx->stream>>>(d_a, (fe_t*)ctx->poly_ws.p, n, lanes);
+    else batch_invert_kernel<Fq><<<nblocks(lanes, POLY_THREADS), POLY_THREADS, 0, ctx->stream>>>(d_a, (fe_t*)ctx->poly_ws.p, n, lanes);
+    ctx->launches++;
+    ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+// y[i] = a[i] + b*y[i+1]; d_y may be null (only the head y[0] is wanted) or alias d_a.
+// The head is left in ctx->poly_heads[0] on the device; *head_out (host) is filled if non-null.
+int32_t recurrence_run(b200zk_ctx* ctx, const fe_t* d_a, fe_t* d_y, size_t n, const host::HFr& b, host::HFr* head_out) {
+    if (n == 0) { if (head_out) *head_out = host::HFr::zero(); return B200ZK_OK; }
+    size_t C = (n + CHUNK - 1) / CHUNK;
+    ZK_TRY(ws_reserve(ctx, ctx->poly_heads, 2 * C * sizeof(fe_t)));
+    fe_t* heads = (fe_t*)ctx->poly_heads.p;
+    fe_t* carries = heads + C;
+    fe_t bd = to_dev(b);
+    recur_local_kernel<<<nblocks(C, POLY_THREADS), POLY_THREADS, 0, ctx->stream>>>(d_a, d_y, n, CHUNK, bd, heads);
+    recur_carries_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(heads, carries, n, CHUNK, bd);
+    ctx->launches += 2;
+    if (d_y) {
+        recur_apply_kernel<<<nblocks(C, POLY_THREADS), POLY_THREADS, 0, ctx->stream>>>(d_y, n, CHUNK, bd, carries);
+        ctx->launches++;
+    }
+    ZK_CUDA(ctx, cudaGetLastError());
+    if (head_out) {
+        ZK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, heads, sizeof(fe_t), cudaMemcpyDeviceToHost, ctx->stream));
+        ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *head_out = host::HFr::from_limbs(ctx->pinned);
+    }
+    return B200ZK_OK;
+}
+
+// z[0] = z0, z[i] = z[i-1] * p[i-1] for i < n  (z may alias p)
+int32_t prefix_product_run(b200zk_ctx* ctx, const fe_t* d_p, fe_t* d_z, size_t n, const host::HFr& z0) {
+    if (n == 0) return B200ZK_OK;
+    size_t C = (n + CHUNK - 1) / CHUNK;
+    ZK_TRY(ws_reserve(ctx, ctx->poly_heads, 2 * C * sizeof(fe_t)));
+    fe_t* prods = (fe_t*)ctx->poly_heads.p;
+    prodscan_product_kernel<<<nblocks(C, POLY_THREADS), POLY_THREADS, 0, ctx->stream>>>(d_p, n, CHUNK, prods);
+    prodscan_carries_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(prods, C, to_dev(z0));
+    prodscan_write_kernel<<<nblocks(C, POLY_THREADS), POLY_THREADS, 0, ctx->stream>>>(d_p, d_z, n, CHUNK, prods);
+    ctx->launches += 3;
+    ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+}  // namespace b200zk

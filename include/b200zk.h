@@ -115,6 +115,18 @@ int32_t b200zk_commit(b200zk_params* p, const void* poly, size_t len, void* out_
 int32_t b200zk_commit_lagrange(b200zk_params* p, const void* poly, size_t len, void* out_g1);
 int32_t b200zk_commit_dev(b200zk_params* p, const void* d_poly, size_t len, int32_t lagrange, void* out_g1_host);
 
+/* ---- arithmetic::eval_polynomial / kate_division, ff::BatchInvert -----------------
+ * eval_polynomial(poly, x) -> Fr (Horner);  kate_division(a, b): quotient of a(X) by
+ * (X - b), len-1 coefficients;  batch_invert: in place, zeros stay zero.
+ * field: 0 = Fr, 1 = Fq. */
+int32_t b200zk_eval_polynomial(b200zk_ctx* ctx, const void* poly, size_t len, const void* x_fr, void* out_fr);
+int32_t b200zk_eval_polynomial_dev(b200zk_ctx* ctx, const void* d_poly, size_t len, const void* x_fr, void* out_fr_host);
+int32_t b200zk_kate_division_dev(b200zk_ctx* ctx, const void* d_a, size_t len, const void* b_fr, void* d_q);
+int32_t b200zk_batch_invert_dev(b200zk_ctx* ctx, void* d_a, size_t len, int32_t field);
+/* z[0] = z0, z[i] = z[i-1] * p[i-1]: the grand-product scan of the permutation and lookup
+ * arguments (plonk/permutation/prover.rs, plonk/lookup/prover.rs).  d_z may alias d_p. */
+int32_t b200zk_prefix_product_dev(b200zk_ctx* ctx, const void* d_p, void* d_z, size_t len, const void* z0_fr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,3 +73,26 @@ def host_fr_consts(wide):
     wide = np.ascontiguousarray(wide, dtype=np.uint64)
     lib().emu_host_fr_consts(_p(r), _p(z), _p(d), _p(wide), _p(w))
     return r, z, d, w
+
+
+def batch_invert(which, a, lanes):
+    a = np.array(a, dtype=np.uint64).reshape(-1, 4)
+    lib().emu_batch_invert(which, _p(a), ctypes.c_size_t(a.shape[0]), ctypes.c_size_t(lanes))
+    return a
+
+
+def recurrence(a, b, m, T, want_y=True):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    y = np.zeros_like(a) if want_y else None
+    head = np.zeros(4, dtype=np.uint64)
+    lib().emu_recurrence(_p(a), _p(y), ctypes.c_size_t(a.shape[0]), ctypes.c_size_t(m), ctypes.c_uint32(T),
+                         _p(np.ascontiguousarray(b)), _p(head))
+    return y, head
+
+
+def prefix_product(p, z0, m, T):
+    p = np.ascontiguousarray(p, dtype=np.uint64).reshape(-1, 4)
+    z = np.zeros_like(p)
+    lib().emu_prefix_product(_p(p), _p(z), ctypes.c_size_t(p.shape[0]), ctypes.c_size_t(m), ctypes.c_uint32(T),
+                             _p(np.ascontiguousarray(z0)))
+    return z

@@ -9,6 +9,7 @@
 #include "../../halo2-experiments_b200/csrc/ntt_plan.hpp"
 #include "../../halo2-experiments_b200/csrc/msm.cuh"
 #include "../../halo2-experiments_b200/csrc/msm_plan.hpp"
+#include "../../halo2-experiments_b200/csrc/poly.cuh"
 
 using namespace b200zk;
 
@@ -118,6 +119,31 @@ void emu_host_field_op(int which, int op, const uint64_t* a, const uint64_t* b, 
 void emu_host_fr_consts(uint64_t* root, uint64_t* zeta, uint64_t* delta, uint64_t* wide_in8, uint64_t* wide_out) {
     host::fr_root_of_unity().store(root); host::fr_zeta().store(zeta); host::fr_delta().store(delta);
     host::HFr::from_u512(wide_in8).store(wide_out);
+}
+
+
+// poly.cuh: launch sequences mirrored from poly.cu
+void emu_batch_invert(int which, fe_t* a, size_t n, size_t lanes) {
+    std::vector<fe_t> scratch(n ? n : 1);
+    for (size_t t = 0; t < lanes; ++t) {
+        if (which == 0) batch_invert_lane<Fr>(a, scratch.data(), n, t, lanes); else batch_invert_lane<Fq>(a, scratch.data(), n, t, lanes);
+    }
+}
+// y may be null; head_out receives y[0]
+void emu_recurrence(const fe_t* a, fe_t* y, size_t n, size_t m, uint32_t T, const fe_t* b, fe_t* head_out) {
+    size_t C = (n + m - 1) / m;
+    std::vector<fe_t> heads(C), carries(C), sm(2 * T);
+    for (size_t c = 0; c < C; ++c) recur_local_chunk(a, y, n, m, c, *b, heads.data());
+    recur_carries_block(heads.data(), carries.data(), n, m, *b, T, sm.data());
+    if (y) for (size_t c = 0; c < C; ++c) recur_apply_chunk(y, n, m, c, *b, carries.data());
+    *head_out = heads[0];
+}
+void emu_prefix_product(const fe_t* p, fe_t* z, size_t n, size_t m, uint32_t T, const fe_t* z0) {
+    size_t C = (n + m - 1) / m;
+    std::vector<fe_t> prods(C), sm(2 * T);
+    for (size_t c = 0; c < C; ++c) prodscan_chunk_product(p, n, m, c, prods.data());
+    prodscan_carries_block(prods.data(), C, *z0, T, sm.data());
+    for (size_t c = 0; c < C; ++c) prodscan_write_chunk(p, z, n, m, c, prods.data());
 }
 
 }  // extern "C"

@@ -157,3 +157,57 @@ def test_params_commit_matches_oracle(zk, backend, orc):
     g2, gl2 = params.read()
     assert np.array_equal(g2, g) and np.array_equal(gl2, gl)
     d.close(); params.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 1000, 4097, 1 << 16, (1 << 18) + 5])
+def test_poly_primitives_match_oracle(backend, orc, n):
+    from oracle import pyref
+    a = np.array(orc.random_fr(n, 120 + n % 13))
+    if n > 10:
+        a[3] = 0
+    x = orc.random_fr(1, 7)[0]
+    assert np.array_equal(backend.eval_polynomial(a, x), orc.eval_polynomial(a, x))
+    if n > 1:
+        assert np.array_equal(backend.kate_division(a, x), orc.kate_division(a, x))
+    assert np.array_equal(backend.batch_invert(a), orc.batch_invert(a))
+    z = backend.prefix_product(a, x)
+    # z[0] = x, z[i] = z[i-1] * a[i-1]
+    assert np.array_equal(z[0], x)
+    if n > 1:
+        assert np.array_equal(z[1:], orc.binop("mul", z[:-1], a[:-1]))
+
+
+def test_batch_invert_fq(backend, orc):
+    a = orc.ints_to_mont([5, 0, 7, 11, 13], orc.FQ)
+    assert np.array_equal(backend.batch_invert(a, field=1)[[0, 2, 3, 4]], orc.inv(a[[0, 2, 3, 4]], orc.FQ))
+
+
+@pytest.mark.parametrize("k", [1, 4, 9, 13])
+def test_params_setup_matches_oracle(zk, backend, orc, k):
+    """ParamsKZG::setup on the device vs the oracle's restatement, same secret s."""
+    s = orc.random_fr(1, 2000 + k)[0]
+    params = zk.ParamsKZG.setup(backend, k, s)
+    g, gl = params.read()
+    og, ogl = orc.params_setup(k, s)
+    assert np.array_equal(g, og)
+    assert np.array_equal(gl, ogl)
+    params.close()
+
+
+def test_params_setup_large_consistency(zk, backend, orc):
+    """k = 18: commit_lagrange(evals) == commit(coeffs) ties both device-generated bases together,
+    and g[i] spot-checks against the oracle."""
+    k = 18
+    s = orc.random_fr(1, 31337)[0]
+    params = zk.ParamsKZG.setup(backend, k, s)
+    d = zk.EvaluationDomain(backend, 3, k)
+    evals = orc.random_fr(1 << k, 55)
+    assert np.array_equal(params.commit_lagrange(evals), params.commit(d.lagrange_to_coeff(evals)))
+    g, _ = params.read()
+    assert orc.g1_on_curve(g[:: 1 << 10])
+    sp = orc.mont_to_ints(s)[0]
+    from oracle import pyref
+    idx = [0, 1, 2, 12345, (1 << k) - 1]
+    want = orc.g1_fixed_base_mul(orc.ints_to_mont([pow(sp, i, pyref.R_MOD) for i in idx]))
+    assert np.array_equal(g[idx], want)
+    d.close(); params.close()

@@ -121,3 +121,31 @@ def test_msm_all_same_small_scalars(orc):
         assert np.array_equal(emu.msm(S, bases, 6), orc.g1_batch_normalize(orc.best_multiexp(S, bases))[0])
     Z = orc.ints_to_mont([0] * n)
     assert np.array_equal(emu.msm(Z, bases, 0), np.zeros(8, dtype=np.uint64))
+
+
+def test_poly_primitives_structure(orc):
+    rnd = random.Random(300)
+    R = P.R_MOD
+    for n, m, T, lanes in ((1, 4, 2, 1), (7, 4, 2, 3), (64, 4, 4, 5), (203, 8, 4, 16), (1000, 16, 8, 40)):
+        vals = [rnd.randrange(R) for _ in range(n)]
+        if n > 5:
+            vals[3] = 0
+        A = orc.ints_to_mont(vals)
+        assert np.array_equal(emu.batch_invert(0, A, lanes), orc.batch_invert(A))
+        b = rnd.randrange(R)
+        B = orc.ints_to_mont([b])[0]
+        y, head = emu.recurrence(A, B, m, T)
+        assert np.array_equal(head, orc.eval_polynomial(A, B))
+        _, head2 = emu.recurrence(A, B, m, T, want_y=False)
+        assert np.array_equal(head2, head)
+        if n > 1:
+            # kate_division(a, b) = recurrence on a[1:]
+            q, _ = emu.recurrence(A[1:], B, m, T)
+            assert np.array_equal(q, orc.kate_division(A, B))
+        z0 = rnd.randrange(R)
+        want, run = [], z0
+        for v in vals:
+            want.append(run); run = run * v % R
+        assert orc.mont_to_ints(emu.prefix_product(A, orc.ints_to_mont([z0])[0], m, T)) == want
+    fq = orc.ints_to_mont([5, 0, 7, P.Q_MOD - 1], orc.FQ)
+    assert orc.mont_to_ints(emu.batch_invert(1, fq, 2), orc.FQ) == [pow(5, -1, P.Q_MOD), 0, pow(7, -1, P.Q_MOD), P.Q_MOD - 1]
