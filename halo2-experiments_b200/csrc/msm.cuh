@@ -79,27 +79,71 @@ ZK_D void msm_scatter_thread(const MsmArgs& a, uint32_t i) {
     });
 }
 
-// Single-block exclusive scan of counts[0..total) into offsets[0..total] and cursor.
-// sm: nthreads + 1 words.
-ZK_D void msm_scan_block(const MsmArgs& a, uint32_t nthreads, uint32_t* sm) {
+// Exclusive scan of counts[0..total) into offsets[0..total] and cursor, three launches:
+//   (1) per-block sums of SCAN_ITEMS consecutive counters, (2) single-block scan of the block
+//   sums, (3) per-block scan + block offset.  Each thread owns 8 consecutive counters.
+static constexpr uint32_t MSM_SCAN_PER_THREAD = 8;
+
+// Hillis-Steele inclusive scan of sm[0..T) (ping-pong in sm[0..2T)); returns the buffer index.
+ZK_D uint32_t msm_block_inclusive_scan(uint32_t* sm, uint32_t T) {
+    uint32_t cur = 0;
+    for (uint32_t d = 1; d < T; d <<= 1) {
+        ZK_PHASE_BEGIN(tid, T)
+        uint32_t v = sm[cur * T + tid];
+        if (tid >= d) v += sm[cur * T + tid - d];
+        sm[(cur ^ 1) * T + tid] = v;
+        ZK_PHASE_END
+        cur ^= 1;
+    }
+    return cur;
+}
+
+// (1) blocksums[bid] = sum of the block's counters.  sm: 2*T words.
+ZK_D void msm_scan_blocksum_block(const MsmArgs& a, uint32_t* blocksums, uint32_t bid, uint32_t T, uint32_t* sm) {
     const uint32_t total = a.nwin << (a.c - 1);
-    const uint32_t per = (total + nthreads - 1) / nthreads;
-    ZK_PHASE_BEGIN(tid, nthreads)
-    uint32_t s = 0, b = tid * per, e = b + per < total ? b + per : total;
-    for (uint32_t k = b; k < e; ++k) s += a.counts[k];
+    ZK_PHASE_BEGIN(tid, T)
+    uint32_t base = (bid * T + tid) * MSM_SCAN_PER_THREAD, s = 0;
+    for (uint32_t i = 0; i < MSM_SCAN_PER_THREAD; ++i) if (base + i < total) s += a.counts[base + i];
     sm[tid] = s;
     ZK_PHASE_END
-    ZK_PHASE_BEGIN(tid, nthreads)
-    if (tid == 0) {
-        uint32_t run = 0;
-        for (uint32_t t = 0; t < nthreads; ++t) { uint32_t v = sm[t]; sm[t] = run; run += v; }
-        sm[nthreads] = run;
-    }
+    uint32_t cur = msm_block_inclusive_scan(sm, T);
+    ZK_PHASE_BEGIN(tid, T)
+    if (tid == T - 1) blocksums[bid] = sm[cur * T + tid];
     ZK_PHASE_END
-    ZK_PHASE_BEGIN(tid, nthreads)
-    uint32_t run = sm[tid], b = tid * per, e = b + per < total ? b + per : total;
-    for (uint32_t k = b; k < e; ++k) { a.offsets[k] = run; a.cursor[k] = run; run += a.counts[k]; }
-    if (tid == 0) a.offsets[total] = sm[nthreads];
+}
+
+// (2) in-place exclusive scan of blocksums[0..nblocks) by one block; grand total to offsets[total].
+ZK_D void msm_scan_top_block(const MsmArgs& a, uint32_t* blocksums, uint32_t nblocks, uint32_t T, uint32_t* sm) {
+    const uint32_t total = a.nwin << (a.c - 1);
+    const uint32_t per = (nblocks + T - 1) / T;
+    ZK_PHASE_BEGIN(tid, T)
+    uint32_t s = 0, b = tid * per, e = b + per < nblocks ? b + per : nblocks;
+    for (uint32_t k = b; k < e; ++k) s += blocksums[k];
+    sm[tid] = s;
+    ZK_PHASE_END
+    uint32_t cur = msm_block_inclusive_scan(sm, T);
+    ZK_PHASE_BEGIN(tid, T)
+    uint32_t run = tid ? sm[cur * T + tid - 1] : 0, b = tid * per, e = b + per < nblocks ? b + per : nblocks;
+    for (uint32_t k = b; k < e; ++k) { uint32_t v = blocksums[k]; blocksums[k] = run; run += v; }
+    if (tid == T - 1) a.offsets[total] = sm[cur * T + tid];
+    ZK_PHASE_END
+}
+
+// (3) offsets / cursor for the block's counters.
+ZK_D void msm_scan_final_block(const MsmArgs& a, const uint32_t* blocksums, uint32_t bid, uint32_t T, uint32_t* sm) {
+    const uint32_t total = a.nwin << (a.c - 1);
+    ZK_PHASE_BEGIN(tid, T)
+    uint32_t base = (bid * T + tid) * MSM_SCAN_PER_THREAD, s = 0;
+    for (uint32_t i = 0; i < MSM_SCAN_PER_THREAD; ++i) if (base + i < total) s += a.counts[base + i];
+    sm[tid] = s;
+    ZK_PHASE_END
+    uint32_t cur = msm_block_inclusive_scan(sm, T);
+    ZK_PHASE_BEGIN(tid, T)
+    uint32_t base = (bid * T + tid) * MSM_SCAN_PER_THREAD;
+    uint32_t run = blocksums[bid] + (tid ? sm[cur * T + tid - 1] : 0);
+    for (uint32_t i = 0; i < MSM_SCAN_PER_THREAD; ++i) {
+        if (base + i < total) { a.offsets[base + i] = run; a.cursor[base + i] = run; run += a.counts[base + i]; }
+    }
     ZK_PHASE_END
 }
 

@@ -90,8 +90,14 @@ void emu_msm(const fe_t* scalars, const affine_t* bases, uint32_t n, int force_c
     a.counts = counts.data(); a.offsets = offsets.data(); a.cursor = cursor.data(); a.entries = entries.data();
     a.buckets = buckets.data(); a.partials = partials.data(); a.window_sums = wsum.data();
     for (uint32_t i = 0; i < n; ++i) msm_count_thread(a, i);
-    std::vector<uint32_t> sm(65);
-    msm_scan_block(a, 64, sm.data());
+    {   // mirrors the three scan launches of msm.cu with a small block size
+        const uint32_t T = 4, items = T * MSM_SCAN_PER_THREAD;
+        const uint32_t nb = (uint32_t)((s.nbuckets + items - 1) / items);
+        std::vector<uint32_t> bs(nb), sm(2 * T);
+        for (uint32_t b = 0; b < nb; ++b) msm_scan_blocksum_block(a, bs.data(), b, T, sm.data());
+        msm_scan_top_block(a, bs.data(), nb, T, sm.data());
+        for (uint32_t b = 0; b < nb; ++b) msm_scan_final_block(a, bs.data(), b, T, sm.data());
+    }
     for (uint32_t i = 0; i < n; ++i) msm_scatter_thread(a, i);
     for (uint32_t k = 0; k < s.nbuckets; ++k) msm_accumulate_thread(a, k);
     for (uint32_t g = 0; g < (s.nwin << s.log_t); ++g) msm_reduce_thread(a, g);
