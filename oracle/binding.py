@@ -250,6 +250,33 @@ def kate_division(a, b):
     return q
 
 
+def binop_scalar(op, a, s):
+    """a (op) s with the Fr scalar s broadcast."""
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    out = _arr(a.shape[0])
+    lib().orc_fr_binop_scalar({"add": 0, "sub": 1, "mul": 2}[op], _p(a), _p(np.ascontiguousarray(s, dtype=np.uint64)), _p(out),
+                              ctypes.c_size_t(a.shape[0]))
+    return out
+
+
+class XorShiftWide:
+    """rand_xorshift::XorShiftRng producing the 512-bit inputs of Fr::random, in draw order."""
+
+    def __init__(self, seed=bytes([0x59, 0x62, 0xbe, 0x5d, 0x76, 0x3d, 0x31, 0x8d, 0x17, 0xdb, 0x37, 0x32, 0x54, 0x06, 0xbc, 0xe5])):
+        self.state = np.frombuffer(bytes(seed), dtype=np.uint32).copy()
+
+    def draw(self, count):
+        out = np.zeros((count, 8), dtype=np.uint64)
+        lib().orc_xorshift_fill_wide(_p(self.state), _p(out), ctypes.c_size_t(count))
+        return out
+
+
+def sort_canonical(raw):
+    raw = np.array(raw, dtype=np.uint64).reshape(-1, 4)
+    lib().orc_sort_canonical(_p(raw), ctypes.c_size_t(raw.shape[0]))
+    return raw
+
+
 class Domain:
     """poly::EvaluationDomain<Fr>::new(j, k)."""
     _FIELDS = ["omega", "omega_inv", "extended_omega", "extended_omega_inv", "g_coset", "g_coset_inv",

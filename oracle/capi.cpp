@@ -5,6 +5,7 @@
 // Fr / Fq), points as G1Affine {x,y} (64 B) or G1 {x,y,z} (96 B).
 #include "arith.hpp"
 #include <cstdio>
+#include <algorithm>
 
 using namespace orc;
 
@@ -163,6 +164,42 @@ void orc_domain_extended_to_coeff(void* d, uint64_t* a) { ((Domain*)d)->extended
 void orc_domain_divide_by_vanishing_poly(void* d, uint64_t* a) { ((Domain*)d)->divide_by_vanishing_poly((Fr*)a); }
 void orc_domain_rotate_omega(void* d, const uint64_t* x, int rot, uint64_t* out) {
     *(Fr*)out = ((Domain*)d)->rotate_omega(*(const Fr*)x, rot);
+}
+
+}  // extern "C"
+
+// ---- extras used by oracle/prover.py (test infrastructure) ----
+extern "C" {
+
+// op: 0 a+s, 1 a-s, 2 a*s  with a scalar s broadcast over n elements (Fr)
+void orc_fr_binop_scalar(int op, const uint64_t* a, const uint64_t* s, uint64_t* out, size_t n) {
+    init_fields();
+    const Fr* A = (const Fr*)a; Fr S = *(const Fr*)s; Fr* O = (Fr*)out;
+    parallelize(n, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) O[i] = op == 0 ? A[i] + S : op == 1 ? A[i] - S : A[i] * S;
+    });
+}
+
+// rand_xorshift::XorShiftRng: fills count x 8 u64 (the 512-bit inputs of Fr::random), advancing state[4]
+void orc_xorshift_fill_wide(uint32_t* state, uint64_t* out, size_t count) {
+    uint32_t x = state[0], y = state[1], z = state[2], w = state[3];
+    for (size_t i = 0; i < count * 8; ++i) {
+        uint32_t lo, hi;
+        { uint32_t t = x ^ (x << 11); x = y; y = z; z = w; w = w ^ (w >> 19) ^ (t ^ (t >> 8)); lo = w; }
+        { uint32_t t = x ^ (x << 11); x = y; y = z; z = w; w = w ^ (w >> 19) ^ (t ^ (t >> 8)); hi = w; }
+        out[i] = (uint64_t)lo | ((uint64_t)hi << 32);
+    }
+    state[0] = x; state[1] = y; state[2] = z; state[3] = w;
+}
+
+// sort rows of canonical 4xu64 values ascending by numeric value (halo2curves `Ord for Fr`)
+void orc_sort_canonical(uint64_t* a, size_t n) {
+    typedef std::array<uint64_t, 4> K;
+    K* k = (K*)a;
+    std::sort(k, k + n, [](const K& x, const K& y) {
+        for (int i = 3; i >= 0; --i) if (x[i] != y[i]) return x[i] < y[i];
+        return false;
+    });
 }
 
 }  // extern "C"

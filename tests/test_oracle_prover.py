@@ -1,0 +1,75 @@
+"""CPU: the oracle prover (restatement of halo2 create_proof) emits proofs that the independent
+restatement of the verifier accepts, and tampering is rejected.  Mirrors the only hot-path test
+of the reference, test_full_prover (/root/reference/src/circuits/merkle_sum_tree.rs:345-358,
+assertion at /root/reference/src/circuits/utils.rs:56-63: verify_proof(..).is_ok())."""
+import numpy as np
+import pytest
+
+from oracle import prover as OP
+from oracle import pyref as P
+
+
+def _job(zk, name, k):
+    import importlib
+    synth = importlib.import_module(zk.__name__ + ".circuits_synth")
+    return getattr(synth, name)(k)
+
+
+def _prove(orc, job, seed_s=77):
+    s = orc.random_fr(1, seed_s)[0]
+    g, gl = orc.params_setup(job.k, s)
+    pk = OP.keygen_pk(job.cs, job.k, job.fixed, job.map_col, job.map_row)
+    wide = orc.XorShiftWide().draw(OP.rng_draws_needed(job.cs, job.k))
+    proof, trace = OP.create_proof(g, gl, pk, job.advice, job.instances, wide, job.transcript_repr)
+    return s, g, pk, proof, trace
+
+
+@pytest.mark.parametrize("name,k", [("small", 5), ("v3_shaped", 6), ("small", 7)])
+def test_oracle_proof_verifies(zk, orc, name, k):
+    job = _job(zk, name, k)
+    cs = job.cs
+    assert cs.blinding_factors() == 5 and cs.degree() == 6
+    s, g, pk, proof, trace = _prove(orc, job)
+    A, L, S, q = cs.num_advice, len(cs.lookups), cs.num_permutation_sets(), cs.degree() - 1
+    n_evals = len(cs.advice_queries) + len(cs.fixed_queries) + 1 + len(cs.permutation) + (3 * S - 1) + 5 * L
+    assert len(proof) == 32 * (A + 2 * L + S + L + 1 + q + n_evals + 2)
+    assert OP.verify_full(orc.mont_to_ints(s)[0], g, pk, job.instances, proof, job.transcript_repr)
+    # deterministic
+    _, _, _, proof2, _ = _prove(orc, job)
+    assert proof2 == proof
+    # tampered proof / wrong public input are rejected
+    bad = bytearray(proof)
+    off = 32 * (A + 2 * L + S + L + 1 + q)          # first advice evaluation
+    bad[off] ^= 1
+    ok = True
+    try:
+        ok = OP.verify_full(orc.mont_to_ints(s)[0], g, pk, job.instances, bytes(bad), job.transcript_repr)
+    except AssertionError:
+        ok = False
+    assert not ok
+    wrong = [[v + 1 for v in job.instances[0]]]
+    assert not OP.verify_full(orc.mont_to_ints(s)[0], g, pk, wrong, proof, job.transcript_repr)
+
+
+def test_mst_shape_counts(zk):
+    """The synthetic job has the MST shape of SURVEY.md §8: A=20, L=8, P=16, d=6, bf=5, S=4."""
+    job = _job(zk, "mst_shaped", 6)
+    cs = job.cs
+    assert (cs.num_advice, len(cs.lookups), len(cs.permutation)) == (20, 8, 16)
+    assert (cs.degree(), cs.blinding_factors(), cs.num_permutation_sets()) == (6, 5, 4)
+    blob = cs.to_blob(6)
+    assert blob[0] == 0x324B5A42 and blob[2] == 6 and blob[3] == 20
+
+
+def test_unsatisfied_witness_is_rejected(zk, orc):
+    job = _job(zk, "small", 5)
+    adv = np.array(job.advice[2])
+    adv[3] = orc.ints_to_mont([5])[0]                # breaks the bool gate
+    job.advice[2] = adv
+    s, g, pk, proof, _ = _prove(orc, job)
+    ok = True
+    try:
+        ok = OP.verify_full(orc.mont_to_ints(s)[0], g, pk, job.instances, proof, job.transcript_repr)
+    except AssertionError:
+        ok = False
+    assert not ok
