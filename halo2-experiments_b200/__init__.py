@@ -277,6 +277,85 @@ class EvaluationDomain:
         self.backend._check(lib().b200zk_divide_by_vanishing_poly_dev(self._h, d_ext.ptr))
 
 
+ESYNTH = -5
+
+
+def _ptr_array(arrays):
+    """(void* const*) over a list of contiguous numpy arrays (kept alive by the caller)."""
+    arr = (ctypes.c_void_p * max(len(arrays), 1))()
+    for i, a in enumerate(arrays):
+        arr[i] = a.ctypes.data
+    return arr
+
+
+class ProvingKey:
+    """plonk::ProvingKey built by keygen_pk, resident on the device (b200zk_pk_create)."""
+
+    def __init__(self, params, cs, k, fixed_columns, map_col, map_row):
+        self.params, self.backend, self.cs, self.k, self.n = params, params.backend, cs, k, 1 << k
+        blob = np.ascontiguousarray(cs.to_blob(k), dtype=np.uint32)
+        fixed = [np.ascontiguousarray(f, dtype=np.uint64).reshape(self.n, 4) for f in fixed_columns]
+        if len(fixed) != cs.num_fixed:
+            raise B200zkError("fixed column count does not match the constraint system")
+        mc = None if map_col is None else np.ascontiguousarray(map_col, dtype=np.uint32)
+        mr = None if map_row is None else np.ascontiguousarray(map_row, dtype=np.uint32)
+        self._h = ctypes.c_void_p()
+        L = lib()
+        L.b200zk_pk_proof_size.restype = ctypes.c_size_t
+        L.b200zk_pk_rng_draws.restype = ctypes.c_size_t
+        L.b200zk_pk_blinding_factors.restype = ctypes.c_uint32
+        L.b200zk_pk_degree.restype = ctypes.c_uint32
+        L.b200zk_pk_destroy.restype = None
+        self.backend._check(L.b200zk_pk_create(params._h, _p(blob), ctypes.c_size_t(blob.shape[0]), _ptr_array(fixed),
+                                               _p(mc), _p(mr), ctypes.byref(self._h)))
+        self.proof_size = int(L.b200zk_pk_proof_size(self._h))
+        self.rng_draws = int(L.b200zk_pk_rng_draws(self._h))
+        self.blinding_factors = int(L.b200zk_pk_blinding_factors(self._h))
+        self.degree = int(L.b200zk_pk_degree(self._h))
+
+    def close(self):
+        if self._h:
+            lib().b200zk_pk_destroy(self._h)
+            self._h = None
+
+    def _instances(self, instances):
+        cols = [np.ascontiguousarray(c, dtype=np.uint64).reshape(-1, 4) for c in instances]
+        lens = np.array([c.shape[0] for c in cols], dtype=np.uint32)
+        keep = [c if c.shape[0] else np.zeros((1, 4), dtype=np.uint64) for c in cols]
+        return keep, _ptr_array(keep), lens
+
+    def create_proof(self, advice_columns, instances, rng_wide, transcript_repr):
+        """plonk::create_proof for one circuit.  advice_columns: A arrays (n,4) as synthesised
+        (unblinded); instances: list of (len,4) Montgomery arrays; rng_wide: (rng_draws, 8) uint64,
+        the 512-bit inputs of each Fr::random call in order; transcript_repr: Fr (4,)."""
+        adv = [np.ascontiguousarray(a, dtype=np.uint64).reshape(self.n, 4) for a in advice_columns]
+        if len(adv) != self.cs.num_advice:
+            raise B200zkError("advice column count does not match the constraint system")
+        keep, inst_ptrs, lens = self._instances(instances)
+        wide = np.ascontiguousarray(rng_wide, dtype=np.uint64).reshape(-1, 8)
+        if wide.shape[0] < self.rng_draws:
+            raise B200zkError(f"rng stream too short: need {self.rng_draws} draws")
+        out = np.zeros(self.proof_size, dtype=np.uint8)
+        ln = ctypes.c_size_t()
+        self.backend._check(lib().b200zk_create_proof(self._h, _ptr_array(adv), inst_ptrs, _p(lens), _p(wide), _p(_fr(transcript_repr, 1)),
+                                                       _p(out), ctypes.c_size_t(out.shape[0]), ctypes.byref(ln)))
+        return bytes(out[: ln.value])
+
+    def create_proof_dev(self, d_advice, instances, d_rng_wide, transcript_repr):
+        """Same with the A x n advice block and the rng stream already in device memory."""
+        keep, inst_ptrs, lens = self._instances(instances)
+        out = np.zeros(self.proof_size, dtype=np.uint8)
+        ln = ctypes.c_size_t()
+        self.backend._check(lib().b200zk_create_proof_dev(self._h, d_advice.ptr, inst_ptrs, _p(lens), d_rng_wide.ptr, _p(_fr(transcript_repr, 1)),
+                                                           _p(out), ctypes.c_size_t(out.shape[0]), ctypes.byref(ln)))
+        return bytes(out[: ln.value])
+
+    def last_phase_ms(self):
+        out = (ctypes.c_float * 7)()
+        self.backend._check(lib().b200zk_pk_last_phase_ms(self._h, out))
+        return dict(zip(["msm", "ntt", "quotient", "lookup", "permutation", "open", "other"], [float(x) for x in out]))
+
+
 class ParamsKZG:
     """poly::kzg::commitment::ParamsKZG<Bn256> with the SRS resident in HBM."""
 

@@ -28,21 +28,6 @@ int32_t ws_reserve(b200zk_ctx* ctx, Workspace& w, size_t bytes) {
 
 }  // namespace b200zk
 
-struct b200zk_domain {
-    b200zk_ctx* ctx;
-    uint32_t k, extended_k, quotient_poly_degree;
-    HFr omega, omega_inv, extended_omega, extended_omega_inv, g_coset, g_coset_inv;
-    HFr ifft_divisor, extended_ifft_divisor, barycentric_weight;
-    fe_t* d_t_evaluations;           // 2^(extended_k - k), already inverted
-};
-
-struct b200zk_params {
-    b200zk_ctx* ctx;
-    uint32_t k;
-    affine_t* d_g;
-    affine_t* d_g_lagrange;
-};
-
 static void write_g1(const host::HAffine& a, void* out_g1) {
     uint64_t* o = (uint64_t*)out_g1;
     if (a.x.is_zero() && a.y.is_zero()) {           // G1::identity() = (0, 1, 0)

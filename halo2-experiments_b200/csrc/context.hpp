@@ -39,9 +39,24 @@ struct b200zk_ctx {
     int sm_count = 148;
     int msm_force_c = 0;
     std::map<std::array<uint64_t, 5>, b200zk::NttPlan> ntt_plans;     // key: log_n + omega limbs
-    b200zk::Workspace ntt_scratch, msm_ws, io_a, io_b, poly_ws, poly_heads, setup_ws;
+    b200zk::Workspace ntt_scratch, msm_ws, io_a, io_b, poly_ws, poly_heads, setup_ws, lookup_ws;
     b200zk::affine_t* d_gen_table = nullptr;                          // fixed-base table of the G1 generator (setup.cu)
     void* pinned = nullptr;                                            // small pinned staging (results)
+};
+
+struct b200zk_domain {
+    b200zk_ctx* ctx;
+    uint32_t k, extended_k, quotient_poly_degree;
+    b200zk::host::HFr omega, omega_inv, extended_omega, extended_omega_inv, g_coset, g_coset_inv;
+    b200zk::host::HFr ifft_divisor, extended_ifft_divisor, barycentric_weight;
+    b200zk::fe_t* d_t_evaluations;           // 2^(extended_k - k), already inverted
+};
+
+struct b200zk_params {
+    b200zk_ctx* ctx;
+    uint32_t k;
+    b200zk::affine_t* d_g;
+    b200zk::affine_t* d_g_lagrange;
 };
 
 namespace b200zk {
@@ -83,5 +98,11 @@ int32_t prefix_product_run(b200zk_ctx* ctx, const fe_t* d_p, fe_t* d_z, size_t n
 // setup.cu -------------------------------------------------------------------
 // ParamsKZG::setup bases on the device: g[i] = [s^i]G, g_lagrange[i] = [l_i(s)]G
 int32_t params_setup_run(b200zk_ctx* ctx, uint32_t k, const host::HFr& s, affine_t* d_g, affine_t* d_g_lagrange);
+
+// out[i] = base^i, i < n (two-level tables built on the device)
+int32_t powers_run(b200zk_ctx* ctx, const host::HFr& base, size_t n, fe_t* d_out);
+
+// lookup_sort.cu --------------------------------------------------------------
+int32_t lookup_permute_run(b200zk_ctx* ctx, const fe_t* d_in, const fe_t* d_tab, uint32_t u, fe_t* d_pin, fe_t* d_ptab, uint32_t* d_err);
 
 }  // namespace b200zk

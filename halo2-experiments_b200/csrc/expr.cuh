@@ -1,0 +1,89 @@
+// Row-wise expression evaluation: the device counterpart of halo2_proofs v2023_02_02
+// plonk/evaluation.rs (`GraphEvaluator::evaluate`, `evaluate`) — reached from create_proof at
+// /root/reference/src/circuits/utils.rs:40-48.  One thread evaluates the whole program for one
+// row of the (extended or Lagrange) domain, so every column element is read once and all
+// intermediates stay on chip.
+//
+// The program is the constraint system's expressions in postfix order over a small value
+// stack, plus FOLD instructions that implement the Horner folds upstream expresses as
+// Calculation::Horner:  acc <- acc * factor + pop().
+//   custom gates : every gate polynomial followed by FOLD(acc0, y)
+//   lookups      : input expressions with FOLD(acc0, theta), table expressions with FOLD(acc1, theta)
+// Upstream's graph evaluator orders and deduplicates the same arithmetic differently; the value
+// per row is the same field element, hence bit-exact.
+#pragma once
+#include "field.cuh"
+
+namespace b200zk {
+
+enum : uint32_t { EX_CONST = 0, EX_FIXED = 1, EX_ADVICE = 2, EX_INSTANCE = 3, EX_NEG = 4, EX_ADD = 5, EX_MUL = 6, EX_SCALE = 7, EX_FOLD = 8 };
+enum : uint32_t { EXF_THETA = 0, EXF_BETA = 1, EXF_GAMMA = 2, EXF_Y = 3 };
+// output modes
+enum : uint32_t {
+    EXM_ACC0 = 0,        // out0[idx] = acc0                                  (custom gates: h)
+    EXM_ACC01 = 1,       // out0[idx] = acc0, out1[idx] = acc1                (lookup compressed input / table)
+    EXM_LOOKUP_PROD = 2  // out0[idx] = (acc0 + beta) * (acc1 + gamma)        (lookup "table_value" in evaluate_h)
+};
+
+static constexpr int EX_STACK = 16;
+
+struct ExprArgs {
+    const uint32_t* prog;
+    uint32_t prog_len;
+    const fe_t* consts;                 // Montgomery form
+    const fe_t* const* fixed;           // device arrays of column base pointers
+    const fe_t* const* advice;
+    const fe_t* const* instance;
+    const int32_t* q_fixed;             // (column, rotation) pairs
+    const int32_t* q_advice;
+    const int32_t* q_instance;
+    uint32_t log_size;                  // rows = 2^log_size
+    uint32_t rot_scale;                 // 1 on the Lagrange domain, 2^(extended_k - k) on the extended one
+    fe_t factors[4];                    // theta, beta, gamma, y
+    uint32_t mode;
+    fe_t* out0;
+    fe_t* out1;
+};
+
+ZK_D fe_t expr_load(const fe_t* const* cols, const int32_t* q, uint32_t qi, uint32_t idx, const ExprArgs& a) {
+    int32_t col = q[2 * qi], rot = q[2 * qi + 1];
+    uint32_t mask = (1u << a.log_size) - 1;
+    uint32_t r = (idx + (uint32_t)(rot * (int32_t)a.rot_scale)) & mask;      // rem_euclid for a power-of-two size
+    return cols[col][r];
+}
+
+ZK_D void expr_eval_row(const ExprArgs& a, uint32_t idx) {
+    fe_t stk[EX_STACK];
+    int sp = 0;
+    fe_t acc0 = Fr::zero(), acc1 = Fr::zero();
+    for (uint32_t pc = 0; pc < a.prog_len; ++pc) {
+        uint32_t w = a.prog[pc], op = w & 0xff, arg = w >> 8;
+        switch (op) {
+            case EX_CONST: stk[sp++] = a.consts[arg]; break;
+            case EX_FIXED: stk[sp++] = expr_load(a.fixed, a.q_fixed, arg, idx, a); break;
+            case EX_ADVICE: stk[sp++] = expr_load(a.advice, a.q_advice, arg, idx, a); break;
+            case EX_INSTANCE: stk[sp++] = expr_load(a.instance, a.q_instance, arg, idx, a); break;
+            case EX_NEG: stk[sp - 1] = Fr::neg(stk[sp - 1]); break;
+            case EX_ADD: stk[sp - 2] = Fr::add(stk[sp - 2], stk[sp - 1]); --sp; break;
+            case EX_MUL: stk[sp - 2] = Fr::mul(stk[sp - 2], stk[sp - 1]); --sp; break;
+            case EX_SCALE: stk[sp - 1] = Fr::mul(stk[sp - 1], a.consts[arg]); break;
+            case EX_FOLD: {
+                fe_t v = stk[--sp];
+                const fe_t f = a.factors[arg & 0xf];
+                if ((arg >> 4) == 0) acc0 = Fr::add(Fr::mul(acc0, f), v);
+                else acc1 = Fr::add(Fr::mul(acc1, f), v);
+                break;
+            }
+            default: break;
+        }
+    }
+    if (a.mode == EXM_ACC0) {
+        a.out0[idx] = acc0;
+    } else if (a.mode == EXM_ACC01) {
+        a.out0[idx] = acc0; a.out1[idx] = acc1;
+    } else {
+        a.out0[idx] = Fr::mul(Fr::add(acc0, a.factors[EXF_BETA]), Fr::add(acc1, a.factors[EXF_GAMMA]));
+    }
+}
+
+}  // namespace b200zk

@@ -35,6 +35,11 @@ struct FrCfg {
                                    0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
         return t[i];
     }
+    ZK_D static constexpr uint32_t r3(int i) {           // R^3 mod r (from_u512 / Fr::random)
+        constexpr uint32_t t[8] = {0xb4bf0040u, 0x5e94d8e1u, 0x1cfbb6b8u, 0x2a489cbeu,
+                                   0xa19fcfedu, 0x893cc664u, 0x7fcc657cu, 0x0cf8594bu};
+        return t[i];
+    }
 };
 
 struct FqCfg {

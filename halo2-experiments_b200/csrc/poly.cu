@@ -80,6 +80,34 @@ int32_t recurrence_run(b200zk_ctx* ctx, const fe_t* d_a, fe_t* d_y, size_t n, co
     return B200ZK_OK;
 }
 
+__global__ void __launch_bounds__(POLY_THREADS) pow_table_kernel(fe_t* out, const fe_t base, uint32_t count, uint32_t shift) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = Fr::pow_u64(base, (unsigned long long)i << shift);
+}
+__global__ void __launch_bounds__(POLY_THREADS) pow_combine_kernel(fe_t* out, size_t n, const fe_t* lo, const fe_t* hi, uint32_t bits) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe_t a = lo[i & ((1u << bits) - 1)], b = hi[i >> bits];
+    out[i] = Fr::mul(a, b);
+}
+
+// out[i] = base^i: base^i = lo[i mod 2^b] * hi[i >> b]
+int32_t powers_run(b200zk_ctx* ctx, const host::HFr& base, size_t n, fe_t* d_out) {
+    if (n == 0) return B200ZK_OK;
+    uint32_t lg = 0; while (((size_t)1 << lg) < n) ++lg;
+    uint32_t bits = (lg + 1) / 2;
+    size_t n_lo = (size_t)1 << bits, n_hi = ((n - 1) >> bits) + 1;
+    ZK_TRY(ws_reserve(ctx, ctx->poly_heads, (n_lo + n_hi) * sizeof(fe_t)));
+    fe_t* lo = (fe_t*)ctx->poly_heads.p;
+    fe_t* hi = lo + n_lo;
+    pow_table_kernel<<<nblocks(n_lo, POLY_THREADS), POLY_THREADS, 0, ctx->stream>>>(lo, to_dev(base), (uint32_t)n_lo, 0);
+    pow_table_kernel<<<nblocks(n_hi, POLY_THREADS), POLY_THREADS, 0, ctx->stream>>>(hi, to_dev(base), (uint32_t)n_hi, bits);
+    pow_combine_kernel<<<nblocks(n, POLY_THREADS), POLY_THREADS, 0, ctx->stream>>>(d_out, n, lo, hi, bits);
+    ctx->launches += 3;
+    ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
 // z[0] = z0, z[i] = z[i-1] * p[i-1] for i < n  (z may alias p)
 int32_t prefix_product_run(b200zk_ctx* ctx, const fe_t* d_p, fe_t* d_z, size_t n, const host::HFr& z0) {
     if (n == 0) return B200ZK_OK;

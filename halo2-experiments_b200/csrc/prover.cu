@@ -1,0 +1,970 @@
+// keygen_pk + create_proof on the device: halo2_proofs v2023_02_02 src/plonk/keygen.rs and
+// src/plonk/prover.rs (+ lookup/permutation/vanishing provers, evaluation.rs, shplonk prover),
+// the calls `full_prover` makes at /root/reference/src/circuits/utils.rs:35 and :40-48.
+// The host side of this file only sequences launches, runs the Blake2b transcript between phases
+// and does O(#queries) scalar work; every O(n) step is a kernel.  Step numbers refer to
+// SURVEY.md §3.2.
+#include "context.hpp"
+#include "expr.cuh"
+#include "prover_kernels.cuh"
+#include "transcript.hpp"
+#include <algorithm>
+#include <map>
+#include <new>
+#include <set>
+
+using namespace b200zk;
+using host::HAffine;
+using host::HFr;
+
+namespace b200zk {
+
+static constexpr uint32_t PK_THREADS = 128;
+static unsigned nb(size_t n, unsigned t = PK_THREADS) { return (unsigned)((n + t - 1) / t); }
+static fe_t to_dev(const HFr& x) { fe_t r; memcpy(r.l, x.v, 32); return r; }
+
+// ------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(PK_THREADS) expr_kernel(const ExprArgs a) {
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < (1u << a.log_size)) expr_eval_row(a, idx);
+}
+__global__ void __launch_bounds__(PK_THREADS) from_u512_kernel(const uint32_t* wide, fe_t* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = from_u512_row(wide + 16 * i);
+}
+__global__ void __launch_bounds__(PK_THREADS) perm_den_kernel(const PermLagArgs a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) perm_denominator_row(a, i);
+}
+__global__ void __launch_bounds__(PK_THREADS) perm_num_kernel(const PermLagArgs a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) perm_numerator_row(a, i);
+}
+__global__ void __launch_bounds__(PK_THREADS) lookup_den_kernel(const LookupProdArgs a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) lookup_den_row(a, i);
+}
+__global__ void __launch_bounds__(PK_THREADS) lookup_num_kernel(const LookupProdArgs a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) lookup_num_row(a, i);
+}
+__global__ void __launch_bounds__(PK_THREADS) quot_perm_a_kernel(const QuotPermAArgs a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (1u << a.log_ext)) quot_perm_a_row(a, i);
+}
+__global__ void __launch_bounds__(PK_THREADS) quot_perm_b_kernel(const QuotPermBArgs a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (1u << a.log_ext)) quot_perm_b_row(a, i);
+}
+__global__ void __launch_bounds__(PK_THREADS) quot_lookup_kernel(const QuotLookupArgs a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (1u << a.log_ext)) quot_lookup_row(a, i);
+}
+__global__ void __launch_bounds__(PK_THREADS) fold_pieces_kernel(const fe_t* pieces, uint32_t npieces, size_t n, const fe_t xn, fe_t* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fold_pieces_row(pieces, npieces, n, xn, out, i);
+}
+__global__ void __launch_bounds__(PK_THREADS) axpy_kernel(fe_t* acc, const fe_t* p, const fe_t s, size_t n, int init) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) axpy_row(acc, p, s, i, init != 0);
+}
+__global__ void __launch_bounds__(PK_THREADS) scale_kernel(fe_t* a, const fe_t s, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) scale_row(a, s, i);
+}
+struct LowCoeffs { fe_t c[8]; uint32_t m; };
+__global__ void sub_low_kernel(fe_t* a, const LowCoeffs lc) {
+    uint32_t i = threadIdx.x;
+    if (i < lc.m) { fe_t v = a[i]; a[i] = Fr::sub(v, lc.c[i]); }
+}
+__global__ void __launch_bounds__(PK_THREADS) one_minus_sum_kernel(const fe_t* a, const fe_t* b, fe_t* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) one_minus_sum_row(a, b, out, i);
+}
+__global__ void __launch_bounds__(PK_THREADS) sigma_kernel(const uint32_t* mc, const uint32_t* mr, const fe_t* dp, const fe_t* op, fe_t* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sigma_row(mc, mr, dp, op, out, i);
+}
+
+// ------------------------------------------------------------------ constraint system
+struct CsDesc {
+    uint32_t k = 0, A = 0, F = 0, I = 0, bf = 0, degree = 0;
+    std::vector<int32_t> adv_q, fix_q, inst_q;                 // (col, rot) flattened
+    std::vector<std::pair<uint32_t, uint32_t>> perm;            // (type, index)
+    std::vector<std::pair<uint32_t, uint32_t>> gates;           // (off, len) into prog
+    struct Lk { std::vector<std::pair<uint32_t, uint32_t>> ins, tabs; };
+    std::vector<Lk> lookups;
+    std::vector<HFr> consts;                                    // Montgomery
+    std::vector<uint32_t> prog;
+};
+
+static uint32_t expr_degree(const CsDesc& cs, uint32_t off, uint32_t len) {
+    std::vector<uint32_t> st;
+    for (uint32_t i = off; i < off + len; ++i) {
+        uint32_t op = cs.prog[i] & 0xff;
+        if (op == EX_CONST) st.push_back(0);
+        else if (op == EX_FIXED || op == EX_ADVICE || op == EX_INSTANCE) st.push_back(1);
+        else if (op == EX_ADD) { uint32_t b = st.back(); st.pop_back(); st.back() = std::max(st.back(), b); }
+        else if (op == EX_MUL) { uint32_t b = st.back(); st.pop_back(); st.back() += b; }
+    }
+    return st.empty() ? 0 : st.back();
+}
+
+// circuit.rs: blinding_factors() and degree()
+static void derive_cs(CsDesc& cs) {
+    std::map<int32_t, uint32_t> per_col;
+    for (size_t i = 0; i < cs.adv_q.size(); i += 2) per_col[cs.adv_q[i]]++;
+    uint32_t factors = 0;
+    for (auto& kv : per_col) factors = std::max(factors, kv.second);
+    cs.bf = std::max(3u, factors) + 2;
+    uint32_t degree = 3;
+    for (auto& lk : cs.lookups) {
+        uint32_t di = 1, dt = 1;
+        for (auto& e : lk.ins) di = std::max(di, expr_degree(cs, e.first, e.second));
+        for (auto& e : lk.tabs) dt = std::max(dt, expr_degree(cs, e.first, e.second));
+        degree = std::max(degree, std::max(4u, 2 + di + dt));
+    }
+    for (auto& g : cs.gates) degree = std::max(degree, expr_degree(cs, g.first, g.second));
+    cs.degree = degree;
+}
+
+static bool parse_cs(const uint32_t* w, size_t nw, CsDesc& cs) {
+    if (nw < 16 || w[0] != 0x324B5A42u || w[1] != 1) return false;
+    cs.k = w[2]; cs.A = w[3]; cs.F = w[4]; cs.I = w[5];
+    uint32_t naq = w[6], nfq = w[7], niq = w[8], ng = w[9], nl = w[10], np = w[11], nc = w[12], nprog = w[13];
+    size_t p = 16;
+    auto need = [&](size_t c) { return p + c <= nw; };
+    auto rd_q = [&](std::vector<int32_t>& q, uint32_t cnt) {
+        if (!need(2 * (size_t)cnt)) return false;
+        for (uint32_t i = 0; i < 2 * cnt; ++i) q.push_back((int32_t)w[p++]);
+        return true;
+    };
+    if (!rd_q(cs.adv_q, naq) || !rd_q(cs.fix_q, nfq) || !rd_q(cs.inst_q, niq)) return false;
+    if (!need(2 * (size_t)np)) return false;
+    for (uint32_t i = 0; i < np; ++i) { cs.perm.push_back({w[p], w[p + 1]}); p += 2; }
+    if (!need(2 * (size_t)ng)) return false;
+    for (uint32_t i = 0; i < ng; ++i) { cs.gates.push_back({w[p], w[p + 1]}); p += 2; }
+    for (uint32_t i = 0; i < nl; ++i) {
+        if (!need(1)) return false;
+        uint32_t m = w[p++];
+        if (!need(4 * (size_t)m)) return false;
+        CsDesc::Lk lk;
+        for (uint32_t j = 0; j < m; ++j) { lk.ins.push_back({w[p], w[p + 1]}); p += 2; }
+        for (uint32_t j = 0; j < m; ++j) { lk.tabs.push_back({w[p], w[p + 1]}); p += 2; }
+        cs.lookups.push_back(lk);
+    }
+    if (!need(8 * (size_t)nc + nprog)) return false;
+    for (uint32_t i = 0; i < nc; ++i) {
+        uint64_t c[4];
+        for (int j = 0; j < 4; ++j) c[j] = (uint64_t)w[p + 2 * j] | ((uint64_t)w[p + 2 * j + 1] << 32);
+        cs.consts.push_back(HFr::from_canonical(c));
+        p += 8;
+    }
+    cs.prog.assign(w + p, w + p + nprog);
+    // validate indices
+    for (size_t i = 0; i < cs.adv_q.size(); i += 2) if ((uint32_t)cs.adv_q[i] >= cs.A) return false;
+    for (size_t i = 0; i < cs.fix_q.size(); i += 2) if ((uint32_t)cs.fix_q[i] >= cs.F) return false;
+    for (size_t i = 0; i < cs.inst_q.size(); i += 2) if ((uint32_t)cs.inst_q[i] >= cs.I) return false;
+    for (uint32_t word : cs.prog) {
+        uint32_t op = word & 0xff, arg = word >> 8;
+        if (op > EX_SCALE) return false;
+        if ((op == EX_CONST || op == EX_SCALE) && arg >= nc) return false;
+        if (op == EX_FIXED && arg >= nfq) return false;
+        if (op == EX_ADVICE && arg >= naq) return false;
+        if (op == EX_INSTANCE && arg >= niq) return false;
+    }
+    derive_cs(cs);
+    if (cs.bf != w[14] || cs.degree != w[15]) return false;      // frontend and library must agree
+    return true;
+}
+
+}  // namespace b200zk
+
+// ------------------------------------------------------------------ proving key
+struct b200zk_pk {
+    b200zk_ctx* ctx = nullptr;
+    b200zk_params* params = nullptr;
+    b200zk_domain* dom = nullptr;
+    CsDesc cs;
+    uint32_t n = 0, ext_n = 0, S = 0, chunk = 0, q = 0, L = 0, P = 0;
+    fe_t *fixed_values = nullptr, *fixed_polys = nullptr, *fixed_cosets = nullptr;
+    fe_t *perm_values = nullptr, *perm_polys = nullptr, *perm_cosets = nullptr;
+    fe_t *l0 = nullptr, *l_last = nullptr, *l_active = nullptr;
+    fe_t *omega_pows = nullptr, *ew_lo = nullptr, *ew_hi = nullptr;
+    uint32_t ew_bits = 0;
+    // device program data
+    uint32_t* d_prog = nullptr;                       // gates program | lookup programs
+    uint32_t gates_len = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> lookup_prog;     // (off, len) into d_prog
+    fe_t* d_consts = nullptr;
+    int32_t *d_q_adv = nullptr, *d_q_fix = nullptr, *d_q_inst = nullptr;
+    const fe_t** d_ptrs = nullptr;                    // pointer tables, see PtrTab
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    uint32_t* d_err = nullptr;
+    float phase_ms[7] = {0, 0, 0, 0, 0, 0, 0};
+    std::vector<void*> owned;
+};
+
+namespace b200zk {
+
+// pointer tables in d_ptrs: [fixed_values F][fixed_cosets F][advice_values A][advice_cosets A][inst_values I][inst_cosets I]
+struct PtrTab {
+    uint32_t F, A, I;
+    uint32_t fixed_values() const { return 0; }
+    uint32_t fixed_cosets() const { return F; }
+    uint32_t advice_values() const { return 2 * F; }
+    uint32_t advice_cosets() const { return 2 * F + A; }
+    uint32_t inst_values() const { return 2 * F + 2 * A; }
+    uint32_t inst_cosets() const { return 2 * F + 2 * A + I; }
+    uint32_t total() const { return 2 * (F + A + I); }
+};
+
+template <class T> static int32_t dev_alloc(b200zk_pk* pk, T** p, size_t count) {
+    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(pk->ctx, B200ZK_ENOMEM, "cudaMalloc(pk)", cudaGetErrorString(e));
+    pk->owned.push_back(*p);
+    return B200ZK_OK;
+}
+
+struct Arena {
+    char* base; size_t cap, off = 0; bool ok = true;
+    template <class T> T* take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
+        if (off + bytes > cap) { ok = false; return nullptr; }
+        T* p = (T*)(base + off); off += bytes; return p;
+    }
+};
+
+static size_t arena_need(const b200zk_pk* pk) {
+    size_t n = pk->n, ext = pk->ext_n, A = pk->cs.A, I = pk->cs.I, L = pk->L, S = pk->S;
+    size_t draws = b200zk_pk_rng_draws(pk);
+    size_t elems = 2 * A * n + 2 * I * n + draws + 7 * L * n + S * n + S * ext + 3 * n   // columns, lookups, perm, tmp
+                   + ext * (1 + A + I + 4)                                                // h, cosets, lookup cosets + table_value
+                   + n * (1 + 8 + 4);                                                     // h_poly, shplonk set sums, hx/lx/tmp
+    return elems * sizeof(fe_t) + (size_t)draws * 64 + (64 << 10);
+}
+
+struct PhaseTimer {
+    b200zk_ctx* ctx; float* acc; cudaEvent_t e0, e1;
+    PhaseTimer(b200zk_pk* pk, int slot) : ctx(pk->ctx), acc(&pk->phase_ms[slot]) {
+        e0 = ctx->events[48 + 2 * slot]; e1 = ctx->events[49 + 2 * slot];
+        cudaEventRecord(e0, ctx->stream);
+    }
+    ~PhaseTimer() {
+        cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); *acc += ms;
+    }
+};
+enum { PH_MSM = 0, PH_NTT = 1, PH_QUOT = 2, PH_LOOKUP = 3, PH_PERM = 4, PH_OPEN = 5, PH_OTHER = 6 };
+
+static int cmp_canonical(const HFr& a, const HFr& b) {
+    uint64_t x[4], y[4]; a.to_canonical(x); b.to_canonical(y);
+    for (int i = 3; i >= 0; --i) if (x[i] != y[i]) return x[i] < y[i] ? -1 : 1;
+    return 0;
+}
+struct FrLess { bool operator()(const HFr& a, const HFr& b) const { return cmp_canonical(a, b) < 0; } };
+
+// arithmetic::lagrange_interpolate (host, <= 8 points): the unique polynomial of degree < m
+static std::vector<HFr> lagrange_interpolate(const std::vector<HFr>& pts, const std::vector<HFr>& evals) {
+    size_t m = pts.size();
+    std::vector<HFr> poly(m, HFr::zero());
+    for (size_t j = 0; j < m; ++j) {
+        std::vector<HFr> num(1, HFr::one());
+        HFr den = HFr::one();
+        for (size_t k = 0; k < m; ++k) {
+            if (k == j) continue;
+            std::vector<HFr> nw(num.size() + 1, HFr::zero());
+            for (size_t i = 0; i < num.size(); ++i) { nw[i] = nw[i] - num[i] * pts[k]; nw[i + 1] = nw[i + 1] + num[i]; }
+            num.swap(nw);
+            den = den * (pts[j] - pts[k]);
+        }
+        HFr s = evals[j] * den.inv();
+        for (size_t i = 0; i < num.size(); ++i) poly[i] = poly[i] + num[i] * s;
+    }
+    return poly;
+}
+static HFr eval_small(const std::vector<HFr>& poly, const HFr& x) {
+    HFr acc = HFr::zero();
+    for (size_t i = poly.size(); i-- > 0;) acc = acc * x + poly[i];
+    return acc;
+}
+static HFr rotate_omega(const b200zk_domain* d, const HFr& x, int rot) {
+    return rot >= 0 ? x * d->omega.pow_u64((uint64_t)rot) : x * d->omega_inv.pow_u64((uint64_t)(-(int64_t)rot));
+}
+
+// ParamsKZG::commit / commit_lagrange on a device polynomial
+static int32_t commit_dev(b200zk_pk* pk, const fe_t* d_poly, size_t len, bool lagrange, HAffine* out) {
+    PhaseTimer t(pk, PH_MSM);
+    return msm_run(pk->ctx, d_poly, lagrange ? pk->params->d_g_lagrange : pk->params->d_g, len, out);
+}
+static int32_t lagrange_to_coeff(b200zk_pk* pk, fe_t* d_a) {
+    PhaseTimer t(pk, PH_NTT);
+    HFr post[3] = {pk->dom->ifft_divisor, pk->dom->ifft_divisor, pk->dom->ifft_divisor};
+    return ntt_run(pk->ctx, d_a, pk->n, d_a, pk->dom->k, pk->dom->omega_inv, nullptr, post);
+}
+static int32_t coeff_to_extended(b200zk_pk* pk, const fe_t* d_coeffs, fe_t* d_out) {
+    PhaseTimer t(pk, PH_NTT);
+    HFr pre[3] = {HFr::one(), pk->dom->g_coset, pk->dom->g_coset_inv};
+    return ntt_run(pk->ctx, d_coeffs, pk->n, d_out, pk->dom->extended_k, pk->dom->extended_omega, pre, nullptr);
+}
+static int32_t eval_dev(b200zk_pk* pk, const fe_t* d_poly, size_t len, const HFr& x, HFr* out) {
+    return recurrence_run(pk->ctx, d_poly, nullptr, len, x, out);
+}
+
+static ExprArgs expr_args(const b200zk_pk* pk, uint32_t prog_off, uint32_t prog_len, bool extended, uint32_t mode,
+                          const HFr ch[4], fe_t* out0, fe_t* out1) {
+    PtrTab pt{pk->cs.F, pk->cs.A, pk->cs.I};
+    ExprArgs a{};
+    a.prog = pk->d_prog + prog_off; a.prog_len = prog_len; a.consts = pk->d_consts;
+    a.fixed = pk->d_ptrs + (extended ? pt.fixed_cosets() : pt.fixed_values());
+    a.advice = pk->d_ptrs + (extended ? pt.advice_cosets() : pt.advice_values());
+    a.instance = pk->d_ptrs + (extended ? pt.inst_cosets() : pt.inst_values());
+    a.q_fixed = pk->d_q_fix; a.q_advice = pk->d_q_adv; a.q_instance = pk->d_q_inst;
+    a.log_size = extended ? pk->dom->extended_k : pk->dom->k;
+    a.rot_scale = extended ? (1u << (pk->dom->extended_k - pk->dom->k)) : 1u;
+    for (int i = 0; i < 4; ++i) a.factors[i] = to_dev(ch[i]);
+    a.mode = mode; a.out0 = out0; a.out1 = out1;
+    return a;
+}
+
+// ------------------------------------------------------------------ create_proof
+static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_device, const void* const* advice_host,
+                     const void* const* instance_columns, const uint32_t* instance_lens, const void* rng_wide, bool rng_on_device,
+                     const HFr& transcript_repr, std::vector<uint8_t>& proof_out) {
+    b200zk_ctx* ctx = pk->ctx;
+    const CsDesc& cs = pk->cs;
+    const b200zk_domain* dom = pk->dom;
+    cudaStream_t st = ctx->stream;
+    const size_t n = pk->n, ext = pk->ext_n;
+    const uint32_t A = cs.A, I = cs.I, F = cs.F, L = pk->L, S = pk->S, bf = cs.bf;
+    const size_t usable = n - (bf + 1);
+    const uint32_t rot_scale = 1u << (dom->extended_k - dom->k);
+    for (float& f : pk->phase_ms) f = 0;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZK_CUDA(ctx, cudaMemsetAsync(pk->d_err, 0, 4, st));
+    host::Transcript tr;
+    Arena ar{pk->arena, pk->arena_bytes};
+    const size_t draws = b200zk_pk_rng_draws(pk);
+
+    // ---- arena carve-up
+    fe_t* advice_values = ar.take<fe_t>(A * n);
+    fe_t* advice_polys = ar.take<fe_t>(A * n);
+    fe_t* inst_values = ar.take<fe_t>(I * n);
+    fe_t* inst_polys = ar.take<fe_t>(I * n);
+    uint32_t* wide = ar.take<uint32_t>(draws * 16);
+    fe_t* rnd = ar.take<fe_t>(draws);
+    fe_t* lk_bufs = ar.take<fe_t>(7 * (size_t)L * n);            // per lookup: cin ctab pin ptab pin_poly ptab_poly z_poly
+    fe_t* perm_polys = ar.take<fe_t>((size_t)S * n);
+    fe_t* perm_cosets = ar.take<fe_t>((size_t)S * ext);
+    fe_t* tmp_n = ar.take<fe_t>(3 * n);
+    fe_t* h = ar.take<fe_t>(ext);
+    fe_t* advice_cosets = ar.take<fe_t>(A * ext);
+    fe_t* inst_cosets = ar.take<fe_t>(I * ext);
+    fe_t* lk_cosets = ar.take<fe_t>(4 * ext);                    // z, a', s', table_value
+    fe_t* h_poly = ar.take<fe_t>(n);
+    fe_t* set_sums = ar.take<fe_t>(8 * n);
+    fe_t* sh_tmp = ar.take<fe_t>(4 * n);
+    if (!ar.ok) return fail(ctx, B200ZK_ENOMEM, "create_proof", "arena too small");
+    auto LK = [&](uint32_t l, uint32_t which) { return lk_bufs + ((size_t)l * 7 + which) * n; };
+
+    // ---- pointer tables for this proof
+    {
+        PtrTab pt{F, A, I};
+        std::vector<const fe_t*> tab(pt.total());
+        for (uint32_t c = 0; c < F; ++c) { tab[pt.fixed_values() + c] = pk->fixed_values + (size_t)c * n; tab[pt.fixed_cosets() + c] = pk->fixed_cosets + (size_t)c * ext; }
+        for (uint32_t c = 0; c < A; ++c) { tab[pt.advice_values() + c] = advice_values + (size_t)c * n; tab[pt.advice_cosets() + c] = advice_cosets + (size_t)c * ext; }
+        for (uint32_t c = 0; c < I; ++c) { tab[pt.inst_values() + c] = inst_values + (size_t)c * n; tab[pt.inst_cosets() + c] = inst_cosets + (size_t)c * ext; }
+        ZK_CUDA(ctx, cudaMemcpyAsync(pk->d_ptrs, tab.data(), tab.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+        ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+
+    // ---- step 0/1: vk.hash_into, instances
+    tr.common_scalar(transcript_repr);
+    ZK_CUDA(ctx, cudaMemsetAsync(inst_values, 0, I * n * sizeof(fe_t), st));
+    for (uint32_t c = 0; c < I; ++c) {
+        uint32_t len = instance_lens[c];
+        if (len > usable) return fail(ctx, B200ZK_ESYNTH, "create_proof", "InstanceTooLarge");
+        const uint64_t* v = (const uint64_t*)instance_columns[c];
+        for (uint32_t i = 0; i < len; ++i) tr.common_scalar(HFr::from_limbs(v + 4 * i));
+        if (len) ZK_CUDA(ctx, cudaMemcpyAsync(inst_values + (size_t)c * n, v, (size_t)len * sizeof(fe_t), cudaMemcpyHostToDevice, st));
+    }
+    ZK_CUDA(ctx, cudaMemcpyAsync(inst_polys, inst_values, I * n * sizeof(fe_t), cudaMemcpyDeviceToDevice, st));
+    for (uint32_t c = 0; c < I; ++c) ZK_TRY(lagrange_to_coeff(pk, inst_polys + (size_t)c * n));
+
+    // ---- randomness: Fr::random = from_u512 of the caller's 64-byte draws, consumed in upstream order
+    if (rng_on_device) ZK_CUDA(ctx, cudaMemcpyAsync(wide, rng_wide, draws * 64, cudaMemcpyDeviceToDevice, st));
+    else ZK_CUDA(ctx, cudaMemcpyAsync(wide, rng_wide, draws * 64, cudaMemcpyHostToDevice, st));
+    from_u512_kernel<<<nb(draws), PK_THREADS, 0, st>>>(wide, rnd, draws);
+    ctx->launches++;
+    size_t rpos = 0;
+    auto rng_take = [&](size_t count) { fe_t* p = rnd + rpos; rpos += count; return p; };
+    auto copy_rows = [&](fe_t* dst, const fe_t* src, size_t count) {
+        return cudaMemcpyAsync(dst, src, count * sizeof(fe_t), cudaMemcpyDeviceToDevice, st);
+    };
+
+    // ---- step 2: advice columns: blinding rows, blinds, commitments
+    if (advice_on_device) ZK_CUDA(ctx, copy_rows(advice_values, d_advice_in, A * n));
+    else for (uint32_t c = 0; c < A; ++c)
+        ZK_CUDA(ctx, cudaMemcpyAsync(advice_values + (size_t)c * n, advice_host[c], n * sizeof(fe_t), cudaMemcpyHostToDevice, st));
+    for (uint32_t c = 0; c < A; ++c) ZK_CUDA(ctx, copy_rows(advice_values + (size_t)c * n + usable, rng_take(bf + 1), bf + 1));
+    rng_take(A);                                                  // Blind per column (unused by KZG)
+    for (uint32_t c = 0; c < A; ++c) {
+        HAffine pt;
+        ZK_TRY(commit_dev(pk, advice_values + (size_t)c * n, n, true, &pt));
+        tr.write_point(pt);
+    }
+    HFr ch[4];                                                    // theta, beta, gamma, y
+    ch[EXF_THETA] = tr.squeeze_challenge();
+    ch[EXF_BETA] = ch[EXF_GAMMA] = ch[EXF_Y] = HFr::zero();
+
+    // ---- step 4: lookups, commit_permuted
+    for (uint32_t l = 0; l < L; ++l) {
+        fe_t *cin = LK(l, 0), *ctab = LK(l, 1), *pin = LK(l, 2), *ptab = LK(l, 3), *pin_poly = LK(l, 4), *ptab_poly = LK(l, 5);
+        {
+            PhaseTimer t(pk, PH_LOOKUP);
+            ExprArgs ea = expr_args(pk, pk->lookup_prog[l].first, pk->lookup_prog[l].second, false, EXM_ACC01, ch, cin, ctab);
+            expr_kernel<<<nb(n), PK_THREADS, 0, st>>>(ea);
+            ctx->launches++;
+            ZK_TRY(lookup_permute_run(ctx, cin, ctab, (uint32_t)usable, pin, ptab, pk->d_err));
+        }
+        ZK_CUDA(ctx, copy_rows(pin + usable, rng_take(bf + 1), bf + 1));
+        ZK_CUDA(ctx, copy_rows(ptab + usable, rng_take(bf + 1), bf + 1));
+        HAffine c_in, c_tab;
+        ZK_CUDA(ctx, copy_rows(pin_poly, pin, n));
+        ZK_TRY(lagrange_to_coeff(pk, pin_poly));
+        rng_take(1);
+        ZK_TRY(commit_dev(pk, pin, n, true, &c_in));
+        ZK_CUDA(ctx, copy_rows(ptab_poly, ptab, n));
+        ZK_TRY(lagrange_to_coeff(pk, ptab_poly));
+        rng_take(1);
+        ZK_TRY(commit_dev(pk, ptab, n, true, &c_tab));
+        tr.write_point(c_in); tr.write_point(c_tab);
+    }
+    {
+        uint32_t err = 0;
+        ZK_CUDA(ctx, cudaMemcpyAsync(&err, pk->d_err, 4, cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(ctx, cudaStreamSynchronize(st));
+        if (err) return fail(ctx, B200ZK_ESYNTH, "create_proof", "ConstraintSystemFailure: lookup input not in table");
+    }
+    ch[EXF_BETA] = tr.squeeze_challenge();
+    ch[EXF_GAMMA] = tr.squeeze_challenge();
+    const HFr beta = ch[EXF_BETA], gamma = ch[EXF_GAMMA];
+
+    // ---- step 6: permutation argument
+    auto column_values = [&](uint32_t type, uint32_t idx) -> const fe_t* {
+        return type == 0 ? advice_values + (size_t)idx * n : type == 1 ? pk->fixed_values + (size_t)idx * n : inst_values + (size_t)idx * n;
+    };
+    auto column_cosets = [&](uint32_t type, uint32_t idx) -> const fe_t* {
+        return type == 0 ? advice_cosets + (size_t)idx * ext : type == 1 ? pk->fixed_cosets + (size_t)idx * ext : inst_cosets + (size_t)idx * ext;
+    };
+    {
+        HFr last_z = HFr::one(), deltaomega = HFr::one();
+        for (uint32_t s = 0; s < S; ++s) {
+            fe_t* z = perm_polys + (size_t)s * n;
+            uint32_t c0 = s * pk->chunk, c1 = std::min<uint32_t>(c0 + pk->chunk, pk->P);
+            {
+                PhaseTimer t(pk, PH_PERM);
+                PermLagArgs pa{};
+                pa.ncols = c1 - c0; pa.n = (uint32_t)n;
+                for (uint32_t j = c0; j < c1; ++j) {
+                    pa.values[j - c0] = column_values(cs.perm[j].first, cs.perm[j].second);
+                    pa.sigma[j - c0] = pk->perm_values + (size_t)j * n;
+                    pa.coef[j - c0] = to_dev(deltaomega * beta);
+                    deltaomega = deltaomega * host::fr_delta();
+                }
+                pa.beta = to_dev(beta); pa.gamma = to_dev(gamma); pa.omega_pows = pk->omega_pows; pa.out = tmp_n;
+                perm_den_kernel<<<nb(n), PK_THREADS, 0, st>>>(pa);
+                ctx->launches++;
+                ZK_TRY(batch_invert_run(ctx, tmp_n, n, 0));
+                perm_num_kernel<<<nb(n), PK_THREADS, 0, st>>>(pa);
+                ctx->launches++;
+                ZK_TRY(prefix_product_run(ctx, tmp_n, z, n, last_z));
+            }
+            ZK_CUDA(ctx, copy_rows(z + (n - bf), rng_take(bf), bf));
+            ZK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, z + (n - (bf + 1)), sizeof(fe_t), cudaMemcpyDeviceToHost, st));
+            ZK_CUDA(ctx, cudaStreamSynchronize(st));
+            last_z = HFr::from_limbs(ctx->pinned);
+            rng_take(1);
+            HAffine pt;
+            ZK_TRY(commit_dev(pk, z, n, true, &pt));
+            tr.write_point(pt);
+            ZK_TRY(lagrange_to_coeff(pk, z));
+            ZK_TRY(coeff_to_extended(pk, z, perm_cosets + (size_t)s * ext));
+        }
+    }
+
+    // ---- step 7: lookups, commit_product
+    for (uint32_t l = 0; l < L; ++l) {
+        fe_t* z = LK(l, 6);
+        {
+            PhaseTimer t(pk, PH_LOOKUP);
+            LookupProdArgs la{LK(l, 2), LK(l, 3), LK(l, 0), LK(l, 1), to_dev(beta), to_dev(gamma), tmp_n, (uint32_t)n};
+            lookup_den_kernel<<<nb(n), PK_THREADS, 0, st>>>(la);
+            ctx->launches++;
+            ZK_TRY(batch_invert_run(ctx, tmp_n, n, 0));
+            lookup_num_kernel<<<nb(n), PK_THREADS, 0, st>>>(la);
+            ctx->launches++;
+            ZK_TRY(prefix_product_run(ctx, tmp_n, z, n, HFr::one()));
+        }
+        ZK_CUDA(ctx, copy_rows(z + (n - bf), rng_take(bf), bf));
+        rng_take(1);
+        HAffine pt;
+        ZK_TRY(commit_dev(pk, z, n, true, &pt));
+        tr.write_point(pt);
+        ZK_TRY(lagrange_to_coeff(pk, z));
+    }
+
+    // ---- step 8: vanishing argument, random polynomial
+    const fe_t* random_poly = rng_take(n);
+    rng_take(1);
+    {
+        HAffine pt;
+        ZK_TRY(commit_dev(pk, random_poly, n, false, &pt));
+        tr.write_point(pt);
+    }
+    ch[EXF_Y] = tr.squeeze_challenge();
+    const HFr y = ch[EXF_Y];
+
+    // ---- step 10: advice polynomials and all cosets
+    ZK_CUDA(ctx, copy_rows(advice_polys, advice_values, A * n));
+    for (uint32_t c = 0; c < A; ++c) ZK_TRY(lagrange_to_coeff(pk, advice_polys + (size_t)c * n));
+    for (uint32_t c = 0; c < A; ++c) ZK_TRY(coeff_to_extended(pk, advice_polys + (size_t)c * n, advice_cosets + (size_t)c * ext));
+    for (uint32_t c = 0; c < I; ++c) ZK_TRY(coeff_to_extended(pk, inst_polys + (size_t)c * n, inst_cosets + (size_t)c * ext));
+
+    // ---- step 11: evaluate_h
+    {
+        PhaseTimer t(pk, PH_QUOT);
+        if (pk->gates_len) {
+            ExprArgs ea = expr_args(pk, 0, pk->gates_len, true, EXM_ACC0, ch, h, nullptr);
+            expr_kernel<<<nb(ext), PK_THREADS, 0, st>>>(ea);
+            ctx->launches++;
+        } else {
+            ZK_CUDA(ctx, cudaMemsetAsync(h, 0, ext * sizeof(fe_t), st));
+        }
+        if (S) {
+            QuotPermAArgs qa{};
+            qa.h = h; qa.y = to_dev(y); qa.l0 = pk->l0; qa.l_last = pk->l_last; qa.nsets = S;
+            qa.log_ext = dom->extended_k; qa.rot_scale = rot_scale; qa.last_rot = -(int32_t)(bf + 1);
+            for (uint32_t s = 0; s < S; ++s) qa.z[s] = perm_cosets + (size_t)s * ext;
+            quot_perm_a_kernel<<<nb(ext), PK_THREADS, 0, st>>>(qa);
+            ctx->launches++;
+            HFr cd = beta * host::fr_zeta();                      // delta_start = beta * ZETA
+            for (uint32_t s = 0; s < S; ++s) {
+                uint32_t c0 = s * pk->chunk, c1 = std::min<uint32_t>(c0 + pk->chunk, pk->P);
+                QuotPermBArgs qb{};
+                qb.h = h; qb.y = to_dev(y); qb.beta = to_dev(beta); qb.gamma = to_dev(gamma); qb.l_active = pk->l_active;
+                qb.z = perm_cosets + (size_t)s * ext; qb.ncols = c1 - c0; qb.log_ext = dom->extended_k; qb.rot_scale = rot_scale;
+                qb.ew_lo = pk->ew_lo; qb.ew_hi = pk->ew_hi; qb.ew_bits = pk->ew_bits;
+                for (uint32_t j = c0; j < c1; ++j) {
+                    qb.values[j - c0] = column_cosets(cs.perm[j].first, cs.perm[j].second);
+                    qb.sigma[j - c0] = pk->perm_cosets + (size_t)j * ext;
+                    qb.cdelta[j - c0] = to_dev(cd);
+                    cd = cd * host::fr_delta();
+                }
+                quot_perm_b_kernel<<<nb(ext), PK_THREADS, 0, st>>>(qb);
+                ctx->launches++;
+            }
+        }
+    }
+    for (uint32_t l = 0; l < L; ++l) {
+        fe_t *zc = lk_cosets, *ac = lk_cosets + ext, *sc = lk_cosets + 2 * ext, *tv = lk_cosets + 3 * ext;
+        ZK_TRY(coeff_to_extended(pk, LK(l, 6), zc));
+        ZK_TRY(coeff_to_extended(pk, LK(l, 4), ac));
+        ZK_TRY(coeff_to_extended(pk, LK(l, 5), sc));
+        PhaseTimer t(pk, PH_QUOT);
+        ExprArgs ea = expr_args(pk, pk->lookup_prog[l].first, pk->lookup_prog[l].second, true, EXM_LOOKUP_PROD, ch, tv, nullptr);
+        expr_kernel<<<nb(ext), PK_THREADS, 0, st>>>(ea);
+        QuotLookupArgs ql{h, to_dev(y), to_dev(beta), to_dev(gamma), pk->l0, pk->l_last, pk->l_active, zc, ac, sc, tv, dom->extended_k, rot_scale};
+        quot_lookup_kernel<<<nb(ext), PK_THREADS, 0, st>>>(ql);
+        ctx->launches += 2;
+    }
+    ZK_CUDA(ctx, cudaGetLastError());
+
+    // ---- step 12: vanishing construct
+    {
+        PhaseTimer t(pk, PH_NTT);
+        ZK_TRY(fr_scale_periodic(ctx, h, ext, dom->d_t_evaluations, rot_scale));
+        HFr dv = dom->extended_ifft_divisor;
+        HFr post[3] = {dv, dv * dom->g_coset_inv, dv * dom->g_coset};
+        ZK_TRY(ntt_run(ctx, h, (uint32_t)ext, h, dom->extended_k, dom->extended_omega_inv, nullptr, post));
+    }
+    const uint32_t q = pk->q;
+    rng_take(q);                                                  // h_blinds
+    for (uint32_t i = 0; i < q; ++i) {
+        HAffine pt;
+        ZK_TRY(commit_dev(pk, h + (size_t)i * n, n, false, &pt));
+        tr.write_point(pt);
+    }
+    if (rpos != draws) return fail(ctx, B200ZK_EINVAL, "create_proof", "internal: rng draw count mismatch");
+    const HFr x = tr.squeeze_challenge();
+    const HFr xn = x.pow_u64(n);
+
+    // ---- step 14: evaluations
+    PhaseTimer* open_timer = new PhaseTimer(pk, PH_OPEN);
+    std::map<std::pair<const fe_t*, std::array<uint64_t, 4>>, HFr> eval_cache;
+    auto eval_at = [&](const fe_t* poly, const HFr& pt, HFr* out) -> int32_t {
+        std::array<uint64_t, 4> key = {pt.v[0], pt.v[1], pt.v[2], pt.v[3]};
+        auto it = eval_cache.find({poly, key});
+        if (it != eval_cache.end()) { *out = it->second; return B200ZK_OK; }
+        ZK_TRY(eval_dev(pk, poly, n, pt, out));
+        eval_cache[{poly, key}] = *out;
+        return B200ZK_OK;
+    };
+    struct Query { const fe_t* poly; HFr point; };
+    std::vector<Query> queries;
+    int32_t rc = B200ZK_OK;
+    auto finish = [&](int32_t r) { delete open_timer; return r; };
+    for (size_t i = 0; i < cs.adv_q.size() && rc == B200ZK_OK; i += 2) {
+        HFr e; rc = eval_at(advice_polys + (size_t)cs.adv_q[i] * n, rotate_omega(dom, x, cs.adv_q[i + 1]), &e);
+        tr.write_scalar(e);
+    }
+    for (size_t i = 0; i < cs.fix_q.size() && rc == B200ZK_OK; i += 2) {
+        HFr e; rc = eval_at(pk->fixed_polys + (size_t)cs.fix_q[i] * n, rotate_omega(dom, x, cs.fix_q[i + 1]), &e);
+        tr.write_scalar(e);
+    }
+    if (rc != B200ZK_OK) return finish(rc);
+    fold_pieces_kernel<<<nb(n), PK_THREADS, 0, st>>>(h, q, n, to_dev(xn), h_poly);
+    ctx->launches++;
+    {
+        HFr e; rc = eval_at(random_poly, x, &e); tr.write_scalar(e);
+    }
+    for (uint32_t j = 0; j < pk->P && rc == B200ZK_OK; ++j) {
+        HFr e; rc = eval_at(pk->perm_polys + (size_t)j * n, x, &e); tr.write_scalar(e);
+    }
+    const HFr x_next = rotate_omega(dom, x, 1), x_prev = rotate_omega(dom, x, -1), x_last = rotate_omega(dom, x, -(int)(bf + 1));
+    for (uint32_t s = 0; s < S && rc == B200ZK_OK; ++s) {
+        const fe_t* zp = perm_polys + (size_t)s * n;
+        HFr e;
+        rc = eval_at(zp, x, &e); tr.write_scalar(e);
+        if (rc == B200ZK_OK) { rc = eval_at(zp, x_next, &e); tr.write_scalar(e); }
+        if (rc == B200ZK_OK && s + 1 < S) { rc = eval_at(zp, x_last, &e); tr.write_scalar(e); }
+    }
+    for (uint32_t l = 0; l < L && rc == B200ZK_OK; ++l) {
+        HFr e;
+        const fe_t *zp = LK(l, 6), *ap = LK(l, 4), *sp = LK(l, 5);
+        rc = eval_at(zp, x, &e); tr.write_scalar(e);
+        if (rc == B200ZK_OK) { rc = eval_at(zp, x_next, &e); tr.write_scalar(e); }
+        if (rc == B200ZK_OK) { rc = eval_at(ap, x, &e); tr.write_scalar(e); }
+        if (rc == B200ZK_OK) { rc = eval_at(ap, x_prev, &e); tr.write_scalar(e); }
+        if (rc == B200ZK_OK) { rc = eval_at(sp, x, &e); tr.write_scalar(e); }
+    }
+    if (rc != B200ZK_OK) return finish(rc);
+
+    // ---- step 15: multiopen queries in upstream order
+    for (size_t i = 0; i < cs.adv_q.size(); i += 2) queries.push_back({advice_polys + (size_t)cs.adv_q[i] * n, rotate_omega(dom, x, cs.adv_q[i + 1])});
+    for (uint32_t s = 0; s < S; ++s) { queries.push_back({perm_polys + (size_t)s * n, x}); queries.push_back({perm_polys + (size_t)s * n, x_next}); }
+    for (uint32_t s = S; s-- > 0;) if (s + 1 < S) queries.push_back({perm_polys + (size_t)s * n, x_last});
+    for (uint32_t l = 0; l < L; ++l) {
+        queries.push_back({LK(l, 6), x}); queries.push_back({LK(l, 4), x}); queries.push_back({LK(l, 5), x});
+        queries.push_back({LK(l, 4), x_prev}); queries.push_back({LK(l, 6), x_next});
+    }
+    for (size_t i = 0; i < cs.fix_q.size(); i += 2) queries.push_back({pk->fixed_polys + (size_t)cs.fix_q[i] * n, rotate_omega(dom, x, cs.fix_q[i + 1])});
+    for (uint32_t j = 0; j < pk->P; ++j) queries.push_back({pk->perm_polys + (size_t)j * n, x});
+    queries.push_back({h_poly, x});
+    queries.push_back({random_poly, x});
+
+    // ---- ProverSHPLONK::create_proof
+    const HFr sy = tr.squeeze_challenge();
+    // construct_intermediate_sets
+    struct CommSet { const fe_t* poly; std::set<HFr, FrLess> pts; };
+    std::vector<CommSet> comm_sets;
+    std::set<HFr, FrLess> super_points;
+    for (auto& qy : queries) {
+        super_points.insert(qy.point);
+        auto it = std::find_if(comm_sets.begin(), comm_sets.end(), [&](const CommSet& c) { return c.poly == qy.poly; });
+        if (it == comm_sets.end()) { comm_sets.push_back({qy.poly, {}}); it = comm_sets.end() - 1; }
+        it->pts.insert(qy.point);
+    }
+    struct RotSet { std::vector<HFr> pts; std::vector<const fe_t*> polys; };
+    std::vector<RotSet> rot_sets;
+    for (auto& c : comm_sets) {
+        std::vector<HFr> pts(c.pts.begin(), c.pts.end());
+        auto it = std::find_if(rot_sets.begin(), rot_sets.end(), [&](const RotSet& r) {
+            return r.pts.size() == pts.size() && std::equal(pts.begin(), pts.end(), r.pts.begin());
+        });
+        if (it == rot_sets.end()) { rot_sets.push_back({pts, {}}); it = rot_sets.end() - 1; }
+        if (std::find(it->polys.begin(), it->polys.end(), c.poly) == it->polys.end()) it->polys.push_back(c.poly);
+    }
+    if (rot_sets.size() > 8) return finish(fail(ctx, B200ZK_EINVAL, "create_proof", "more than 8 rotation sets"));
+    // low-degree equivalents
+    std::vector<std::vector<std::vector<HFr>>> low(rot_sets.size());
+    for (size_t i = 0; i < rot_sets.size(); ++i) {
+        if (rot_sets[i].pts.size() > 8) return finish(fail(ctx, B200ZK_EINVAL, "create_proof", "rotation set with more than 8 points"));
+        for (const fe_t* poly : rot_sets[i].polys) {
+            std::vector<HFr> evals;
+            for (auto& pt : rot_sets[i].pts) { HFr e; rc = eval_at(poly, pt, &e); if (rc != B200ZK_OK) return finish(rc); evals.push_back(e); }
+            low[i].push_back(lagrange_interpolate(rot_sets[i].pts, evals));
+        }
+    }
+    const HFr sv = tr.squeeze_challenge();
+    fe_t *hx = sh_tmp, *lx = sh_tmp + n, *t0 = sh_tmp + 2 * n, *t1 = sh_tmp + 3 * n;
+    ZK_CUDA(ctx, cudaMemsetAsync(hx, 0, n * sizeof(fe_t), st));
+    {
+        HFr v_pow = HFr::one();
+        for (size_t i = 0; i < rot_sets.size(); ++i) {
+            fe_t* sum = set_sums + i * n;                        // A_i = sum_j y^j P_ij
+            HFr y_pow = HFr::one();
+            std::vector<HFr> rlow(rot_sets[i].pts.size(), HFr::zero());   // R_i = sum_j y^j r_ij
+            for (size_t j = 0; j < rot_sets[i].polys.size(); ++j) {
+                axpy_kernel<<<nb(n), PK_THREADS, 0, st>>>(sum, rot_sets[i].polys[j], to_dev(y_pow), n, j == 0 ? 1 : 0);
+                ctx->launches++;
+                for (size_t c = 0; c < low[i][j].size(); ++c) rlow[c] = rlow[c] + low[i][j][c] * y_pow;
+                y_pow = y_pow * sy;
+            }
+            // N_i = A_i - R_i ; Q_i = N_i / prod (X - p)
+            ZK_CUDA(ctx, copy_rows(t0, sum, n));
+            LowCoeffs lc{}; lc.m = (uint32_t)rlow.size();
+            for (size_t c = 0; c < rlow.size(); ++c) lc.c[c] = to_dev(rlow[c]);
+            sub_low_kernel<<<1, 8, 0, st>>>(t0, lc);
+            ctx->launches++;
+            fe_t *src = t0, *dst = t1;
+            size_t len = n;
+            for (auto& pt : rot_sets[i].pts) {
+                ZK_TRY(recurrence_run(ctx, src + 1, dst, len - 1, pt, nullptr));   // kate_division
+                --len; std::swap(src, dst);
+            }
+            axpy_kernel<<<nb(len), PK_THREADS, 0, st>>>(hx, src, to_dev(v_pow), len, 0);
+            ctx->launches++;
+            v_pow = v_pow * sv;
+        }
+    }
+    {
+        delete open_timer; open_timer = nullptr;
+        HAffine pt;
+        ZK_TRY(commit_dev(pk, hx, n, false, &pt));
+        tr.write_point(pt);
+        open_timer = new PhaseTimer(pk, PH_OPEN);
+    }
+    const HFr su = tr.squeeze_challenge();
+    {
+        auto vanish = [&](const std::vector<HFr>& roots) { HFr acc = HFr::one(); for (auto& r : roots) acc = acc * (su - r); return acc; };
+        HFr v_pow = HFr::one(), const_term = HFr::zero(), z0_diff = HFr::zero();
+        for (size_t i = 0; i < rot_sets.size(); ++i) {
+            std::vector<HFr> diffs;
+            for (auto& p : super_points)
+                if (std::find_if(rot_sets[i].pts.begin(), rot_sets[i].pts.end(), [&](const HFr& o) { return o == p; }) == rot_sets[i].pts.end()) diffs.push_back(p);
+            HFr z_i = vanish(diffs);
+            if (i == 0) z0_diff = z_i;
+            HFr y_pow = HFr::one(), c_i = HFr::zero();
+            for (size_t j = 0; j < rot_sets[i].polys.size(); ++j) { c_i = c_i + eval_small(low[i][j], su) * y_pow; y_pow = y_pow * sy; }
+            HFr coef = z_i * v_pow;
+            axpy_kernel<<<nb(n), PK_THREADS, 0, st>>>(lx, set_sums + i * n, to_dev(coef), n, i == 0 ? 1 : 0);
+            ctx->launches++;
+            const_term = const_term + coef * c_i;
+            v_pow = v_pow * sv;
+        }
+        std::vector<HFr> sp(super_points.begin(), super_points.end());
+        HFr zt = vanish(sp);
+        axpy_kernel<<<nb(n), PK_THREADS, 0, st>>>(lx, hx, to_dev(zt.neg()), n, 0);
+        LowCoeffs lc{}; lc.m = 1; lc.c[0] = to_dev(const_term);
+        sub_low_kernel<<<1, 8, 0, st>>>(lx, lc);
+        ctx->launches += 2;
+        ZK_TRY(recurrence_run(ctx, lx + 1, t0, n - 1, su, nullptr));              // (L(X)) / (X - u)
+        scale_kernel<<<nb(n - 1), PK_THREADS, 0, st>>>(t0, to_dev(z0_diff.inv()), n - 1);
+        ctx->launches++;
+        ZK_CUDA(ctx, cudaGetLastError());
+        delete open_timer; open_timer = nullptr;
+        HAffine pt;
+        ZK_TRY(commit_dev(pk, t0, n - 1, false, &pt));
+        tr.write_point(pt);
+    }
+    proof_out = tr.proof();
+    return B200ZK_OK;
+}
+
+}  // namespace b200zk
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+size_t b200zk_pk_rng_draws(const b200zk_pk* pk) {
+    if (!pk) return 0;
+    const CsDesc& cs = pk->cs;
+    size_t bf = cs.bf;
+    return cs.A * (bf + 1) + cs.A + pk->L * (2 * (bf + 1) + 2) + pk->S * (bf + 1) + pk->L * (bf + 1) + pk->n + 1 + pk->q;
+}
+
+size_t b200zk_pk_proof_size(const b200zk_pk* pk) {
+    if (!pk) return 0;
+    const CsDesc& cs = pk->cs;
+    size_t S = pk->S, L = pk->L;
+    size_t points = cs.A + 2 * L + S + L + 1 + pk->q + 2;
+    size_t evals = cs.adv_q.size() / 2 + cs.fix_q.size() / 2 + 1 + pk->P + (S ? 3 * S - 1 : 0) + 5 * L;
+    return 32 * (points + evals);
+}
+
+uint32_t b200zk_pk_blinding_factors(const b200zk_pk* pk) { return pk ? pk->cs.bf : 0; }
+uint32_t b200zk_pk_degree(const b200zk_pk* pk) { return pk ? pk->cs.degree : 0; }
+
+int32_t b200zk_pk_last_phase_ms(const b200zk_pk* pk, float* out7) {
+    if (!pk || !out7) return B200ZK_EINVAL;
+    memcpy(out7, pk->phase_ms, sizeof(pk->phase_ms));
+    return B200ZK_OK;
+}
+
+void b200zk_pk_destroy(b200zk_pk* pk) {
+    if (!pk) return;
+    cudaSetDevice(pk->ctx->device);
+    cudaStreamSynchronize(pk->ctx->stream);
+    for (void* p : pk->owned) cudaFree(p);
+    if (pk->dom) b200zk_domain_destroy(pk->dom);
+    delete pk;
+}
+
+int32_t b200zk_pk_create(b200zk_params* params, const uint32_t* cs_blob, size_t blob_words, const void* const* fixed_columns,
+                         const uint32_t* map_col, const uint32_t* map_row, b200zk_pk** out) {
+    if (!params || !cs_blob || !out) return B200ZK_EINVAL;
+    b200zk_ctx* ctx = params->ctx;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    b200zk_pk* pk = new (std::nothrow) b200zk_pk();
+    if (!pk) return B200ZK_ENOMEM;
+    pk->ctx = ctx; pk->params = params;
+    auto bail = [&](int32_t rc) { b200zk_pk_destroy(pk); return rc; };
+    if (!parse_cs(cs_blob, blob_words, pk->cs)) return bail(fail(ctx, B200ZK_EINVAL, "pk_create", "malformed constraint-system blob"));
+    CsDesc& cs = pk->cs;
+    if (cs.k != params->k || !params->d_g_lagrange) return bail(fail(ctx, B200ZK_EINVAL, "pk_create", "params do not match k / lagrange basis missing"));
+    if (cs.F && !fixed_columns) return bail(B200ZK_EINVAL);
+    int32_t rc = b200zk_domain_create(ctx, cs.degree, cs.k, &pk->dom);
+    if (rc != B200ZK_OK) return bail(rc);
+    const b200zk_domain* dom = pk->dom;
+    pk->n = 1u << cs.k; pk->ext_n = 1u << dom->extended_k;
+    pk->P = (uint32_t)cs.perm.size(); pk->L = (uint32_t)cs.lookups.size();
+    pk->chunk = cs.degree - 2;
+    pk->S = (pk->P + pk->chunk - 1) / pk->chunk;
+    pk->q = dom->quotient_poly_degree;
+    if (pk->chunk > ZK_MAXC || pk->S > ZK_MAXC) return bail(fail(ctx, B200ZK_EINVAL, "pk_create", "permutation too wide for this build"));
+    if (pk->P && (!map_col || !map_row)) return bail(B200ZK_EINVAL);
+    const size_t n = pk->n, ext = pk->ext_n;
+    const uint32_t F = cs.F, P = pk->P;
+    cudaStream_t st = ctx->stream;
+#define PK_TRY(expr) do { int32_t _r = (expr); if (_r != B200ZK_OK) return bail(_r); } while (0)
+#define PK_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return bail(fail(ctx, B200ZK_ECUDA, #expr, cudaGetErrorString(_e))); } while (0)
+    PK_TRY(dev_alloc(pk, &pk->fixed_values, F * n)); PK_TRY(dev_alloc(pk, &pk->fixed_polys, F * n)); PK_TRY(dev_alloc(pk, &pk->fixed_cosets, F * ext));
+    PK_TRY(dev_alloc(pk, &pk->perm_values, P * n)); PK_TRY(dev_alloc(pk, &pk->perm_polys, P * n)); PK_TRY(dev_alloc(pk, &pk->perm_cosets, P * ext));
+    PK_TRY(dev_alloc(pk, &pk->l0, ext)); PK_TRY(dev_alloc(pk, &pk->l_last, ext)); PK_TRY(dev_alloc(pk, &pk->l_active, ext));
+    PK_TRY(dev_alloc(pk, &pk->omega_pows, n));
+    PK_TRY(dev_alloc(pk, &pk->d_err, 1));
+    // fixed columns
+    for (uint32_t c = 0; c < F; ++c) PK_CUDA(cudaMemcpyAsync(pk->fixed_values + (size_t)c * n, fixed_columns[c], n * sizeof(fe_t), cudaMemcpyHostToDevice, st));
+    PK_CUDA(cudaMemcpyAsync(pk->fixed_polys, pk->fixed_values, F * n * sizeof(fe_t), cudaMemcpyDeviceToDevice, st));
+    for (uint32_t c = 0; c < F; ++c) {
+        PK_TRY(lagrange_to_coeff(pk, pk->fixed_polys + (size_t)c * n));
+        PK_TRY(coeff_to_extended(pk, pk->fixed_polys + (size_t)c * n, pk->fixed_cosets + (size_t)c * ext));
+    }
+    // omega powers, extended-omega two-level table
+    PK_TRY(powers_run(ctx, dom->omega, n, pk->omega_pows));
+    pk->ew_bits = (dom->extended_k + 1) / 2;
+    {
+        size_t n_lo = (size_t)1 << pk->ew_bits, n_hi = ext >> pk->ew_bits ? ext >> pk->ew_bits : 1;
+        PK_TRY(dev_alloc(pk, &pk->ew_lo, n_lo)); PK_TRY(dev_alloc(pk, &pk->ew_hi, n_hi));
+        PK_TRY(powers_run(ctx, dom->extended_omega, n_lo, pk->ew_lo));
+        PK_TRY(powers_run(ctx, dom->extended_omega.pow_u64(n_lo), n_hi, pk->ew_hi));
+    }
+    // permutation polynomials: sigma_c[r] = delta^map_col * omega^map_row
+    if (P) {
+        uint32_t *d_mc = nullptr, *d_mr = nullptr; fe_t* d_dp = nullptr;
+        PK_TRY(dev_alloc(pk, &d_mc, P * n)); PK_TRY(dev_alloc(pk, &d_mr, P * n)); PK_TRY(dev_alloc(pk, &d_dp, P));
+        for (size_t i = 0; i < (size_t)P * n; ++i) if (map_col[i] >= P || map_row[i] >= n) return bail(fail(ctx, B200ZK_EINVAL, "pk_create", "permutation mapping out of range"));
+        PK_CUDA(cudaMemcpyAsync(d_mc, map_col, P * n * 4, cudaMemcpyHostToDevice, st));
+        PK_CUDA(cudaMemcpyAsync(d_mr, map_row, P * n * 4, cudaMemcpyHostToDevice, st));
+        PK_TRY(powers_run(ctx, host::fr_delta(), P, d_dp));
+        sigma_kernel<<<nb((size_t)P * n), PK_THREADS, 0, st>>>(d_mc, d_mr, d_dp, pk->omega_pows, pk->perm_values, (size_t)P * n);
+        ctx->launches++;
+        PK_CUDA(cudaMemcpyAsync(pk->perm_polys, pk->perm_values, P * n * sizeof(fe_t), cudaMemcpyDeviceToDevice, st));
+        for (uint32_t c = 0; c < P; ++c) {
+            PK_TRY(lagrange_to_coeff(pk, pk->perm_polys + (size_t)c * n));
+            PK_TRY(coeff_to_extended(pk, pk->perm_polys + (size_t)c * n, pk->perm_cosets + (size_t)c * ext));
+        }
+    }
+    // l0, l_last, l_blind -> l_active_row
+    {
+        fe_t* tmp = nullptr; fe_t* lb = nullptr;
+        PK_TRY(dev_alloc(pk, &tmp, n)); PK_TRY(dev_alloc(pk, &lb, ext));
+        fe_t one = to_dev(HFr::one());
+        auto indicator = [&](size_t lo, size_t hi, fe_t* out_ext) -> int32_t {
+            ZK_CUDA(ctx, cudaMemsetAsync(tmp, 0, n * sizeof(fe_t), st));
+            std::vector<fe_t> ones(hi - lo, one);
+            ZK_CUDA(ctx, cudaMemcpyAsync(tmp + lo, ones.data(), ones.size() * sizeof(fe_t), cudaMemcpyHostToDevice, st));
+            ZK_CUDA(ctx, cudaStreamSynchronize(st));
+            ZK_TRY(lagrange_to_coeff(pk, tmp));
+            return coeff_to_extended(pk, tmp, out_ext);
+        };
+        PK_TRY(indicator(0, 1, pk->l0));
+        PK_TRY(indicator(n - cs.bf, n, lb));
+        PK_TRY(indicator(n - cs.bf - 1, n - cs.bf, pk->l_last));
+        one_minus_sum_kernel<<<nb(ext), PK_THREADS, 0, st>>>(pk->l_last, lb, pk->l_active, ext);
+        ctx->launches++;
+    }
+    // programs: gates with FOLD(acc0, y); lookups with FOLD(acc0/acc1, theta)
+    {
+        std::vector<uint32_t> prog;
+        for (auto& g : cs.gates) {
+            prog.insert(prog.end(), cs.prog.begin() + g.first, cs.prog.begin() + g.first + g.second);
+            prog.push_back(EX_FOLD | ((0u << 4 | EXF_Y) << 8));
+        }
+        pk->gates_len = (uint32_t)prog.size();
+        for (auto& lk : cs.lookups) {
+            uint32_t off = (uint32_t)prog.size();
+            for (auto& e : lk.ins) { prog.insert(prog.end(), cs.prog.begin() + e.first, cs.prog.begin() + e.first + e.second); prog.push_back(EX_FOLD | ((0u << 4 | EXF_THETA) << 8)); }
+            for (auto& e : lk.tabs) { prog.insert(prog.end(), cs.prog.begin() + e.first, cs.prog.begin() + e.first + e.second); prog.push_back(EX_FOLD | ((1u << 4 | EXF_THETA) << 8)); }
+            pk->lookup_prog.push_back({off, (uint32_t)prog.size() - off});
+        }
+        // stack depth check
+        int depth = 0, maxd = 0;
+        for (uint32_t w : prog) {
+            uint32_t op = w & 0xff;
+            if (op <= EX_INSTANCE) ++depth; else if (op == EX_ADD || op == EX_MUL || op == EX_FOLD) --depth;
+            maxd = std::max(maxd, depth);
+            if (depth < 0) return bail(fail(ctx, B200ZK_EINVAL, "pk_create", "malformed expression program"));
+        }
+        if (maxd > EX_STACK) return bail(fail(ctx, B200ZK_EINVAL, "pk_create", "expression too deep for the evaluator stack"));
+        PK_TRY(dev_alloc(pk, &pk->d_prog, prog.size()));
+        PK_CUDA(cudaMemcpyAsync(pk->d_prog, prog.data(), prog.size() * 4, cudaMemcpyHostToDevice, st));
+        PK_TRY(dev_alloc(pk, &pk->d_consts, cs.consts.size()));
+        PK_CUDA(cudaMemcpyAsync(pk->d_consts, cs.consts.data(), cs.consts.size() * sizeof(fe_t), cudaMemcpyHostToDevice, st));
+        PK_TRY(dev_alloc(pk, &pk->d_q_adv, cs.adv_q.size())); PK_TRY(dev_alloc(pk, &pk->d_q_fix, cs.fix_q.size())); PK_TRY(dev_alloc(pk, &pk->d_q_inst, cs.inst_q.size()));
+        PK_CUDA(cudaMemcpyAsync(pk->d_q_adv, cs.adv_q.data(), cs.adv_q.size() * 4, cudaMemcpyHostToDevice, st));
+        PK_CUDA(cudaMemcpyAsync(pk->d_q_fix, cs.fix_q.data(), cs.fix_q.size() * 4, cudaMemcpyHostToDevice, st));
+        PK_CUDA(cudaMemcpyAsync(pk->d_q_inst, cs.inst_q.data(), cs.inst_q.size() * 4, cudaMemcpyHostToDevice, st));
+        PK_CUDA(cudaStreamSynchronize(st));
+        PtrTab pt{cs.F, cs.A, cs.I};
+        PK_TRY(dev_alloc(pk, &pk->d_ptrs, pt.total()));
+    }
+    pk->arena_bytes = arena_need(pk);
+    PK_TRY(dev_alloc(pk, &pk->arena, pk->arena_bytes));
+    PK_CUDA(cudaStreamSynchronize(st));
+    PK_CUDA(cudaGetLastError());
+#undef PK_TRY
+#undef PK_CUDA
+    *out = pk;
+    return B200ZK_OK;
+}
+
+static int32_t finish_proof(b200zk_pk* pk, int32_t rc, const std::vector<uint8_t>& proof, uint8_t* proof_out, size_t cap, size_t* proof_len) {
+    if (rc != B200ZK_OK) return rc;
+    if (proof_len) *proof_len = proof.size();
+    if (proof.size() > cap) return fail(pk->ctx, B200ZK_EINVAL, "create_proof", "proof buffer too small");
+    memcpy(proof_out, proof.data(), proof.size());
+    return B200ZK_OK;
+}
+
+int32_t b200zk_create_proof(b200zk_pk* pk, const void* const* advice_columns, const void* const* instance_columns,
+                            const uint32_t* instance_lens, const void* rng_wide, const void* transcript_repr,
+                            uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+    if (!pk || !rng_wide || !transcript_repr || !proof_out || (pk->cs.A && !advice_columns) || (pk->cs.I && (!instance_columns || !instance_lens))) return B200ZK_EINVAL;
+    std::vector<uint8_t> proof;
+    int32_t rc = prove(pk, nullptr, false, advice_columns, instance_columns, instance_lens, rng_wide, false, HFr::from_limbs(transcript_repr), proof);
+    return finish_proof(pk, rc, proof, proof_out, proof_cap, proof_len);
+}
+
+int32_t b200zk_create_proof_dev(b200zk_pk* pk, const void* d_advice, const void* const* instance_columns,
+                                const uint32_t* instance_lens, const void* d_rng_wide, const void* transcript_repr,
+                                uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+    if (!pk || !d_rng_wide || !transcript_repr || !proof_out || (pk->cs.A && !d_advice) || (pk->cs.I && (!instance_columns || !instance_lens))) return B200ZK_EINVAL;
+    std::vector<uint8_t> proof;
+    int32_t rc = prove(pk, (const fe_t*)d_advice, true, nullptr, instance_columns, instance_lens, d_rng_wide, true, HFr::from_limbs(transcript_repr), proof);
+    return finish_proof(pk, rc, proof, proof_out, proof_cap, proof_len);
+}
+
+}  // extern "C"

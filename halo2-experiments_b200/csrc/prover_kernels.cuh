@@ -1,0 +1,172 @@
+// Per-row device bodies of the prover's O(n) / O(ext) steps — everything in
+// halo2_proofs v2023_02_02 create_proof (plonk/prover.rs, reached from
+// /root/reference/src/circuits/utils.rs:40-48) that is neither an MSM, an NTT nor a scan:
+//   plonk/permutation/prover.rs  Argument::commit           perm_denominator / perm_numerator
+//   plonk/lookup/prover.rs       commit_product             lookup_den / lookup_num
+//   plonk/evaluation.rs          evaluate_h (permutation and lookup parts)   quot_*
+//   plonk/vanishing/prover.rs    evaluate (h pieces folded in x^n)           fold_pieces
+//   poly/kzg/multiopen/shplonk/prover.rs  linear combinations of polynomials  axpy / scale
+//   halo2curves Fr::random = from_u512                       from_u512_row
+// Field arithmetic is exact, so any evaluation order gives the same canonical element.
+#pragma once
+#include "field.cuh"
+
+namespace b200zk {
+
+static constexpr int ZK_MAXC = 16;      // columns per permutation set (d - 2) / number of sets handled per launch
+
+// ---- Fr::random(rng) = from_u512(8 x next_u64): lo * R^2 + hi * R^3 (Montgomery products) ----
+ZK_D fe_t from_u512_row(const uint32_t* wide16) {
+    fe_t lo, hi, r2, r3;
+    for (int i = 0; i < 8; ++i) { lo.l[i] = wide16[i]; hi.l[i] = wide16[8 + i]; r2.l[i] = FrCfg::r2(i); r3.l[i] = FrCfg::r3(i); }
+    // inputs are arbitrary 256-bit integers (not reduced): the CIOS multiplier accepts any a < 2^256
+    // with b < p and returns a value < 2p that reduce_once brings into range.
+    return Fr::add(Fr::mul(lo, r2), Fr::mul(hi, r3));
+}
+
+// ---- permutation grand product (Lagrange domain) ----
+struct PermLagArgs {
+    uint32_t ncols, n;
+    const fe_t* values[ZK_MAXC];
+    const fe_t* sigma[ZK_MAXC];
+    fe_t coef[ZK_MAXC];                 // delta^(global column index) * beta
+    fe_t beta, gamma;
+    const fe_t* omega_pows;             // omega^i
+    fe_t* out;
+};
+ZK_D void perm_denominator_row(const PermLagArgs& a, uint32_t i) {
+    fe_t acc = Fr::one();
+    for (uint32_t j = 0; j < a.ncols; ++j) {
+        fe_t s = a.sigma[j][i], v = a.values[j][i];
+        acc = Fr::mul(acc, Fr::add(Fr::add(Fr::mul(a.beta, s), a.gamma), v));
+    }
+    a.out[i] = acc;
+}
+ZK_D void perm_numerator_row(const PermLagArgs& a, uint32_t i) {
+    fe_t acc = a.out[i], w = a.omega_pows[i];
+    for (uint32_t j = 0; j < a.ncols; ++j) {
+        fe_t v = a.values[j][i];
+        acc = Fr::mul(acc, Fr::add(Fr::add(Fr::mul(w, a.coef[j]), a.gamma), v));
+    }
+    a.out[i] = acc;
+}
+
+// ---- lookup grand product (Lagrange domain) ----
+struct LookupProdArgs {
+    const fe_t *pin, *ptab, *cin, *ctab;
+    fe_t beta, gamma;
+    fe_t* out;
+    uint32_t n;
+};
+ZK_D void lookup_den_row(const LookupProdArgs& a, uint32_t i) {
+    fe_t x = a.pin[i], y = a.ptab[i];
+    a.out[i] = Fr::mul(Fr::add(a.beta, x), Fr::add(a.gamma, y));
+}
+ZK_D void lookup_num_row(const LookupProdArgs& a, uint32_t i) {
+    fe_t d = a.out[i], x = a.cin[i], y = a.ctab[i];
+    a.out[i] = Fr::mul(Fr::mul(d, Fr::add(x, a.beta)), Fr::add(y, a.gamma));
+}
+
+// ---- evaluate_h: permutation part (extended domain) ----
+struct QuotPermAArgs {
+    fe_t* h;
+    fe_t y;
+    const fe_t *l0, *l_last;
+    uint32_t nsets, log_ext, rot_scale;
+    int32_t last_rot;                   // -(blinding_factors + 1)
+    const fe_t* z[ZK_MAXC];             // permutation_product_coset per set
+};
+ZK_D uint32_t rot_idx(uint32_t idx, int32_t rot, uint32_t rot_scale, uint32_t log_size) {
+    return (idx + (uint32_t)(rot * (int32_t)rot_scale)) & ((1u << log_size) - 1);
+}
+ZK_D void quot_perm_a_row(const QuotPermAArgs& a, uint32_t idx) {
+    fe_t h = a.h[idx], l0 = a.l0[idx], ll = a.l_last[idx];
+    fe_t zf = a.z[0][idx], zl = a.z[a.nsets - 1][idx];
+    // l_0 (1 - z_0)
+    h = Fr::add(Fr::mul(h, a.y), Fr::mul(Fr::sub(Fr::one(), zf), l0));
+    // l_last (z_l^2 - z_l)
+    h = Fr::add(Fr::mul(h, a.y), Fr::mul(Fr::sub(Fr::sqr(zl), zl), ll));
+    // l_0 (z_i - z_{i-1}(omega^last X))
+    uint32_t r_last = rot_idx(idx, a.last_rot, a.rot_scale, a.log_ext);
+    for (uint32_t s = 1; s < a.nsets; ++s) {
+        fe_t zi = a.z[s][idx], zp = a.z[s - 1][r_last];
+        h = Fr::add(Fr::mul(h, a.y), Fr::mul(Fr::sub(zi, zp), l0));
+    }
+    a.h[idx] = h;
+}
+
+struct QuotPermBArgs {
+    fe_t* h;
+    fe_t y, beta, gamma;
+    const fe_t* l_active;
+    const fe_t* z;
+    uint32_t ncols, log_ext, rot_scale, ew_bits;
+    const fe_t* values[ZK_MAXC];        // column cosets
+    const fe_t* sigma[ZK_MAXC];         // permutation cosets
+    fe_t cdelta[ZK_MAXC];               // beta * zeta * delta^(global column index)
+    const fe_t *ew_lo, *ew_hi;          // extended_omega^idx two-level table
+};
+ZK_D void quot_perm_b_row(const QuotPermBArgs& a, uint32_t idx) {
+    uint32_t lo = idx & ((1u << a.ew_bits) - 1), hi = idx >> a.ew_bits;
+    fe_t wl = a.ew_lo[lo], wh = a.ew_hi[hi];
+    fe_t beta_term = Fr::mul(wl, wh);                                       // extended_omega^idx
+    fe_t left = a.z[rot_idx(idx, 1, a.rot_scale, a.log_ext)], right = a.z[idx];
+    for (uint32_t j = 0; j < a.ncols; ++j) {
+        fe_t v = a.values[j][idx], s = a.sigma[j][idx];
+        left = Fr::mul(left, Fr::add(Fr::add(v, Fr::mul(a.beta, s)), a.gamma));
+        right = Fr::mul(right, Fr::add(Fr::add(v, Fr::mul(a.cdelta[j], beta_term)), a.gamma));
+    }
+    fe_t h = a.h[idx], la = a.l_active[idx];
+    a.h[idx] = Fr::add(Fr::mul(h, a.y), Fr::mul(Fr::sub(left, right), la));
+}
+
+// ---- evaluate_h: one lookup argument (extended domain) ----
+struct QuotLookupArgs {
+    fe_t* h;
+    fe_t y, beta, gamma;
+    const fe_t *l0, *l_last, *l_active;
+    const fe_t *z, *a, *s;              // product / permuted input / permuted table cosets
+    const fe_t* table_value;            // (compressed input + beta)(compressed table + gamma)
+    uint32_t log_ext, rot_scale;
+};
+ZK_D void quot_lookup_row(const QuotLookupArgs& q, uint32_t idx) {
+    fe_t h = q.h[idx], l0 = q.l0[idx], ll = q.l_last[idx], la = q.l_active[idx];
+    fe_t z = q.z[idx], zn = q.z[rot_idx(idx, 1, q.rot_scale, q.log_ext)];
+    fe_t a = q.a[idx], ap = q.a[rot_idx(idx, -1, q.rot_scale, q.log_ext)], s = q.s[idx], tv = q.table_value[idx];
+    fe_t a_minus_s = Fr::sub(a, s);
+    h = Fr::add(Fr::mul(h, q.y), Fr::mul(Fr::sub(Fr::one(), z), l0));
+    h = Fr::add(Fr::mul(h, q.y), Fr::mul(Fr::sub(Fr::sqr(z), z), ll));
+    fe_t lhs = Fr::mul(Fr::mul(zn, Fr::add(a, q.beta)), Fr::add(s, q.gamma));
+    h = Fr::add(Fr::mul(h, q.y), Fr::mul(Fr::sub(lhs, Fr::mul(z, tv)), la));
+    h = Fr::add(Fr::mul(h, q.y), Fr::mul(a_minus_s, l0));
+    h = Fr::add(Fr::mul(h, q.y), Fr::mul(Fr::mul(a_minus_s, Fr::sub(a, ap)), la));
+    q.h[idx] = h;
+}
+
+// ---- vanishing::evaluate: h_poly = sum_j (x^n)^j piece_j  (pieces contiguous, n apart) ----
+ZK_D void fold_pieces_row(const fe_t* pieces, uint32_t npieces, size_t n, const fe_t& xn, fe_t* out, size_t i) {
+    fe_t acc = pieces[(size_t)(npieces - 1) * n + i];
+    for (uint32_t j = npieces - 1; j-- > 0;) { fe_t p = pieces[(size_t)j * n + i]; acc = Fr::add(Fr::mul(acc, xn), p); }
+    out[i] = acc;
+}
+
+// ---- polynomial linear algebra ----
+ZK_D void axpy_row(fe_t* acc, const fe_t* p, const fe_t& s, size_t i, bool init) {
+    fe_t v = p[i];
+    fe_t t = Fr::mul(v, s);
+    if (!init) { fe_t a = acc[i]; t = Fr::add(a, t); }
+    acc[i] = t;
+}
+ZK_D void scale_row(fe_t* a, const fe_t& s, size_t i) { fe_t v = a[i]; a[i] = Fr::mul(v, s); }
+// out = 1 - (a + b)   (l_active_row)
+ZK_D void one_minus_sum_row(const fe_t* a, const fe_t* b, fe_t* out, size_t i) {
+    fe_t x = a[i], y = b[i];
+    out[i] = Fr::sub(Fr::one(), Fr::add(x, y));
+}
+// sigma[i] = delta^col * omega^row of the mapped cell (permutation keygen)
+ZK_D void sigma_row(const uint32_t* map_col, const uint32_t* map_row, const fe_t* delta_pows, const fe_t* omega_pows, fe_t* out, size_t i) {
+    fe_t d = delta_pows[map_col[i]], w = omega_pows[map_row[i]];
+    out[i] = Fr::mul(d, w);
+}
+
+}  // namespace b200zk

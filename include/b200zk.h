@@ -127,6 +127,46 @@ int32_t b200zk_batch_invert_dev(b200zk_ctx* ctx, void* d_a, size_t len, int32_t 
  * arguments (plonk/permutation/prover.rs, plonk/lookup/prover.rs).  d_z may alias d_p. */
 int32_t b200zk_prefix_product_dev(b200zk_ctx* ctx, const void* d_p, void* d_z, size_t len, const void* z0_fr);
 
+/* ---- plonk::keygen_pk / plonk::create_proof (src/plonk/keygen.rs, src/plonk/prover.rs) --------
+ * The call `full_prover` makes at /root/reference/src/circuits/utils.rs:35 and :40-48, for one
+ * circuit instance with KZGCommitmentScheme<Bn256>, ProverSHPLONK, Challenge255 and Blake2bWrite.
+ *
+ * pk_create: cs_blob is the constraint-system description (column counts, query lists, gate and
+ * lookup expressions, permutation columns — the serialisation is documented in
+ * halo2-experiments_b200/circuit.py::ConstraintSystem.to_blob); fixed_columns are the F fixed
+ * columns (selectors already compressed into them) as n Lagrange values each; map_col/map_row are
+ * the permutation Assembly's mapping (P x n, row-major): cell (c, r) maps to
+ * (map_col[c*n+r], map_row[c*n+r]).  Everything derived (polys, cosets, sigma, l0/l_last/
+ * l_active_row) is computed on the device and stays resident in HBM.
+ *
+ * create_proof: advice_columns = A columns of n Lagrange values as produced by witness synthesis
+ * (batch-inverted, not yet blinded); instance_columns / instance_lens = the public inputs;
+ * rng_wide = the 64-byte little-endian inputs of every Fr::random(rng) call create_proof makes, in
+ * call order (b200zk_pk_rng_draws() of them: the Rust shim fills it from the caller's RngCore, so
+ * the proof is a pure function of its inputs); transcript_repr = vk.transcript_repr (Fr).
+ * The proof bytes are exactly what `transcript.finalize()` returns.
+ * Returns B200ZK_ESYNTH for upstream's Error::ConstraintSystemFailure (lookup input not in table)
+ * and Error::InstanceTooLarge. */
+#define B200ZK_ESYNTH (-5)
+typedef struct b200zk_pk b200zk_pk;
+int32_t b200zk_pk_create(b200zk_params* params, const uint32_t* cs_blob, size_t blob_words,
+                         const void* const* fixed_columns, const uint32_t* map_col, const uint32_t* map_row,
+                         b200zk_pk** out);
+void b200zk_pk_destroy(b200zk_pk* pk);
+size_t b200zk_pk_proof_size(const b200zk_pk* pk);
+size_t b200zk_pk_rng_draws(const b200zk_pk* pk);
+uint32_t b200zk_pk_blinding_factors(const b200zk_pk* pk);
+uint32_t b200zk_pk_degree(const b200zk_pk* pk);
+int32_t b200zk_create_proof(b200zk_pk* pk, const void* const* advice_columns, const void* const* instance_columns,
+                            const uint32_t* instance_lens, const void* rng_wide, const void* transcript_repr,
+                            uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+/* same, with the advice columns (A x n, contiguous) and the rng stream already in device memory */
+int32_t b200zk_create_proof_dev(b200zk_pk* pk, const void* d_advice, const void* const* instance_columns,
+                                const uint32_t* instance_lens, const void* d_rng_wide, const void* transcript_repr,
+                                uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+/* per-phase device times (ms) of the last create_proof: msm, ntt, quotient, lookup, permutation, evals+shplonk, other */
+int32_t b200zk_pk_last_phase_ms(const b200zk_pk* pk, float* out7);
+
 #ifdef __cplusplus
 }
 #endif

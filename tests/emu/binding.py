@@ -96,3 +96,13 @@ def prefix_product(p, z0, m, T):
     lib().emu_prefix_product(_p(p), _p(z), ctypes.c_size_t(p.shape[0]), ctypes.c_size_t(m), ctypes.c_uint32(T),
                              _p(np.ascontiguousarray(z0)))
     return z
+
+
+def transcript(ops, data, n_squeeze):
+    ops = np.asarray(ops, dtype=np.uint8)
+    data = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1)
+    out = np.zeros((max(n_squeeze, 1), 4), dtype=np.uint64)
+    proof = np.zeros(32 * len(ops) + 32, dtype=np.uint8)
+    lib().emu_transcript.restype = ctypes.c_size_t
+    ln = lib().emu_transcript(_p(ops), ctypes.c_size_t(len(ops)), _p(data), _p(out), _p(proof))
+    return out[:n_squeeze], bytes(proof[:ln])

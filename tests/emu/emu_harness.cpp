@@ -10,6 +10,7 @@
 #include "../../halo2-experiments_b200/csrc/msm.cuh"
 #include "../../halo2-experiments_b200/csrc/msm_plan.hpp"
 #include "../../halo2-experiments_b200/csrc/poly.cuh"
+#include "../../halo2-experiments_b200/csrc/transcript.hpp"
 
 using namespace b200zk;
 
@@ -127,6 +128,22 @@ void emu_host_fr_consts(uint64_t* root, uint64_t* zeta, uint64_t* delta, uint64_
     host::HFr::from_u512(wide_in8).store(wide_out);
 }
 
+
+// transcript.hpp: replay a script of ops: 0 = squeeze (writes 32 B Montgomery challenge to out),
+// 1 = common_scalar(next 32 B Montgomery), 2 = write_point(next 64 B affine Montgomery),
+// 3 = write_scalar(next 32 B).  Returns the proof length; proof bytes copied to proof_out.
+size_t emu_transcript(const uint8_t* ops, size_t nops, const uint64_t* data, uint64_t* out, uint8_t* proof_out) {
+    host::Transcript t;
+    size_t d = 0, o = 0;
+    for (size_t i = 0; i < nops; ++i) {
+        if (ops[i] == 0) { t.squeeze_challenge().store(out + 4 * o++); }
+        else if (ops[i] == 1) { t.common_scalar(host::HFr::from_limbs(data + d)); d += 4; }
+        else if (ops[i] == 2) { host::HAffine p{host::HFq::from_limbs(data + d), host::HFq::from_limbs(data + d + 4)}; t.write_point(p); d += 8; }
+        else { t.write_scalar(host::HFr::from_limbs(data + d)); d += 4; }
+    }
+    memcpy(proof_out, t.proof().data(), t.proof().size());
+    return t.proof().size();
+}
 
 // poly.cuh: launch sequences mirrored from poly.cu
 void emu_batch_invert(int which, fe_t* a, size_t n, size_t lanes) {

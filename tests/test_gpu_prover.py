@@ -1,0 +1,83 @@
+"""GPU: create_proof through the C ABI is byte-identical to the oracle's restatement of halo2's
+CPU prover on the same circuit, witness, SRS and RNG stream, and the proof verifies (the
+reference's own assertion, /root/reference/src/circuits/utils.rs:56-63)."""
+import importlib
+
+import numpy as np
+import pytest
+
+from oracle import prover as OP
+
+pytestmark = pytest.mark.gpu
+
+
+def _synth(zk):
+    return importlib.import_module(zk.__name__ + ".circuits_synth")
+
+
+def _mont_ints(orc, vals):
+    return orc.ints_to_mont([v % OP.R for v in vals]) if len(vals) else np.zeros((0, 4), dtype=np.uint64)
+
+
+def _first_diff(a, b):
+    for i in range(0, min(len(a), len(b)), 32):
+        if a[i:i + 32] != b[i:i + 32]:
+            return i // 32
+    return None
+
+
+def _run(zk, backend, orc, job, check_verify=True):
+    s = orc.random_fr(1, 4321)[0]
+    params = zk.ParamsKZG.setup(backend, job.k, s)
+    g, gl = params.read()
+    pk_gpu = zk.ProvingKey(params, job.cs, job.k, job.fixed, job.map_col, job.map_row)
+    assert pk_gpu.blinding_factors == job.cs.blinding_factors() and pk_gpu.degree == job.cs.degree()
+    assert pk_gpu.rng_draws == OP.rng_draws_needed(job.cs, job.k)
+    wide = orc.XorShiftWide().draw(pk_gpu.rng_draws)
+    inst = [_mont_ints(orc, c) for c in job.instances]
+    tr_repr = orc.ints_to_mont([job.transcript_repr])[0]
+    got = pk_gpu.create_proof(job.advice, inst, wide, tr_repr)
+    pk_cpu = OP.keygen_pk(job.cs, job.k, job.fixed, job.map_col, job.map_row)
+    want, _ = OP.create_proof(g, gl, pk_cpu, job.advice, job.instances, wide, job.transcript_repr)
+    assert len(got) == len(want) == pk_gpu.proof_size
+    assert got == want, f"first differing 32-byte item: {_first_diff(got, want)} of {len(want) // 32}"
+    if check_verify:
+        assert OP.verify_full(orc.mont_to_ints(s)[0], g, pk_cpu, job.instances, got, job.transcript_repr)
+    # device-resident entry point gives the same bytes
+    d_adv = backend.to_device(np.concatenate([np.ascontiguousarray(a).reshape(-1, 4) for a in job.advice]))
+    d_wide = backend.to_device(wide)
+    assert pk_gpu.create_proof_dev(d_adv, inst, d_wide, tr_repr) == want
+    d_adv.free(); d_wide.free()
+    pk_gpu.close(); params.close()
+    return got
+
+
+@pytest.mark.parametrize("name,k", [("small", 5), ("small", 6), ("v3_shaped", 6), ("small", 8), ("mst_shaped", 9), ("v3_shaped", 11)])
+def test_proof_bytes_match_oracle(zk, backend, orc, name, k):
+    job = getattr(_synth(zk), name)(k)
+    _run(zk, backend, orc, job, check_verify=(k <= 9))
+
+
+def test_mst_shaped_k12(zk, backend, orc):
+    _run(zk, backend, orc, _synth(zk).mst_shaped(12), check_verify=False)
+
+
+def test_lookup_failure_is_reported(zk, backend, orc):
+    """An input value missing from the table is Error::ConstraintSystemFailure upstream."""
+    synth = _synth(zk)
+    job = synth.small(6)
+    byte_col = 5 + 3 + 2
+    bad = np.array(job.advice[byte_col])
+    bad[3] = orc.ints_to_mont([100000])[0]
+    job.advice[byte_col] = bad
+    s = orc.random_fr(1, 4321)[0]
+    params = zk.ParamsKZG.setup(backend, job.k, s)
+    pk = zk.ProvingKey(params, job.cs, job.k, job.fixed, job.map_col, job.map_row)
+    wide = orc.XorShiftWide().draw(pk.rng_draws)
+    with pytest.raises(zk.B200zkError, match="-5"):
+        pk.create_proof(job.advice, [_mont_ints(orc, c) for c in job.instances], wide, orc.ints_to_mont([job.transcript_repr])[0])
+    with pytest.raises(Exception):          # the oracle rejects the same witness
+        g, gl = params.read()
+        pk_cpu = OP.keygen_pk(job.cs, job.k, job.fixed, job.map_col, job.map_row)
+        OP.create_proof(g, gl, pk_cpu, job.advice, job.instances, wide, job.transcript_repr)
+    pk.close(); params.close()

@@ -149,3 +149,32 @@ def test_poly_primitives_structure(orc):
         assert orc.mont_to_ints(emu.prefix_product(A, orc.ints_to_mont([z0])[0], m, T)) == want
     fq = orc.ints_to_mont([5, 0, 7, P.Q_MOD - 1], orc.FQ)
     assert orc.mont_to_ints(emu.batch_invert(1, fq, 2), orc.FQ) == [pow(5, -1, P.Q_MOD), 0, pow(7, -1, P.Q_MOD), P.Q_MOD - 1]
+
+
+def test_host_transcript_matches_pyref(orc):
+    """The product's BLAKE2b transcript vs hashlib (oracle/pyref.py) incl. the SURVEY KATs."""
+    ch, _ = emu.transcript([0], np.zeros(4, dtype=np.uint64), 1)
+    assert orc.mont_to_ints(ch)[0] == 0x0e89c2c9ef365f095ec7aa36500bb0ba58bf7d5e17194055afb5a1c746f1786a
+    ch, _ = emu.transcript([1, 0], orc.ints_to_mont([1]).reshape(-1), 1)
+    assert orc.mont_to_ints(ch)[0] == 0x1ba5cdb93688afe0b4eaa4bf9094a4fce372769e41db9e398206953797569832
+    # long mixed script (crosses several 128-byte blocks), compared step by step with pyref
+    rnd = random.Random(9)
+    t = P.Blake2bTranscript()
+    ops, data, want = [], [], []
+    pts = [P.g1_mul(P.G1_GEN, rnd.randrange(P.R_MOD)) for _ in range(5)] + [None]
+    for i in range(40):
+        r = rnd.randrange(4)
+        if r == 0:
+            ops.append(0); want.append(t.squeeze_challenge())
+        elif r == 1:
+            s = rnd.randrange(P.R_MOD); ops.append(1); data += list(orc.ints_to_mont([s])[0]); t.common_scalar(s)
+        elif r == 2:
+            p = pts[rnd.randrange(len(pts))]
+            x, y = (0, 0) if p is None else p
+            ops.append(2); data += list(orc.ints_to_mont([x], orc.FQ)[0]) + list(orc.ints_to_mont([y], orc.FQ)[0]); t.write_point(p)
+        else:
+            s = rnd.randrange(P.R_MOD); ops.append(3); data += list(orc.ints_to_mont([s])[0]); t.write_scalar(s)
+    ops.append(0); want.append(t.squeeze_challenge())
+    ch, proof = emu.transcript(ops, np.array(data, dtype=np.uint64), len(want))
+    assert orc.mont_to_ints(ch) == want
+    assert proof == bytes(t.proof)
