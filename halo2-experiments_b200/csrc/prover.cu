@@ -12,6 +12,7 @@
 #include <map>
 #include <new>
 #include <set>
+#include <string>
 
 using namespace b200zk;
 using host::HAffine;
@@ -204,6 +205,7 @@ struct b200zk_pk {
     uint32_t* d_err = nullptr;
     float phase_ms[7] = {0, 0, 0, 0, 0, 0, 0};
     std::vector<void*> owned;
+    std::map<std::string, std::pair<const void*, size_t>> dbg;     // buffers of the last proof, for b200zk_pk_debug_buffer
 };
 
 namespace b200zk {
@@ -367,6 +369,11 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     fe_t* sh_tmp = ar.take<fe_t>(4 * n);
     if (!ar.ok) return fail(ctx, B200ZK_ENOMEM, "create_proof", "arena too small");
     auto LK = [&](uint32_t l, uint32_t which) { return lk_bufs + ((size_t)l * 7 + which) * n; };
+    pk->dbg.clear();
+    pk->dbg["advice_values"] = {advice_values, A * n}; pk->dbg["advice_polys"] = {advice_polys, A * n};
+    pk->dbg["lookups"] = {lk_bufs, 7 * (size_t)L * n}; pk->dbg["perm_polys"] = {perm_polys, (size_t)S * n};
+    pk->dbg["h"] = {h, ext}; pk->dbg["rnd"] = {rnd, draws}; pk->dbg["tmp_n"] = {tmp_n, 3 * n};
+    pk->dbg["advice_cosets"] = {advice_cosets, A * ext}; pk->dbg["h_poly"] = {h_poly, n};
 
     // ---- pointer tables for this proof
     {
@@ -796,6 +803,17 @@ size_t b200zk_pk_proof_size(const b200zk_pk* pk) {
 
 uint32_t b200zk_pk_blinding_factors(const b200zk_pk* pk) { return pk ? pk->cs.bf : 0; }
 uint32_t b200zk_pk_degree(const b200zk_pk* pk) { return pk ? pk->cs.degree : 0; }
+
+// debugging aid: copy a named device buffer of the last proof to the host (elements of 32 bytes)
+int32_t b200zk_pk_debug_buffer(b200zk_pk* pk, const char* name, void* host_out, size_t max_elems, size_t* count) {
+    if (!pk || !name || !host_out) return B200ZK_EINVAL;
+    auto it = pk->dbg.find(name);
+    if (it == pk->dbg.end()) return fail(pk->ctx, B200ZK_EINVAL, "debug_buffer", "unknown buffer");
+    size_t c = std::min(max_elems, it->second.second);
+    if (count) *count = it->second.second;
+    ZK_CUDA(pk->ctx, cudaMemcpy(host_out, it->second.first, c * sizeof(fe_t), cudaMemcpyDeviceToHost));
+    return B200ZK_OK;
+}
 
 int32_t b200zk_pk_last_phase_ms(const b200zk_pk* pk, float* out7) {
     if (!pk || !out7) return B200ZK_EINVAL;

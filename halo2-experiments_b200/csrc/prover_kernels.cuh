@@ -19,9 +19,10 @@ static constexpr int ZK_MAXC = 16;      // columns per permutation set (d - 2) /
 ZK_D fe_t from_u512_row(const uint32_t* wide16) {
     fe_t lo, hi, r2, r3;
     for (int i = 0; i < 8; ++i) { lo.l[i] = wide16[i]; hi.l[i] = wide16[8 + i]; r2.l[i] = FrCfg::r2(i); r3.l[i] = FrCfg::r3(i); }
-    // inputs are arbitrary 256-bit integers (not reduced): the CIOS multiplier accepts any a < 2^256
-    // with b < p and returns a value < 2p that reduce_once brings into range.
-    return Fr::add(Fr::mul(lo, r2), Fr::mul(hi, r3));
+    // lo / hi are arbitrary 256-bit integers (not reduced).  They must be the SECOND operand: the
+    // CIOS rounds keep the accumulator below 2p as long as the first operand is < p, whatever the
+    // 32-bit digits of the second are; an unreduced first operand can overflow the 9-limb window.
+    return Fr::add(Fr::mul(r2, lo), Fr::mul(r3, hi));
 }
 
 // ---- permutation grand product (Lagrange domain) ----

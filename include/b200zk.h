@@ -164,6 +164,8 @@ int32_t b200zk_create_proof(b200zk_pk* pk, const void* const* advice_columns, co
 int32_t b200zk_create_proof_dev(b200zk_pk* pk, const void* d_advice, const void* const* instance_columns,
                                 const uint32_t* instance_lens, const void* d_rng_wide, const void* transcript_repr,
                                 uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+/* debugging aid: copy a named device buffer of the last proof (32-byte elements) to the host */
+int32_t b200zk_pk_debug_buffer(b200zk_pk* pk, const char* name, void* host_out, size_t max_elems, size_t* count);
 /* per-phase device times (ms) of the last create_proof: msm, ntt, quotient, lookup, permutation, evals+shplonk, other */
 int32_t b200zk_pk_last_phase_ms(const b200zk_pk* pk, float* out7);
 

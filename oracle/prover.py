@@ -328,6 +328,7 @@ def create_proof(params_g, params_g_lagrange, pk, advice_in, instances, rng_wide
         rng.one()
         tr.write_point(commit(params_g_lagrange, z))
         lk["z_poly"] = dom.lagrange_to_coeff(z)
+        trace.setdefault("lookup_z", []).append(z)
     # -- vanishing commit
     random_poly = rng.take(n); rng.one()
     tr.write_point(commit(params_g, random_poly))

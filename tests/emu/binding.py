@@ -106,3 +106,10 @@ def transcript(ops, data, n_squeeze):
     lib().emu_transcript.restype = ctypes.c_size_t
     ln = lib().emu_transcript(_p(ops), ctypes.c_size_t(len(ops)), _p(data), _p(out), _p(proof))
     return out[:n_squeeze], bytes(proof[:ln])
+
+
+def from_u512(wide):
+    wide = np.ascontiguousarray(wide, dtype=np.uint64).reshape(-1, 8)
+    out = np.zeros((wide.shape[0], 4), dtype=np.uint64)
+    lib().emu_from_u512(_p(wide), _p(out), ctypes.c_size_t(wide.shape[0]))
+    return out

@@ -11,6 +11,7 @@
 #include "../../halo2-experiments_b200/csrc/msm_plan.hpp"
 #include "../../halo2-experiments_b200/csrc/poly.cuh"
 #include "../../halo2-experiments_b200/csrc/transcript.hpp"
+#include "../../halo2-experiments_b200/csrc/prover_kernels.cuh"
 
 using namespace b200zk;
 
@@ -143,6 +144,11 @@ size_t emu_transcript(const uint8_t* ops, size_t nops, const uint64_t* data, uin
     }
     memcpy(proof_out, t.proof().data(), t.proof().size());
     return t.proof().size();
+}
+
+// prover_kernels.cuh: Fr::random's from_u512 on the device path
+void emu_from_u512(const uint32_t* wide, fe_t* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) out[i] = from_u512_row(wide + 16 * i);
 }
 
 // poly.cuh: launch sequences mirrored from poly.cu

@@ -178,3 +178,15 @@ def test_host_transcript_matches_pyref(orc):
     ch, proof = emu.transcript(ops, np.array(data, dtype=np.uint64), len(want))
     assert orc.mont_to_ints(ch) == want
     assert proof == bytes(t.proof)
+
+
+def test_device_from_u512_unreduced_inputs(orc):
+    """Fr::random on the device path: 512-bit inputs whose halves exceed r (incl. all-ones)."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    wide = rng.integers(0, 1 << 64, size=(20000, 8), dtype=np.uint64)
+    wide[0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    wide[1, :4] = np.uint64(0xFFFFFFFFFFFFFFFF); wide[1, 4:] = 0
+    wide[2] = 0
+    wide[3:200, 3] |= np.uint64(0xFFFFFFFF00000000)       # top limb of the low half near 2^64
+    wide[3:200, 7] |= np.uint64(0xFFFFFFFFF0000000)
+    assert np.array_equal(emu.from_u512(wide), orc.from_u512(wide))
