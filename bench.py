@@ -1,24 +1,28 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the b200zk proving backend.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload msm|ntt] [--log-n L]
-  python bench.py --impl reference ...        # CPU arm: the oracle's restatement of halo2's
-                                              # rayon CPU path on this box's host cores
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload prove|msm|ntt] [--k K] [--log-n L]
+  python bench.py --impl reference ...     # CPU arm: the oracle's restatement of halo2's CPU
+                                           # prover / best_multiexp / best_fft on this box's cores
 
-One "step" = one pass of the hot path over one batch of synthetic input:
-  msm : one best_multiexp over 2^L uniform scalars and 2^L SRS points ([s^i]G, device-generated)
-  ntt : one coeff_to_extended-sized best_fft over 2^L uniform Fr elements
-Prints ONE JSON line (see the task contract): value = device-timed whole-job throughput with
-inputs resident in HBM; e2e = the same through the host-buffer C-ABI call (pinned host scalars
--> H2D -> kernels -> D2H result) ; roofline for the dominant kernel; cpu_baseline on rank 0.
+Workloads (one "step" = one pass of the hot path over one batch of synthetic input):
+  prove (default) : create_proof for the MST-shaped synthetic circuit (20 advice,
+                    8 u8 lookups, 16 permutation columns, degree 6) at k = 20 — BASELINE.json's
+                    headline "create_proof ms (MST k=20)".  SRS and proving key resident in HBM.
+  msm             : one best_multiexp over 2^L uniform scalars and 2^L SRS points
+  ntt             : one best_fft over 2^L uniform Fr elements
+Prints ONE JSON line: value = device-timed with inputs resident in HBM; e2e = the same call through
+the host-buffer C-ABI entry point (pinned host witness / scalars -> H2D -> kernels -> D2H proof);
+roofline for the dominant kernel; cpu_baseline on rank 0.  With N > 1 every rank proves its own
+instance (weak scaling, no data-path collective); time is the max over ranks.
 """
 import argparse
+import importlib
 import json
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -30,6 +34,11 @@ sys.path.insert(0, ROOT)
 # IMAD.WIDE.U32 issues at 32 lanes/clk/SM -> 9.19e12 wide multiply-adds per second
 IMAD_WIDE_PEAK = 9.19e12
 MUL32_PER_FIELD_MUL = 136           # 8x8 product + 8x8 reduction + 8 (m = t0 * inv)
+
+
+def msm_work_mul32(n):
+    """SURVEY.md §8(d) accounting (c = 16, W = 16): (N*16*11 + 2*65536*16*16) * 136 mul32."""
+    return (n * 16 * 11 + 2 * 65536 * 16 * 16) * MUL32_PER_FIELD_MUL
 
 
 def measured_peaks():
@@ -77,13 +86,13 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
@@ -91,11 +100,11 @@ class ClockSampler:
                     reasons.add(name)
         os.unlink(self.path)
         if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "power_w_max": max(pw), "reasons": sorted(reasons), "samples": len(sm)}
         return out
 
 
-def dist_setup(n_gpus):
+def dist_setup():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -125,76 +134,116 @@ def barrier(dist, be):
         torch.cuda.synchronize()
 
 
+def timed(be, dist, local, steps, fn):
+    """CUDA events on the library's stream around `steps` calls, max over ranks -> total ms."""
+    barrier(dist, be)
+    be.event_record(0)
+    for _ in range(steps):
+        fn()
+    be.event_record(1)
+    be.sync()
+    ms = be.event_elapsed_ms(0, 1)
+    barrier(dist, be)
+    return max_over_ranks(dist, local, ms)
+
+
+WORKLOAD_TEXT = {
+    "prove": "create_proof (KZG/SHPLONK/Blake2b), MST-shaped synthetic circuit k={k}: 20 advice, 8 u8 lookups, 16 permutation columns, degree 6, ext 8n; SRS + pk resident in HBM",
+    "msm": "bn256 G1 MSM 2^{L} points (best_multiexp drop-in), uniform scalars, bases [s^i]G resident in HBM",
+    "ntt": "bn256 Fr NTT 2^{L} (best_fft drop-in), uniform input",
+}
+
+
 # --------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     from __graft_entry__ import load_package
     zk = load_package()
-    rank, world, local, dist = dist_setup(args.gpus)
+    rank, world, local, dist = dist_setup()
     be = zk.Backend(local)
     peaks, peak_src = measured_peaks()
-    L = args.log_n
-    n = 1 << L
-    line = {"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "data": "synthetic", "impl": "b200zk"}
+    line = {"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "scaling": "weak", "vs_baseline": None,
+            "data": "synthetic", "impl": "b200zk"}
+    extra = {}
+    if args.workload == "prove":
+        k = args.k
+        n = 1 << k
+        synth = importlib.import_module(zk.__name__ + ".circuits_synth")
+        job = synth.mst_shaped(k, seed=1 + rank)
+        params = zk.ParamsKZG.setup(be, k, random_scalars(1, 4242)[0])
+        pk = zk.ProvingKey(params, job.cs, k, job.fixed, job.map_col, job.map_row)
+        A = job.cs.num_advice
+        h_adv = be.pinned_empty((A * n, 4))
+        for c in range(A):
+            h_adv[c * n:(c + 1) * n] = job.advice[c]
+        h_cols = [h_adv[c * n:(c + 1) * n] for c in range(A)]
+        h_wide = be.pinned_empty((pk.rng_draws, 8))
+        h_wide[:] = np.random.Generator(np.random.PCG64(99 + rank)).integers(0, 1 << 64, size=(pk.rng_draws, 8), dtype=np.uint64)
+        d_adv, d_wide = be.to_device(h_adv), be.to_device(h_wide)
+        lut = synth.mont_from_ints(job.instances[0] + [job.transcript_repr])
+        inst, tr_repr = [lut[:-1]], lut[-1]
 
-    if args.workload == "msm":
-        s = random_scalars(1, 4242)[0]
-        params = zk.ParamsKZG.setup(be, L, s)                      # SRS resident in HBM, generated on device
+        def step_dev():
+            return pk.create_proof_dev(d_adv, inst, d_wide, tr_repr)
+
+        def step_e2e():
+            return pk.create_proof(h_cols, inst, h_wide, tr_repr)
+
+        unit, metric, hib = "ms", "create_proof_ms", False
+        h2d, d2h = int(h_adv.nbytes + h_wide.nbytes), pk.proof_size
+        dtype = "u32x8 Montgomery (bn256 Fr/Fq, IMAD pipe)"
+        workload = WORKLOAD_TEXT["prove"].format(k=k)
+    elif args.workload == "msm":
+        L = args.log_n
+        n = 1 << L
+        params = zk.ParamsKZG.setup(be, L, random_scalars(1, 4242)[0])
         h_scalars = be.pinned_empty((n, 4))
         random_scalars(n, 100 + rank, out=h_scalars)
         d_scalars = be.to_device(h_scalars)
-        launches0 = be.launch_count()
 
         def step_dev():
             return params.commit_dev(d_scalars, n, lagrange=False)
 
         def step_e2e():
-            return params.commit(h_scalars)                        # H2D n*32 B + kernels + D2H 96 B
+            return params.commit(h_scalars)
 
-        unit, metric = "Mpts/s", "msm_mpts_per_s"
+        unit, metric, hib = "Mpts/s", "msm_mpts_per_s", True
         units_per_step = n / 1e6
         h2d, d2h = n * 32, 96
         dtype = "u32x8 Montgomery (bn256 Fq/Fr, IMAD pipe)"
-        workload = f"bn256 G1 MSM 2^{L} points (best_multiexp drop-in), uniform scalars, bases [s^i]G resident in HBM"
+        workload = WORKLOAD_TEXT["msm"].format(L=L)
     else:
+        import ctypes
+        L = args.log_n
+        n = 1 << L
         dom = zk.EvaluationDomain(be, 2, L)
         h_a = be.pinned_empty((n, 4))
         random_scalars(n, 200 + rank, out=h_a)
         d_a = be.to_device(h_a)
         omega = dom.omega
-        launches0 = be.launch_count()
 
         def step_dev():
             be.best_fft_dev(d_a, omega, L)
 
         def step_e2e():
-            lib = zk.lib()
-            be._check(lib.b200zk_fft(be._ctx, h_a.ctypes.data_as(__import__("ctypes").c_void_p),
-                                     omega.ctypes.data_as(__import__("ctypes").c_void_p), L))
+            be._check(zk.lib().b200zk_fft(be._ctx, h_a.ctypes.data_as(ctypes.c_void_p), omega.ctypes.data_as(ctypes.c_void_p), L))
 
-        unit, metric = "GB/s", "ntt_gb_per_s"
-        units_per_step = 64.0 * n / 1e9                             # compulsory bytes: read + write once
+        unit, metric, hib = "GB/s", "ntt_gb_per_s", True
+        units_per_step = 64.0 * n / 1e9
         h2d, d2h = n * 32, n * 32
         dtype = "u32x8 Montgomery (bn256 Fr, IMAD pipe)"
-        workload = f"bn256 Fr NTT 2^{L} (best_fft drop-in), uniform input"
+        workload = WORKLOAD_TEXT["ntt"].format(L=L)
 
     # ---- device-timed region: inputs resident in HBM --------------------------------
     for _ in range(max(args.warmup, 3)):
         step_dev()
-    barrier(dist, be)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = be.launch_count()
-    be.event_record(0)
-    for _ in range(args.steps):
-        step_dev()
-    be.event_record(1)
-    be.sync()
-    ms_local = be.event_elapsed_ms(0, 1)
-    launches = be.launch_count() - l0
-    barrier(dist, be)
-    ms = max_over_ranks(dist, local, ms_local)
+    ms = timed(be, dist, local, args.steps, step_dev)
+    launches = (be.launch_count() - l0) // args.steps
+    if args.workload == "prove":
+        extra["phase_ms"] = pk.last_phase_ms()
     # ---- end-to-end region: host buffers through the C ABI ---------------------------
     for _ in range(2):
         step_e2e()
@@ -203,33 +252,49 @@ def run_gpu(args):
     for _ in range(args.steps):
         step_e2e()
     be.sync()
-    e2e_ms = max_over_ranks(dist, local, (time.perf_counter() - t0) * 1e3)
+    e2e_ms = max_over_ranks(dist, local, (time.perf_counter() - t0) * 1e3) / args.steps
     clocks = sampler.stop() if rank == 0 else None
 
     ms_per_step = ms / args.steps
-    value = units_per_step * world / (ms_per_step / 1e3)
-    e2e_value = units_per_step * world / (e2e_ms / args.steps / 1e3)
-    line.update({"metric": metric, "unit": unit, "value": value, "ms_per_step": ms_per_step, "dtype": dtype,
-                 "config": {"workload": workload, "log_n": L, "l2": "inputs larger than L2" if n * 32 > 126e6 else "inputs fit L2; timed back to back"},
-                 "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                         "ms_per_step": e2e_ms / args.steps},
+    if args.workload == "prove":
+        value, e2e_value = ms_per_step, e2e_ms
+        extra["proofs_per_s_all_gpus"] = world / (ms_per_step / 1e3)
+    else:
+        value = units_per_step * world / (ms_per_step / 1e3)
+        e2e_value = units_per_step * world / (e2e_ms / 1e3)
+    line.update({"metric": metric, "unit": unit, "value": value, "ms_per_step": ms_per_step, "higher_is_better": hib, "dtype": dtype,
+                 "config": {"workload": workload, "l2": "working set larger than L2 (126 MB); steps timed back to back"},
+                 "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
                  "gpu_launches": int(launches), "clocks": clocks})
 
-    if args.workload == "msm":
-        # work model of SURVEY §8(d): c = 16, W = 16: (N*16*11 + 2*65536*16*16) * 136 mul32
-        work = (n * 16 * 11 + 2 * 65536 * 16 * 16) * MUL32_PER_FIELD_MUL
-        ach = work / (ms_per_step / 1e3)
-        line["roofline"] = {"bound": "imad", "achieved": ach / 1e12, "peak": IMAD_WIDE_PEAK / 1e12, "unit": "T IMAD.WIDE/s",
-                            "frac": ach / IMAD_WIDE_PEAK, "traffic": None,
-                            "note": "peak = measured IMAD.WIDE.U32 issue rate (tools/imad_bench.cu); whole-MSM time, accumulate kernel dominates"}
+    # ---- roofline of the dominant kernel ------------------------------------------------
+    if args.workload in ("prove", "msm"):
+        if args.workload == "prove":
+            # dominant kernel = msm_accumulate inside the ~56 commits; time one dense commit of the
+            # same size on the same SRS with events (the random_poly commit of the proof)
+            d_dense = be.to_device(random_scalars(n, 5))
+            for _ in range(3):
+                params.commit_dev(d_dense, n, lagrange=False)
+            reps = 5
+            ms_msm = timed(be, dist, local, reps, lambda: params.commit_dev(d_dense, n, lagrange=False)) / reps
+            share = extra["phase_ms"]["msm"] / max(sum(extra["phase_ms"].values()), 1e-9)
+        else:
+            ms_msm, share = ms_per_step, 1.0
+        ach = msm_work_mul32(n) / (ms_msm / 1e3)
+        line["roofline"] = {"bound": "imad", "kernel": f"MSM 2^{int(np.log2(n))} (msm_accumulate dominates)", "achieved": ach / 1e12,
+                            "peak": IMAD_WIDE_PEAK / 1e12, "unit": "T IMAD.WIDE.U32/s", "frac": ach / IMAD_WIDE_PEAK, "traffic": None,
+                            "ms_per_launch_group": ms_msm, "share_of_step": share,
+                            "note": "no HBM/tensor bound applies: 254-bit Montgomery arithmetic is IMAD-pipe bound; peak = measured "
+                                    "IMAD.WIDE.U32 issue rate on this B200 (tools/imad_bench.cu, profiles/r01_imad_microbench.jsonl); "
+                                    "work per SURVEY.md 8(d)"}
     else:
         ach = 64.0 * n / (ms_per_step / 1e3) / 1e9
         line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                             "traffic": None, "peak_source": peak_src,
                             "note": "254-bit butterflies are IMAD-bound on B200 (see DESIGN.md): 64N bytes vs ~15N field muls"}
-
+    line.update(extra)
     if rank == 0:
-        line["cpu_baseline"] = cpu_baseline(args, zk, be, params if args.workload == "msm" else None)
+        line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
     barrier(dist, be)
     be.close()
@@ -238,86 +303,91 @@ def run_gpu(args):
 
 
 # --------------------------------------------------------------------------- CPU legs
-def cpu_baseline(args, zk, be, params):
-    """The oracle's restatement of halo2's CPU algorithm, on a bounded sample, all host cores."""
+def cpu_sample(args):
+    """(callable, units, description, scale) for the oracle's restatement on a bounded sample."""
+    from __graft_entry__ import load_package
     from oracle import binding as orc
-    cores = orc.get_threads()
-    if args.workload == "msm":
-        Ls = min(args.log_n, args.cpu_log_n)
-        ns = 1 << Ls
-        g, _ = params.read(lagrange=False)
-        bases = np.ascontiguousarray(g[:ns])
-        sc = random_scalars(ns, 7)
-        t0 = time.perf_counter()
-        orc.best_multiexp(sc, bases)
-        dt = time.perf_counter() - t0
-        return {"value": ns / 1e6 / dt, "unit": "Mpts/s", "cores": cores, "kind": "port",
-                "sample": f"best_multiexp restatement on 2^{Ls} of the same points, {dt:.2f} s"}
+    from oracle import pyref
+    orc.build()
+    if args.workload == "prove":
+        from oracle import prover as OP
+        zk = load_package()
+        synth = importlib.import_module(zk.__name__ + ".circuits_synth")
+        ks = min(args.k, args.cpu_k)
+        job = synth.mst_shaped(ks, seed=1)
+        g, gl = orc.params_setup(ks, orc.random_fr(1, 4242)[0])
+        pk = OP.keygen_pk(job.cs, ks, job.fixed, job.map_col, job.map_row)
+        wide = np.random.Generator(np.random.PCG64(99)).integers(0, 1 << 64, size=(OP.rng_draws_needed(job.cs, ks), 8), dtype=np.uint64)
+        fn = lambda: OP.create_proof(g, gl, pk, job.advice, job.instances, wide, job.transcript_repr)
+        return fn, None, f"oracle create_proof (restatement of halo2 v2023_02_02 CPU prover) on the same circuit at k={ks}", float(1 << (args.k - ks))
     Ls = min(args.log_n, args.cpu_log_n)
     ns = 1 << Ls
+    if args.workload == "msm":
+        bases, _ = orc.params_setup(Ls, orc.random_fr(1, 4242)[0], with_lagrange=False)
+        sc = random_scalars(ns, 7)
+        return (lambda: orc.best_multiexp(sc, bases)), ns / 1e6, f"best_multiexp restatement on 2^{Ls} points", 1.0
     a = random_scalars(ns, 8)
-    from oracle import pyref
     w = orc.ints_to_mont([pyref.omega_for_k(Ls)])[0]
+    return (lambda: orc.best_fft(a, w, Ls)), 64.0 * ns / 1e9, f"best_fft restatement on 2^{Ls} elements", 1.0
+
+
+def cpu_baseline(args):
+    from oracle import binding as orc
+    fn, units, desc, scale = cpu_sample(args)
     t0 = time.perf_counter()
-    orc.best_fft(a, w, Ls)
+    fn()
     dt = time.perf_counter() - t0
-    return {"value": 64.0 * ns / 1e9 / dt, "unit": "GB/s", "cores": cores, "kind": "port",
-            "sample": f"best_fft restatement on 2^{Ls} elements, {dt:.2f} s"}
+    cores = orc.get_threads()
+    if args.workload == "prove":
+        return {"value": dt * 1e3 * scale, "unit": "ms", "cores": cores, "kind": "port", "measured_ms": dt * 1e3,
+                "sample": f"{desc}: {dt:.1f} s measured, x{scale:g} linear extrapolation to k={args.k} (MSM/NTT are n log n, so this flatters the CPU)"}
+    return {"value": units / dt, "unit": "Mpts/s" if args.workload == "msm" else "GB/s", "cores": cores, "kind": "port",
+            "sample": f"{desc}, {dt:.2f} s"}
 
 
 def run_reference(args):
     """--impl reference: halo2's CPU algorithm (oracle restatement; the Rust crate cannot be built
     here) on this box's host cores, same metric/config, each step a bounded sample."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle import binding as orc
-    from oracle import pyref
-    orc.build()
+    fn, units, desc, scale = cpu_sample(args)
     cores = orc.get_threads()
-    Ls = min(args.log_n, args.cpu_log_n)
-    ns = 1 << Ls
-    if args.workload == "msm":
-        s = orc.random_fr(1, 4242)[0]
-        bases, _ = orc.params_setup(Ls, s, with_lagrange=False)
-        sc = random_scalars(ns, 7)
-        fn = lambda: orc.best_multiexp(sc, bases)
-        units, unit, metric = ns / 1e6, "Mpts/s", "msm_mpts_per_s"
-        workload = f"bn256 G1 MSM 2^{args.log_n} points (best_multiexp drop-in), uniform scalars, bases [s^i]G resident in HBM"
-    else:
-        a = random_scalars(ns, 8)
-        w = orc.ints_to_mont([pyref.omega_for_k(Ls)])[0]
-        fn = lambda: orc.best_fft(a, w, Ls)
-        units, unit, metric = 64.0 * ns / 1e9, "GB/s", "ntt_gb_per_s"
-        workload = f"bn256 Fr NTT 2^{args.log_n} (best_fft drop-in), uniform input"
     for _ in range(min(args.warmup, 1)):
         fn()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         fn()
     dt = (time.perf_counter() - t0) / args.steps
-    v = units / dt
+    if args.workload == "prove":
+        v, unit, metric, hib = dt * 1e3 * scale, "ms", "create_proof_ms", False
+        workload = WORKLOAD_TEXT["prove"].format(k=args.k)
+        sample = f"{desc}: {dt:.1f} s per step measured, x{scale:g} linear extrapolation to k={args.k}"
+    else:
+        v = units / dt
+        unit, metric, hib = ("Mpts/s", "msm_mpts_per_s", True) if args.workload == "msm" else ("GB/s", "ntt_gb_per_s", True)
+        workload = WORKLOAD_TEXT[args.workload].format(L=args.log_n)
+        sample = f"{desc} per step"
     print(json.dumps({"impl": "reference", "metric": metric, "unit": unit, "value": v, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": hib,
                       "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 Montgomery (CPU)", "data": "synthetic",
-                      "config": {"workload": workload, "log_n": args.log_n},
-                      "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port",
-                                       "sample": f"2^{Ls} units per step of the 2^{args.log_n} workload"},
+                      "config": {"workload": workload},
+                      "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
                       "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200zk", choices=["b200zk", "reference"])
-    ap.add_argument("--workload", default="msm", choices=["msm", "ntt"])
-    ap.add_argument("--log-n", type=int, default=None)
-    ap.add_argument("--cpu-log-n", type=int, default=None, help="size of the bounded CPU sample")
+    ap.add_argument("--workload", default="prove", choices=["prove", "msm", "ntt"])
+    ap.add_argument("--k", type=int, default=20, help="prove: circuit size")
+    ap.add_argument("--cpu-k", type=int, default=14, help="prove: size of the bounded CPU sample")
+    ap.add_argument("--log-n", type=int, default=24, help="msm / ntt size")
+    ap.add_argument("--cpu-log-n", type=int, default=None, help="msm / ntt: size of the bounded CPU sample")
     args = ap.parse_args()
-    if args.log_n is None:
-        args.log_n = 24 if args.workload == "msm" else 24
     if args.cpu_log_n is None:
         args.cpu_log_n = 20 if args.workload == "msm" else 22
     if args.impl == "reference":

@@ -271,6 +271,29 @@ class XorShiftWide:
         return out
 
 
+def prefix_product(p, z0):
+    p = np.ascontiguousarray(p, dtype=np.uint64).reshape(-1, 4)
+    z = _arr(p.shape[0])
+    lib().orc_prefix_product(_p(p), _p(np.ascontiguousarray(z0, dtype=np.uint64)), _p(z), ctypes.c_size_t(p.shape[0]))
+    return z
+
+
+def powers(base, n):
+    out = _arr(n)
+    lib().orc_powers(_p(np.ascontiguousarray(base, dtype=np.uint64)), _p(out), ctypes.c_size_t(n))
+    return out
+
+
+def permute_expression_pair(inp, tab, usable):
+    inp = np.ascontiguousarray(inp, dtype=np.uint64).reshape(-1, 4)
+    tab = np.ascontiguousarray(tab, dtype=np.uint64).reshape(-1, 4)
+    a, s = _arr(usable), _arr(usable)
+    rc = lib().orc_permute_expression_pair(_p(inp), _p(tab), ctypes.c_size_t(usable), _p(a), _p(s))
+    if rc:
+        raise ValueError("ConstraintSystemFailure: lookup input not in table")
+    return a, s
+
+
 def sort_canonical(raw):
     raw = np.array(raw, dtype=np.uint64).reshape(-1, 4)
     lib().orc_sort_canonical(_p(raw), ctypes.c_size_t(raw.shape[0]))

@@ -6,6 +6,7 @@
 #include "arith.hpp"
 #include <cstdio>
 #include <algorithm>
+#include <map>
 
 using namespace orc;
 
@@ -190,6 +191,56 @@ void orc_xorshift_fill_wide(uint32_t* state, uint64_t* out, size_t count) {
         out[i] = (uint64_t)lo | ((uint64_t)hi << 32);
     }
     state[0] = x; state[1] = y; state[2] = z; state[3] = w;
+}
+
+// z[0] = z0, z[i] = z[i-1] * p[i-1]  (the serial grand-product loops of permutation/lookup provers)
+void orc_prefix_product(const uint64_t* p, const uint64_t* z0, uint64_t* z, size_t n) {
+    init_fields();
+    const Fr* P = (const Fr*)p; Fr* Z = (Fr*)z;
+    Fr run = *(const Fr*)z0;
+    for (size_t i = 0; i < n; ++i) { Z[i] = run; run = run * P[i]; }
+}
+
+// out[i] = base^i
+void orc_powers(const uint64_t* base, uint64_t* out, size_t n) {
+    init_fields();
+    Fr b = *(const Fr*)base, cur = Fr::one();
+    for (size_t i = 0; i < n; ++i) { ((Fr*)out)[i] = cur; cur *= b; }
+}
+
+// lookup::prover::permute_expression_pair on the first `usable` rows (halo2_proofs v2023_02_02
+// plonk/lookup/prover.rs): sort the input, BTreeMap multiset of the table, fill repeated rows
+// from the leftover table values in ascending order, popping rows from the back.
+// Returns 0 on success, 1 if an input value is missing from the table (ConstraintSystemFailure).
+int orc_permute_expression_pair(const uint64_t* input, const uint64_t* table, size_t usable, uint64_t* a_out, uint64_t* s_out) {
+    init_fields();
+    struct Less { bool operator()(const Fr& x, const Fr& y) const { return Fr::less(x, y); } };
+    std::vector<Fr> a((const Fr*)input, (const Fr*)input + usable);
+    // sort by canonical value; compare on canonical limbs to avoid repeated conversions
+    std::vector<std::array<uint64_t, 5>> keyed(usable);
+    for (size_t i = 0; i < usable; ++i) { uint64_t r[4]; a[i].to_raw(r); keyed[i] = {r[3], r[2], r[1], r[0], (uint64_t)i}; }
+    std::stable_sort(keyed.begin(), keyed.end(), [](const std::array<uint64_t, 5>& x, const std::array<uint64_t, 5>& y) {
+        for (int i = 0; i < 4; ++i) if (x[i] != y[i]) return x[i] < y[i];
+        return false;
+    });
+    std::vector<Fr> sorted(usable);
+    for (size_t i = 0; i < usable; ++i) sorted[i] = a[keyed[i][4]];
+    std::map<Fr, uint32_t, Less> leftover;
+    for (size_t i = 0; i < usable; ++i) leftover[((const Fr*)table)[i]] += 1;
+    std::vector<Fr> s(usable, Fr::zero());
+    std::vector<size_t> repeated;
+    for (size_t row = 0; row < usable; ++row) {
+        if (row == 0 || sorted[row] != sorted[row - 1]) {
+            s[row] = sorted[row];
+            auto it = leftover.find(sorted[row]);
+            if (it == leftover.end() || it->second == 0) return 1;
+            it->second -= 1;
+        } else repeated.push_back(row);
+    }
+    for (auto& kv : leftover) for (uint32_t c = 0; c < kv.second; ++c) { s[repeated.back()] = kv.first; repeated.pop_back(); }
+    if (!repeated.empty()) return 1;
+    memcpy(a_out, sorted.data(), usable * 32); memcpy(s_out, s.data(), usable * 32);
+    return 0;
 }
 
 // sort rows of canonical 4xu64 values ascending by numeric value (halo2curves `Ord for Fr`)

@@ -125,11 +125,8 @@ class ProvingKey:
 def sigma_from_mapping(dom, map_col, map_row):
     """permutation::keygen::Assembly::build_pk: sigma_i[j] = delta^col * omega^row of the mapped cell."""
     n = dom.n
-    w, d = I(dom.omega), P.FR_DELTA
-    omega_pows = [1] * n
-    for i in range(1, n):
-        omega_pows[i] = omega_pows[i - 1] * w % R
-    om = B.ints_to_mont(omega_pows)
+    d = P.FR_DELTA
+    om = B.powers(dom.omega, n)
     out = []
     for c in range(map_col.shape[0]):
         col = om[map_row[c]]
@@ -199,7 +196,15 @@ def lagrange_interpolate(points, evals):
 
 
 def permute_expression_pair(inp, tab, usable, rng, bf):
-    """lookup::prover::permute_expression_pair (SURVEY Appendix A.4)."""
+    """lookup::prover::permute_expression_pair (SURVEY Appendix A.4); C++ restatement for speed."""
+    a_sorted, s_vals = B.permute_expression_pair(inp, tab, usable)
+    a_full = np.concatenate([a_sorted, rng.take(bf + 1)])
+    s_full = np.concatenate([s_vals, rng.take(bf + 1)])
+    return a_full, s_full
+
+
+def permute_expression_pair_py(inp, tab, usable):
+    """The same algorithm in plain Python (cross-check of the C++ restatement in tests)."""
     a_sorted_raw = B.sort_canonical(B.to_raw(inp[:usable]))
     a_sorted = B.from_raw(a_sorted_raw)
     keys = [tuple(r) for r in a_sorted_raw[:, ::-1].tolist()]          # most significant limb first
@@ -221,10 +226,7 @@ def permute_expression_pair(inp, tab, usable, rng, bf):
         for _ in range(leftover[key]):
             s_raw[repeated.pop()] = np.array(key[::-1], dtype=np.uint64)
     assert not repeated
-    s_vals = B.from_raw(s_raw)
-    a_full = np.concatenate([a_sorted, rng.take(bf + 1)])
-    s_full = np.concatenate([s_vals, rng.take(bf + 1)])
-    return a_full, s_full
+    return a_sorted, B.from_raw(s_raw)
 
 
 # ------------------------------------------------------------------ create_proof
@@ -286,11 +288,7 @@ def create_proof(params_g, params_g_lagrange, pk, advice_in, instances, rng_wide
     chunk = cs.permutation_chunk_len()
     omega_pows = None
     if cs.permutation:
-        w = I(dom.omega)
-        pw = [1] * n
-        for i in range(1, n):
-            pw[i] = pw[i - 1] * w % R
-        omega_pows = B.ints_to_mont(pw)
+        omega_pows = B.powers(dom.omega, n)
     last_z, deltaomega = 1, 1
     for s0 in range(0, len(cs.permutation), chunk):
         cols = cs.permutation[s0:s0 + chunk]
@@ -303,12 +301,7 @@ def create_proof(params_g, params_g_lagrange, pk, advice_in, instances, rng_wide
             v = perm_column_values(ct, ci)
             mod = vmul(mod, vadd(vadds(vscale(omega_pows, deltaomega * beta % R), gamma), v))
             deltaomega = deltaomega * P.FR_DELTA % R
-        z = np.zeros((n, 4), dtype=np.uint64)
-        zi = [last_z]
-        mi = B.mont_to_ints(mod)
-        for row in range(1, n):
-            zi.append(zi[-1] * mi[row - 1] % R)
-        z[:] = B.ints_to_mont(zi)
+        z = B.prefix_product(mod, M(last_z))
         z[n - bf:] = rng.take(bf)
         last_z = I(z[n - (bf + 1)])
         rng.one()
@@ -320,11 +313,7 @@ def create_proof(params_g, params_g_lagrange, pk, advice_in, instances, rng_wide
         den = vmul(vadds(lk["pin"], beta), vadds(lk["ptab"], gamma))
         den = B.batch_invert(den)
         prod = vmul(vmul(den, vadds(lk["cin"], beta)), vadds(lk["ctab"], gamma))
-        pi = B.mont_to_ints(prod)
-        zi = [1]
-        for row in range(1, n - bf):
-            zi.append(zi[-1] * pi[row - 1] % R)
-        z = np.concatenate([B.ints_to_mont(zi), rng.take(bf)])
+        z = np.concatenate([B.prefix_product(prod, M(1))[: n - bf], rng.take(bf)])
         rng.one()
         tr.write_point(commit(params_g_lagrange, z))
         lk["z_poly"] = dom.lagrange_to_coeff(z)
@@ -353,11 +342,7 @@ def create_proof(params_g, params_g_lagrange, pk, advice_in, instances, rng_wide
             prev_last = np.roll(sets[si - 1]["coset"], -last_rot * rot_scale, axis=0)
             h = fold(h, vmul(vsub(sets[si]["coset"], prev_last), pk.l0))
         # beta_term[idx] = extended_omega^idx ; current_delta = beta * zeta * beta_term * delta^j
-        ew = I(dom.extended_omega)
-        pw = [1] * ext_n
-        for i in range(1, ext_n):
-            pw[i] = pw[i - 1] * ew % R
-        ext_pows = B.ints_to_mont(pw)
+        ext_pows = B.powers(dom.extended_omega, ext_n)
         delta_pow = 1
         cos_cols = {0: adv_cos, 1: pk.fixed_cosets, 2: inst_cos}
         for si, s0 in enumerate(range(0, len(cs.permutation), chunk)):

@@ -73,3 +73,18 @@ def test_unsatisfied_witness_is_rejected(zk, orc):
     except AssertionError:
         ok = False
     assert not ok
+
+
+def test_permute_expression_pair_cpp_matches_python(orc):
+    import random
+    rnd = random.Random(3)
+    u = 300
+    table = [rnd.randrange(40) for _ in range(u)]
+    inp = [rnd.choice(table) for _ in range(u)]
+    I_, T_ = orc.ints_to_mont(inp), orc.ints_to_mont(table)
+    a1, s1 = orc.permute_expression_pair(I_, T_, u)
+    a2, s2 = OP.permute_expression_pair_py(I_, T_, u)
+    assert np.array_equal(a1, a2) and np.array_equal(s1, s2)
+    assert sorted(orc.mont_to_ints(s1)) == sorted(table) and orc.mont_to_ints(a1) == sorted(inp)
+    with pytest.raises(ValueError):
+        orc.permute_expression_pair(orc.ints_to_mont([1, 2, 99]), orc.ints_to_mont([1, 2, 3]), 3)
