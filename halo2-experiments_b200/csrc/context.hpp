@@ -39,7 +39,7 @@ struct b200zk_ctx {
     int sm_count = 148;
     int msm_force_c = 0;
     std::map<std::array<uint64_t, 5>, b200zk::NttPlan> ntt_plans;     // key: log_n + omega limbs
-    b200zk::Workspace ntt_scratch, msm_ws, io_a, io_b, poly_ws, poly_heads, setup_ws, lookup_ws;
+    b200zk::Workspace ntt_scratch, msm_ws, msm_ws2, io_a, io_b, poly_ws, poly_heads, setup_ws, lookup_ws;
     b200zk::affine_t* d_gen_table = nullptr;                          // fixed-base table of the G1 generator (setup.cu)
     void* pinned = nullptr;                                            // small pinned staging (results)
 };

@@ -1,6 +1,7 @@
 // Launch side of the Pippenger MSM (see msm.cuh for the pipeline and the reference mapping).
 #include "context.hpp"
 #include "msm.cuh"
+#include <cmath>
 
 namespace b200zk {
 
@@ -8,6 +9,7 @@ static constexpr uint32_t MSM_DIGIT_THREADS = 256;
 static constexpr uint32_t MSM_ACC_THREADS = 128;
 static constexpr uint32_t MSM_SCAN_THREADS = 256;
 static constexpr uint32_t MSM_FOLD_THREADS = 128;
+static constexpr uint32_t MSM_FAST_MAX = 96;        // thread-per-bucket while no bucket exceeds this many entries
 
 __global__ void __launch_bounds__(MSM_DIGIT_THREADS) msm_count_kernel(const MsmArgs a) {
     msm_count_thread(a, blockIdx.x * blockDim.x + threadIdx.x);
@@ -15,20 +17,29 @@ __global__ void __launch_bounds__(MSM_DIGIT_THREADS) msm_count_kernel(const MsmA
 __global__ void __launch_bounds__(MSM_DIGIT_THREADS) msm_scatter_kernel(const MsmArgs a) {
     msm_scatter_thread(a, blockIdx.x * blockDim.x + threadIdx.x);
 }
-__global__ void __launch_bounds__(MSM_SCAN_THREADS) msm_scan_blocksum_kernel(const MsmArgs a, uint32_t* blocksums) {
+__global__ void __launch_bounds__(MSM_SCAN_THREADS) scan_blocksum_kernel(const ScanArgs s) {
     __shared__ uint32_t sm[2 * MSM_SCAN_THREADS];
-    msm_scan_blocksum_block(a, blocksums, blockIdx.x, blockDim.x, sm);
+    scan_blocksum_block(s, blockIdx.x, blockDim.x, sm);
 }
-__global__ void __launch_bounds__(MSM_SCAN_THREADS) msm_scan_top_kernel(const MsmArgs a, uint32_t* blocksums, uint32_t nblocks) {
+__global__ void __launch_bounds__(MSM_SCAN_THREADS) scan_top_kernel(const ScanArgs s, uint32_t nblocks) {
     __shared__ uint32_t sm[2 * MSM_SCAN_THREADS];
-    msm_scan_top_block(a, blocksums, nblocks, blockDim.x, sm);
+    scan_top_block(s, nblocks, blockDim.x, sm);
 }
-__global__ void __launch_bounds__(MSM_SCAN_THREADS) msm_scan_final_kernel(const MsmArgs a, const uint32_t* blocksums) {
+__global__ void __launch_bounds__(MSM_SCAN_THREADS) scan_final_kernel(const ScanArgs s) {
     __shared__ uint32_t sm[2 * MSM_SCAN_THREADS];
-    msm_scan_final_block(a, blocksums, blockIdx.x, blockDim.x, sm);
+    scan_final_block(s, blockIdx.x, blockDim.x, sm);
 }
 __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_accumulate_kernel(const MsmArgs a) {
     msm_accumulate_thread(a, blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_accumulate_task_kernel(const MsmArgs a, const MsmTaskArgs t) {
+    msm_accumulate_task_thread(a, t, blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_combine_task_kernel(const MsmTaskArgs t) {
+    msm_combine_task_thread(t, blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_combine_bucket_kernel(const MsmTaskArgs t) {
+    msm_combine_bucket_thread(t, blockIdx.x * blockDim.x + threadIdx.x);
 }
 __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_reduce_kernel(const MsmArgs a) {
     msm_reduce_thread(a, blockIdx.x * blockDim.x + threadIdx.x);
@@ -39,22 +50,33 @@ __global__ void __launch_bounds__(MSM_FOLD_THREADS) msm_fold_kernel(const MsmArg
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static unsigned nb(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+static void run_scan(b200zk_ctx* ctx, ScanArgs s) {
+    const uint32_t items = MSM_SCAN_THREADS * MSM_SCAN_PER_THREAD;
+    const uint32_t blocks = (s.total + items - 1) / items;
+    scan_blocksum_kernel<<<blocks, MSM_SCAN_THREADS, 0, ctx->stream>>>(s);
+    scan_top_kernel<<<1, MSM_SCAN_THREADS, 0, ctx->stream>>>(s, blocks);
+    scan_final_kernel<<<blocks, MSM_SCAN_THREADS, 0, ctx->stream>>>(s);
+    ctx->launches += 3;
+}
 
 int32_t msm_run(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, host::HAffine* out) {
     if (n == 0) { *out = {host::HFq::zero(), host::HFq::zero()}; return B200ZK_OK; }
     if (n >= ((size_t)1 << 31)) return fail(ctx, B200ZK_EINVAL, "msm_run", "len must be < 2^31");
     MsmShape s = msm_plan_shape(n, ctx->msm_force_c);
+    const uint32_t B = (uint32_t)s.nbuckets;
     // workspace layout
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    size_t o_counts = take(s.nbuckets * 4), o_offsets = take((s.nbuckets + 1) * 4), o_cursor = take(s.nbuckets * 4);
+    size_t o_counts = take((size_t)B * 4 + 4), o_offsets = take(((size_t)B + 1) * 4), o_cursor = take((size_t)B * 4);
     size_t o_entries = take(n * s.nwin * 4);
-    size_t o_buckets = take(s.nbuckets * sizeof(xyzz_t));
+    size_t o_buckets = take((size_t)B * sizeof(xyzz_t));
     size_t o_partials = take(((size_t)s.nwin << s.log_t) * sizeof(xyzz_t));
     size_t o_wsum = take(s.nwin * sizeof(xyzz_t));
     const uint32_t scan_items = MSM_SCAN_THREADS * MSM_SCAN_PER_THREAD;
-    const uint32_t scan_blocks = (uint32_t)((s.nbuckets + scan_items - 1) / scan_items);
-    size_t o_bsums = take((size_t)scan_blocks * 4);
+    size_t o_bsums = take((size_t)((B + scan_items - 1) / scan_items) * 4);
+    size_t o_toff1 = take(((size_t)B + 1) * 4), o_toff2 = take(((size_t)B + 1) * 4);
     ZK_TRY(ws_reserve(ctx, ctx->msm_ws, off));
     char* base = (char*)ctx->msm_ws.p;
     MsmArgs a{};
@@ -63,21 +85,47 @@ int32_t msm_run(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases,
     a.counts = (uint32_t*)(base + o_counts); a.offsets = (uint32_t*)(base + o_offsets); a.cursor = (uint32_t*)(base + o_cursor);
     a.entries = (uint32_t*)(base + o_entries);
     a.buckets = (xyzz_t*)(base + o_buckets); a.partials = (xyzz_t*)(base + o_partials); a.window_sums = (xyzz_t*)(base + o_wsum);
+    uint32_t* d_max = a.counts + B;                         // one extra word after the histogram
+    uint32_t* bsums = (uint32_t*)(base + o_bsums);
 
     cudaStream_t st = ctx->stream;
-    ZK_CUDA(ctx, cudaMemsetAsync(a.counts, 0, s.nbuckets * 4, st));
-    unsigned nb = (unsigned)((n + MSM_DIGIT_THREADS - 1) / MSM_DIGIT_THREADS);
-    msm_count_kernel<<<nb, MSM_DIGIT_THREADS, 0, st>>>(a);
-    uint32_t* bsums = (uint32_t*)(base + o_bsums);
-    msm_scan_blocksum_kernel<<<scan_blocks, MSM_SCAN_THREADS, 0, st>>>(a, bsums);
-    msm_scan_top_kernel<<<1, MSM_SCAN_THREADS, 0, st>>>(a, bsums, scan_blocks);
-    msm_scan_final_kernel<<<scan_blocks, MSM_SCAN_THREADS, 0, st>>>(a, bsums);
-    msm_scatter_kernel<<<nb, MSM_DIGIT_THREADS, 0, st>>>(a);
-    msm_accumulate_kernel<<<(unsigned)((s.nbuckets + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
+    ZK_CUDA(ctx, cudaMemsetAsync(a.counts, 0, (size_t)B * 4 + 4, st));
+    msm_count_kernel<<<nb(n, MSM_DIGIT_THREADS), MSM_DIGIT_THREADS, 0, st>>>(a);
+    ctx->launches++;
+    run_scan(ctx, ScanArgs{a.counts, a.offsets, a.cursor, bsums, d_max, B, 0, 0});
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, d_max, 4, cudaMemcpyDeviceToHost, st));
+    msm_scatter_kernel<<<nb(n, MSM_DIGIT_THREADS), MSM_DIGIT_THREADS, 0, st>>>(a);
+    ctx->launches++;
+    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t maxcnt = *(const uint32_t*)ctx->pinned;
+
+    if (maxcnt <= MSM_FAST_MAX) {
+        msm_accumulate_kernel<<<nb(B, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
+        ctx->launches++;
+    } else {
+        // three balanced levels with segment length L ~ cbrt(largest bucket)
+        uint32_t L = (uint32_t)std::ceil(std::cbrt((double)maxcnt));
+        if (L < 32) L = 32;
+        const size_t t1_bound = n * (size_t)s.nwin / L + B;
+        const size_t t2_bound = t1_bound / L + B;
+        ZK_TRY(ws_reserve(ctx, ctx->msm_ws2, (t1_bound + t2_bound) * sizeof(xyzz_t) + 512));
+        xyzz_t* partial1 = (xyzz_t*)ctx->msm_ws2.p;
+        xyzz_t* partial2 = partial1 + t1_bound;
+        uint32_t *toff1 = (uint32_t*)(base + o_toff1), *toff2 = (uint32_t*)(base + o_toff2);
+        run_scan(ctx, ScanArgs{a.counts, toff1, nullptr, bsums, nullptr, B, 0, L});
+        MsmTaskArgs t1{a.offsets, toff1, B, toff1 + B, L, nullptr, partial1};
+        msm_accumulate_task_kernel<<<nb(t1_bound, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a, t1);
+        run_scan(ctx, ScanArgs{toff1, toff2, nullptr, bsums, nullptr, B, 1, L});
+        MsmTaskArgs t2{toff1, toff2, B, toff2 + B, L, partial1, partial2};
+        msm_combine_task_kernel<<<nb(t2_bound, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(t2);
+        MsmTaskArgs t3{toff2, nullptr, B, nullptr, 0, partial2, a.buckets};
+        msm_combine_bucket_kernel<<<nb(B, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(t3);
+        ctx->launches += 3;
+    }
     size_t nred = (size_t)s.nwin << s.log_t;
-    msm_reduce_kernel<<<(unsigned)((nred + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
+    msm_reduce_kernel<<<nb(nred, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
     msm_fold_kernel<<<s.nwin, MSM_FOLD_THREADS, 0, st>>>(a);
-    ctx->launches += 8;
+    ctx->launches += 2;
     ZK_CUDA(ctx, cudaGetLastError());
     ZK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, a.window_sums, s.nwin * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
     ZK_CUDA(ctx, cudaStreamSynchronize(st));

@@ -79,10 +79,32 @@ ZK_D void msm_scatter_thread(const MsmArgs& a, uint32_t i) {
     });
 }
 
-// Exclusive scan of counts[0..total) into offsets[0..total] and cursor, three launches:
-//   (1) per-block sums of SCAN_ITEMS consecutive counters, (2) single-block scan of the block
-//   sums, (3) per-block scan + block offset.  Each thread owns 8 consecutive counters.
+// ---- exclusive scans (three launches: per-block sums, single-block scan of the sums, per-block
+// scan + offset; each thread owns 8 consecutive items) --------------------------------------
+// Scanned value of item i:  v = from_offsets ? in[i+1] - in[i] : in[i];  if div: v = max(1, ceil(v / div)).
 static constexpr uint32_t MSM_SCAN_PER_THREAD = 8;
+
+struct ScanArgs {
+    const uint32_t* in;
+    uint32_t* out;              // [total + 1]
+    uint32_t* out2;             // optional copy of out[0..total) (scatter cursors)
+    uint32_t* blocksums;
+    uint32_t* maxv;             // optional: atomicMax of the raw (undivided) values
+    uint32_t total, from_offsets, div;
+};
+
+ZK_D uint32_t scan_raw(const ScanArgs& s, uint32_t i) { return s.from_offsets ? s.in[i + 1] - s.in[i] : s.in[i]; }
+ZK_D uint32_t scan_value(const ScanArgs& s, uint32_t i) {
+    uint32_t v = scan_raw(s, i);
+    if (s.div) { v = (v + s.div - 1) / s.div; if (v == 0) v = 1; }
+    return v;
+}
+
+#if defined(__CUDACC__)
+ZK_D void zk_atomic_max(uint32_t* p, uint32_t v) { atomicMax(p, v); }
+#else
+inline void zk_atomic_max(uint32_t* p, uint32_t v) { if (v > *p) *p = v; }
+#endif
 
 // Hillis-Steele inclusive scan of sm[0..T) (ping-pong in sm[0..2T)); returns the buffer index.
 ZK_D uint32_t msm_block_inclusive_scan(uint32_t* sm, uint32_t T) {
@@ -98,55 +120,61 @@ ZK_D uint32_t msm_block_inclusive_scan(uint32_t* sm, uint32_t T) {
     return cur;
 }
 
-// (1) blocksums[bid] = sum of the block's counters.  sm: 2*T words.
-ZK_D void msm_scan_blocksum_block(const MsmArgs& a, uint32_t* blocksums, uint32_t bid, uint32_t T, uint32_t* sm) {
-    const uint32_t total = a.nwin << (a.c - 1);
+// (1) blocksums[bid] = sum of the block's items (+ running max of the raw values).  sm: 2*T words.
+ZK_D void scan_blocksum_block(const ScanArgs& s, uint32_t bid, uint32_t T, uint32_t* sm) {
     ZK_PHASE_BEGIN(tid, T)
-    uint32_t base = (bid * T + tid) * MSM_SCAN_PER_THREAD, s = 0;
-    for (uint32_t i = 0; i < MSM_SCAN_PER_THREAD; ++i) if (base + i < total) s += a.counts[base + i];
-    sm[tid] = s;
+    uint32_t base = (bid * T + tid) * MSM_SCAN_PER_THREAD, sum = 0, mx = 0;
+    for (uint32_t i = 0; i < MSM_SCAN_PER_THREAD; ++i) if (base + i < s.total) {
+        sum += scan_value(s, base + i);
+        uint32_t r = scan_raw(s, base + i); if (r > mx) mx = r;
+    }
+    sm[tid] = sum;
+    if (s.maxv && mx) zk_atomic_max(s.maxv, mx);
     ZK_PHASE_END
     uint32_t cur = msm_block_inclusive_scan(sm, T);
     ZK_PHASE_BEGIN(tid, T)
-    if (tid == T - 1) blocksums[bid] = sm[cur * T + tid];
+    if (tid == T - 1) s.blocksums[bid] = sm[cur * T + tid];
     ZK_PHASE_END
 }
 
-// (2) in-place exclusive scan of blocksums[0..nblocks) by one block; grand total to offsets[total].
-ZK_D void msm_scan_top_block(const MsmArgs& a, uint32_t* blocksums, uint32_t nblocks, uint32_t T, uint32_t* sm) {
-    const uint32_t total = a.nwin << (a.c - 1);
+// (2) in-place exclusive scan of blocksums[0..nblocks) by one block; grand total to out[total].
+ZK_D void scan_top_block(const ScanArgs& s, uint32_t nblocks, uint32_t T, uint32_t* sm) {
     const uint32_t per = (nblocks + T - 1) / T;
     ZK_PHASE_BEGIN(tid, T)
-    uint32_t s = 0, b = tid * per, e = b + per < nblocks ? b + per : nblocks;
-    for (uint32_t k = b; k < e; ++k) s += blocksums[k];
-    sm[tid] = s;
+    uint32_t sum = 0, b = tid * per, e = b + per < nblocks ? b + per : nblocks;
+    for (uint32_t k = b; k < e; ++k) sum += s.blocksums[k];
+    sm[tid] = sum;
     ZK_PHASE_END
     uint32_t cur = msm_block_inclusive_scan(sm, T);
     ZK_PHASE_BEGIN(tid, T)
     uint32_t run = tid ? sm[cur * T + tid - 1] : 0, b = tid * per, e = b + per < nblocks ? b + per : nblocks;
-    for (uint32_t k = b; k < e; ++k) { uint32_t v = blocksums[k]; blocksums[k] = run; run += v; }
-    if (tid == T - 1) a.offsets[total] = sm[cur * T + tid];
+    for (uint32_t k = b; k < e; ++k) { uint32_t v = s.blocksums[k]; s.blocksums[k] = run; run += v; }
+    if (tid == T - 1) s.out[s.total] = sm[cur * T + tid];
     ZK_PHASE_END
 }
 
-// (3) offsets / cursor for the block's counters.
-ZK_D void msm_scan_final_block(const MsmArgs& a, const uint32_t* blocksums, uint32_t bid, uint32_t T, uint32_t* sm) {
-    const uint32_t total = a.nwin << (a.c - 1);
+// (3) out / out2 for the block's items.
+ZK_D void scan_final_block(const ScanArgs& s, uint32_t bid, uint32_t T, uint32_t* sm) {
     ZK_PHASE_BEGIN(tid, T)
-    uint32_t base = (bid * T + tid) * MSM_SCAN_PER_THREAD, s = 0;
-    for (uint32_t i = 0; i < MSM_SCAN_PER_THREAD; ++i) if (base + i < total) s += a.counts[base + i];
-    sm[tid] = s;
+    uint32_t base = (bid * T + tid) * MSM_SCAN_PER_THREAD, sum = 0;
+    for (uint32_t i = 0; i < MSM_SCAN_PER_THREAD; ++i) if (base + i < s.total) sum += scan_value(s, base + i);
+    sm[tid] = sum;
     ZK_PHASE_END
     uint32_t cur = msm_block_inclusive_scan(sm, T);
     ZK_PHASE_BEGIN(tid, T)
     uint32_t base = (bid * T + tid) * MSM_SCAN_PER_THREAD;
-    uint32_t run = blocksums[bid] + (tid ? sm[cur * T + tid - 1] : 0);
+    uint32_t run = s.blocksums[bid] + (tid ? sm[cur * T + tid - 1] : 0);
     for (uint32_t i = 0; i < MSM_SCAN_PER_THREAD; ++i) {
-        if (base + i < total) { a.offsets[base + i] = run; a.cursor[base + i] = run; run += a.counts[base + i]; }
+        if (base + i < s.total) {
+            uint32_t v = scan_value(s, base + i);       // read before write: out may alias nothing, but keep order explicit
+            s.out[base + i] = run; if (s.out2) s.out2[base + i] = run; run += v;
+        }
     }
     ZK_PHASE_END
 }
 
+// ---- bucket accumulation ---------------------------------------------------------------------
+// Fast path (every bucket has at most L entries): one thread per bucket.
 ZK_D void msm_accumulate_thread(const MsmArgs& a, uint32_t key) {
     if (key >= (a.nwin << (a.c - 1))) return;
     uint32_t b = a.offsets[key], e = a.offsets[key + 1];
@@ -156,6 +184,65 @@ ZK_D void msm_accumulate_thread(const MsmArgs& a, uint32_t key) {
         xyzz_madd(acc, a.bases[en >> 1], en & 1);
     }
     a.buckets[key] = acc;
+}
+
+// General path: witness columns put millions of points into a handful of buckets (bits, bytes,
+// small integers), so buckets are cut into tasks of at most L entries and reduced in three
+// balanced levels:  entries -> partial1 (per task) -> partial2 (per task of tasks) -> bucket.
+// task_off* are exclusive scans of max(1, ceil(count / L)); the owning bucket of a task is found
+// by binary search in the scan.
+struct MsmTaskArgs {
+    const uint32_t* seg_off;    // offsets of the items being reduced, per bucket   [nb + 1]
+    const uint32_t* task_off;   // tasks per bucket, scanned                         [nb + 1]
+    uint32_t nb;
+    const uint32_t* ntasks_ptr; // device word holding the task count (= task_off[nb]); launches over-provision
+    uint32_t L;
+    const xyzz_t* in;           // level >= 2: partial sums of the level below
+    xyzz_t* out;                // one sum per task
+};
+
+ZK_D uint32_t upper_bound_u32(const uint32_t* a, uint32_t n, uint32_t v) {   // first i with a[i] > v
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (a[mid] <= v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+ZK_D void msm_task_range(const MsmTaskArgs& t, uint32_t task, uint32_t& begin, uint32_t& end) {
+    uint32_t b = upper_bound_u32(t.task_off, t.nb + 1, task) - 1;
+    uint32_t seg = task - t.task_off[b];
+    begin = t.seg_off[b] + seg * t.L;
+    uint32_t stop = t.seg_off[b + 1];
+    end = begin + t.L < stop ? begin + t.L : stop;
+    if (begin > stop) begin = end = stop;                 // the single task of an empty bucket
+}
+
+ZK_D void msm_accumulate_task_thread(const MsmArgs& a, const MsmTaskArgs& t, uint32_t task) {
+    if (task >= *t.ntasks_ptr) return;
+    uint32_t b, e;
+    msm_task_range(t, task, b, e);
+    xyzz_t acc = xyzz_identity();
+    for (uint32_t k = b; k < e; ++k) {
+        uint32_t en = a.entries[k];
+        xyzz_madd(acc, a.bases[en >> 1], en & 1);
+    }
+    t.out[task] = acc;
+}
+
+ZK_D void msm_combine_task_thread(const MsmTaskArgs& t, uint32_t task) {
+    if (task >= *t.ntasks_ptr) return;
+    uint32_t b, e;
+    msm_task_range(t, task, b, e);
+    xyzz_t acc = xyzz_identity();
+    for (uint32_t k = b; k < e; ++k) xyzz_add(acc, t.in[k]);
+    t.out[task] = acc;
+}
+
+// last level: bucket b = sum of its (few) level-2 partials
+ZK_D void msm_combine_bucket_thread(const MsmTaskArgs& t, uint32_t b) {
+    if (b >= t.nb) return;
+    xyzz_t acc = xyzz_identity();
+    for (uint32_t k = t.seg_off[b]; k < t.seg_off[b + 1]; ++k) xyzz_add(acc, t.in[k]);
+    t.out[b] = acc;
 }
 
 // gid -> (window j, chunk t).  Chunk covers bucket indices [b0, b0 + m), bucket b has

@@ -52,11 +52,12 @@ def ntt(a, log_n, omega, n_in=None, max_log_m=10, max_log_tw=2, tile_cap_log=12,
     return out
 
 
-def msm(scalars, bases, force_c=0):
+def msm(scalars, bases, force_c=0, fast_max=96, seg_len=32):
     scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
     bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
     out = np.zeros(8, dtype=np.uint64)
-    lib().emu_msm(_p(scalars), _p(bases), ctypes.c_uint32(scalars.shape[0]), ctypes.c_int(force_c), _p(out))
+    lib().emu_msm(_p(scalars), _p(bases), ctypes.c_uint32(scalars.shape[0]), ctypes.c_int(force_c),
+                  ctypes.c_int(fast_max), ctypes.c_uint32(seg_len), _p(out))
     return out
 
 

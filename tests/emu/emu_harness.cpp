@@ -83,7 +83,7 @@ void emu_ntt(const fe_t* in, uint32_t n_in, fe_t* out, uint32_t log_n, const fe_
 
 // Full MSM through the block programs of msm.cuh + the host finish of msm_plan.hpp.
 // out_affine: 64 bytes (x, y Montgomery).
-void emu_msm(const fe_t* scalars, const affine_t* bases, uint32_t n, int force_c, uint32_t* out_affine64) {
+void emu_msm(const fe_t* scalars, const affine_t* bases, uint32_t n, int force_c, int fast_max, uint32_t seg_len, uint32_t* out_affine64) {
     MsmShape s = msm_plan_shape(n, force_c);
     std::vector<uint32_t> counts(s.nbuckets, 0), offsets(s.nbuckets + 1), cursor(s.nbuckets), entries((size_t)n * s.nwin + 1);
     std::vector<xyzz_t> buckets(s.nbuckets), partials((size_t)s.nwin << s.log_t), wsum(s.nwin);
@@ -92,16 +92,35 @@ void emu_msm(const fe_t* scalars, const affine_t* bases, uint32_t n, int force_c
     a.counts = counts.data(); a.offsets = offsets.data(); a.cursor = cursor.data(); a.entries = entries.data();
     a.buckets = buckets.data(); a.partials = partials.data(); a.window_sums = wsum.data();
     for (uint32_t i = 0; i < n; ++i) msm_count_thread(a, i);
-    {   // mirrors the three scan launches of msm.cu with a small block size
+    const uint32_t B = (uint32_t)s.nbuckets;
+    uint32_t maxcnt = 0;
+    auto scan = [&](ScanArgs sa) {   // mirrors run_scan() of msm.cu with a small block size
         const uint32_t T = 4, items = T * MSM_SCAN_PER_THREAD;
-        const uint32_t nb = (uint32_t)((s.nbuckets + items - 1) / items);
+        const uint32_t nb = (sa.total + items - 1) / items;
         std::vector<uint32_t> bs(nb), sm(2 * T);
-        for (uint32_t b = 0; b < nb; ++b) msm_scan_blocksum_block(a, bs.data(), b, T, sm.data());
-        msm_scan_top_block(a, bs.data(), nb, T, sm.data());
-        for (uint32_t b = 0; b < nb; ++b) msm_scan_final_block(a, bs.data(), b, T, sm.data());
-    }
+        sa.blocksums = bs.data();
+        for (uint32_t b = 0; b < nb; ++b) scan_blocksum_block(sa, b, T, sm.data());
+        scan_top_block(sa, nb, T, sm.data());
+        for (uint32_t b = 0; b < nb; ++b) scan_final_block(sa, b, T, sm.data());
+    };
+    scan(ScanArgs{a.counts, a.offsets, a.cursor, nullptr, &maxcnt, B, 0, 0});
     for (uint32_t i = 0; i < n; ++i) msm_scatter_thread(a, i);
-    for (uint32_t k = 0; k < s.nbuckets; ++k) msm_accumulate_thread(a, k);
+    if ((int)maxcnt <= fast_max) {
+        for (uint32_t k = 0; k < B; ++k) msm_accumulate_thread(a, k);
+    } else {
+        uint32_t L = seg_len;
+        size_t t1_bound = (size_t)n * s.nwin / L + B, t2_bound = t1_bound / L + B;
+        std::vector<uint32_t> toff1(B + 1), toff2(B + 1);
+        std::vector<xyzz_t> p1(t1_bound), p2(t2_bound);
+        scan(ScanArgs{a.counts, toff1.data(), nullptr, nullptr, nullptr, B, 0, L});
+        MsmTaskArgs t1{a.offsets, toff1.data(), B, toff1.data() + B, L, nullptr, p1.data()};
+        for (uint32_t t = 0; t < t1_bound; ++t) msm_accumulate_task_thread(a, t1, t);
+        scan(ScanArgs{toff1.data(), toff2.data(), nullptr, nullptr, nullptr, B, 1, L});
+        MsmTaskArgs t2{toff1.data(), toff2.data(), B, toff2.data() + B, L, p1.data(), p2.data()};
+        for (uint32_t t = 0; t < t2_bound; ++t) msm_combine_task_thread(t2, t);
+        MsmTaskArgs t3{toff2.data(), nullptr, B, nullptr, 0, p2.data(), a.buckets};
+        for (uint32_t b = 0; b < B; ++b) msm_combine_bucket_thread(t3, b);
+    }
     for (uint32_t g = 0; g < (s.nwin << s.log_t); ++g) msm_reduce_thread(a, g);
     std::vector<xyzz_t> smx(8);
     for (uint32_t j = 0; j < s.nwin; ++j) msm_fold_block(a, j, 8, smx.data());

@@ -211,3 +211,29 @@ def test_params_setup_large_consistency(zk, backend, orc):
     want = orc.g1_fixed_base_mul(orc.ints_to_mont([pow(sp, i, pyref.R_MOD) for i in idx]))
     assert np.array_equal(g[idx], want)
     d.close(); params.close()
+
+
+@pytest.mark.parametrize("kind", ["bits", "bytes", "u40", "one-bucket", "mixed"])
+def test_best_multiexp_skewed_columns(backend, orc, kind):
+    """Witness-like columns (bits, bytes, small integers) put thousands of points in a few buckets:
+    exercises the task-balanced accumulation path."""
+    k = 15
+    n = 1 << k
+    g, _ = _setup(orc, k)
+    rng = np.random.Generator(np.random.PCG64(7))
+    if kind == "bits":
+        vals = rng.integers(0, 2, size=n)
+    elif kind == "bytes":
+        vals = rng.integers(0, 256, size=n)
+    elif kind == "u40":
+        vals = rng.integers(0, 1 << 40, size=n)
+    elif kind == "one-bucket":
+        vals = np.full(n, 3)
+    else:
+        vals = np.where(rng.integers(0, 4, size=n) == 0, rng.integers(0, 1 << 62, size=n), rng.integers(0, 2, size=n))
+    lut_keys, inv = np.unique(vals, return_inverse=True)
+    S = orc.ints_to_mont([int(v) for v in lut_keys])[inv]
+    if kind == "mixed":
+        S[: n // 8] = orc.random_fr(n // 8, 3)           # a dense stretch on top
+    got = backend.best_multiexp(S, g)
+    assert np.array_equal(_affine(got), orc.g1_batch_normalize(orc.best_multiexp(S, g))[0])

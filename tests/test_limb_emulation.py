@@ -190,3 +190,20 @@ def test_device_from_u512_unreduced_inputs(orc):
     wide[3:200, 3] |= np.uint64(0xFFFFFFFF00000000)       # top limb of the low half near 2^64
     wide[3:200, 7] |= np.uint64(0xFFFFFFFFF0000000)
     assert np.array_equal(emu.from_u512(wide), orc.from_u512(wide))
+
+
+@pytest.mark.parametrize("seg_len", [2, 3, 7])
+def test_msm_task_balanced_accumulation(orc, seg_len):
+    """General (three-level, task-balanced) bucket accumulation forced on, incl. skewed columns."""
+    rnd = random.Random(400 + seg_len)
+    n = 150
+    ks = [rnd.randrange(P.R_MOD) for _ in range(n)]
+    bases = orc.g1_fixed_base_mul(orc.ints_to_mont(ks))
+    for name, ss in (("uniform", [rnd.randrange(P.R_MOD) for _ in range(n)]),
+                     ("bits", [rnd.randrange(2) for _ in range(n)]),
+                     ("bytes", [rnd.randrange(256) for _ in range(n)]),
+                     ("one-bucket", [3] * n),
+                     ("sparse", [0] * (n - 3) + [5, 0, 7])):
+        S = orc.ints_to_mont(ss)
+        got = emu.msm(S, bases, force_c=5, fast_max=0, seg_len=seg_len)
+        assert np.array_equal(got, orc.g1_batch_normalize(orc.best_multiexp(S, bases))[0]), name
