@@ -254,6 +254,10 @@ def run_gpu(args):
     be.sync()
     e2e_ms = max_over_ranks(dist, local, (time.perf_counter() - t0) * 1e3) / args.steps
     clocks = sampler.stop() if rank == 0 else None
+    if args.profile_step:                       # one extra step inside cudaProfilerStart/Stop for ncu
+        be.profiler_range(True)
+        step_dev()
+        be.profiler_range(False)
 
     ms_per_step = ms / args.steps
     if args.workload == "prove":
@@ -387,6 +391,7 @@ def main():
     ap.add_argument("--cpu-k", type=int, default=14, help="prove: size of the bounded CPU sample")
     ap.add_argument("--log-n", type=int, default=24, help="msm / ntt size")
     ap.add_argument("--cpu-log-n", type=int, default=None, help="msm / ntt: size of the bounded CPU sample")
+    ap.add_argument("--profile-step", action="store_true", help="bracket one extra step with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.cpu_log_n is None:
         args.cpu_log_n = 20 if args.workload == "msm" else 22

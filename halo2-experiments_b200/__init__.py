@@ -119,6 +119,9 @@ class Backend:
     def sync(self):
         self._check(lib().b200zk_sync(self._ctx))
 
+    def profiler_range(self, start):
+        self._check(lib().b200zk_profiler_range(self._ctx, ctypes.c_int32(1 if start else 0)))
+
     def launch_count(self):
         return int(lib().b200zk_launch_count(self._ctx))
 

@@ -1,6 +1,7 @@
 // C ABI of libb200zk.so (declarations and reference mapping: include/b200zk.h).
 #include "context.hpp"
 #include <new>
+#include <cuda_profiler_api.h>
 
 using namespace b200zk;
 using host::HFr;
@@ -82,6 +83,13 @@ int32_t b200zk_sync(b200zk_ctx* ctx) {
 }
 
 uint64_t b200zk_launch_count(const b200zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t b200zk_profiler_range(b200zk_ctx* ctx, int32_t start) {
+    if (!ctx) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (start) ZK_CUDA(ctx, cudaProfilerStart()); else ZK_CUDA(ctx, cudaProfilerStop());
+    return B200ZK_OK;
+}
 
 int32_t b200zk_event_record(b200zk_ctx* ctx, uint32_t slot) {
     if (!ctx || slot >= 64) return B200ZK_EINVAL;

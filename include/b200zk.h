@@ -49,6 +49,8 @@ const char* b200zk_last_error(const b200zk_ctx* ctx);
 int32_t b200zk_sync(b200zk_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t b200zk_launch_count(const b200zk_ctx* ctx);
+/* cudaProfilerStart / cudaProfilerStop (for `ncu --profile-from-start off` captures of one step) */
+int32_t b200zk_profiler_range(b200zk_ctx* ctx, int32_t start);
 /* CUDA events on the ctx stream, for device-side timing of the calls in between */
 int32_t b200zk_event_record(b200zk_ctx* ctx, uint32_t slot /* < 64 */);
 int32_t b200zk_event_elapsed_ms(b200zk_ctx* ctx, uint32_t from_slot, uint32_t to_slot, float* ms);
