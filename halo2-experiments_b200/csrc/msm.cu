@@ -2,6 +2,7 @@
 #include "context.hpp"
 #include "msm.cuh"
 #include <cmath>
+#include <cstdlib>
 
 namespace b200zk {
 
@@ -9,7 +10,10 @@ static constexpr uint32_t MSM_DIGIT_THREADS = 256;
 static constexpr uint32_t MSM_ACC_THREADS = 128;
 static constexpr uint32_t MSM_SCAN_THREADS = 256;
 static constexpr uint32_t MSM_FOLD_THREADS = 128;
-static constexpr uint32_t MSM_FAST_MAX = 96;        // thread-per-bucket while no bucket exceeds this many entries
+// thread-per-bucket only while no bucket exceeds this many entries; beyond that the task-balanced
+// path wins even for uniform scalars (Poisson bucket sizes leave warps waiting for their longest
+// bucket: 5.09 ms -> 4.6 ms for a dense 2^20 MSM, profiles/r01_sweep_tunables.jsonl)
+static constexpr uint32_t MSM_FAST_MAX = 16;
 
 __global__ void __launch_bounds__(MSM_DIGIT_THREADS) msm_count_kernel(const MsmArgs a) {
     msm_count_thread(a, blockIdx.x * blockDim.x + threadIdx.x);
@@ -99,13 +103,18 @@ int32_t msm_run(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases,
     ZK_CUDA(ctx, cudaStreamSynchronize(st));
     const uint32_t maxcnt = *(const uint32_t*)ctx->pinned;
 
-    if (maxcnt <= MSM_FAST_MAX) {
+    uint32_t fast_max = MSM_FAST_MAX;
+    if (const char* e = getenv("B200ZK_MSM_FAST_MAX")) fast_max = (uint32_t)strtoul(e, nullptr, 10);
+    uint32_t seg_min = 16;
+    if (const char* e = getenv("B200ZK_MSM_SEG_MIN")) seg_min = (uint32_t)strtoul(e, nullptr, 10);
+    if (maxcnt <= fast_max) {
         msm_accumulate_kernel<<<nb(B, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
         ctx->launches++;
     } else {
         // three balanced levels with segment length L ~ cbrt(largest bucket)
         uint32_t L = (uint32_t)std::ceil(std::cbrt((double)maxcnt));
-        if (L < 32) L = 32;
+        if (L < seg_min) L = seg_min;
+        if (L < 2) L = 2;
         const size_t t1_bound = n * (size_t)s.nwin / L + B;
         const size_t t2_bound = t1_bound / L + B;
         ZK_TRY(ws_reserve(ctx, ctx->msm_ws2, (t1_bound + t2_bound) * sizeof(xyzz_t) + 512));

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cstddef>
+#include <cstdlib>
 #include "host_field.hpp"
 
 namespace b200zk {
@@ -23,7 +24,9 @@ inline MsmShape msm_plan_shape(size_t n, int force_c = 0) {
     s.c = c;
     s.nwin = (255 + c - 1) / c;
     uint32_t log_b = c - 1;
-    s.log_t = log_b > 5 ? log_b - 5 : 0;                // 32 buckets per reduce thread
+    uint32_t log_m = 5;                                 // 32 buckets per reduce thread
+    if (const char* e = getenv("B200ZK_MSM_REDUCE_M")) { long v = strtol(e, nullptr, 10); if (v >= 1 && v <= 8) log_m = (uint32_t)v; }
+    s.log_t = log_b > log_m ? log_b - log_m : 0;
     s.nbuckets = (size_t)s.nwin << (c - 1);
     return s;
 }

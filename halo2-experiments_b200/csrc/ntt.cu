@@ -28,7 +28,15 @@ __global__ void fr_scale_periodic_kernel(fe_t* a, size_t n, const fe_t* m, uint3
 static fe_t to_dev(const host::HFr& x) { fe_t r; memcpy(r.l, x.v, 32); return r; }
 
 static int32_t build_plan(b200zk_ctx* ctx, uint32_t log_n, const host::HFr& omega, NttPlan& plan) {
-    plan.shape = ntt_plan_shape(log_n, NTT_MAX_LOG_M, NTT_MAX_LOG_TW, NTT_TILE_CAP_LOG);
+    // tuning overrides (profiling sweeps): B200ZK_NTT_MAX_M / _MAX_TW / _TILE_CAP, log2 values
+    auto tune = [](const char* name, uint32_t dflt, uint32_t lo, uint32_t hi) {
+        const char* e = getenv(name);
+        if (!e) return dflt;
+        long v = strtol(e, nullptr, 10);
+        return (v < (long)lo || v > (long)hi) ? dflt : (uint32_t)v;
+    };
+    plan.shape = ntt_plan_shape(log_n, tune("B200ZK_NTT_MAX_M", NTT_MAX_LOG_M, 2, NTT_MAX_LOG_M),
+                                tune("B200ZK_NTT_MAX_TW", NTT_MAX_LOG_TW, 0, 5), tune("B200ZK_NTT_TILE_CAP", NTT_TILE_CAP_LOG, 6, 12));
     const NttShape& s = plan.shape;
     size_t n_roots = (size_t)1 << (s.log_roots ? s.log_roots - 1 : 0);
     size_t n_lo = (size_t)1 << s.tw_lo_bits, n_hi = ((size_t)1 << log_n) >> s.tw_lo_bits;

@@ -64,6 +64,30 @@ template <class F, int CHAINS> __global__ void __launch_bounds__(256) k_mul(fe_t
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// FP64 pipe: DFMA alone (MIX = 0) and DFMA interleaved 1:1 with the lo.cc/hi IMAD.WIDE pair (MIX = 1)
+template <int MIX> __global__ void __launch_bounds__(256) k_dfma(double* out, double a0, uint32_t b0, long long* cycles) {
+    double x[8];
+    uint32_t u[8], v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[i] = a0 + threadIdx.x + i; u[i] = b0 + i; v[i] = b0 * 3 + i; }
+    double a = a0 * 1.0000001, b = a0 * 0.5;
+    uint32_t ia = b0 | 1, ib = b0 | 3;
+    long long t0 = clock64();
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x[i]) : "d"(a), "d"(b));
+            if (MIX) asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(u[i]), "+r"(v[i]) : "r"(ia), "r"(ib));
+        }
+    }
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i] + (double)(u[i] ^ v[i]);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 static double median_cycles(long long* d_cycles, int blocks) {
     long long* h = new long long[blocks];
     cudaMemcpy(h, d_cycles, blocks * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -103,6 +127,23 @@ int main() {
             double ops = (double)blocks * 256 * ITERS * 8 * ops_per_inner[mode];
             printf("{\"test\": \"%s\", \"blocks_per_sm\": %d, \"ops_per_clk_per_sm\": %.2f, \"gops\": %.1f, \"ms\": %.4f, \"mhz_eff\": %.0f}\n",
                    names[mode], bps, ops / cyc / sms, ops / ms / 1e6, ms, cyc / ms / 1e3);
+        }
+    }
+    {
+        double* d_dout; cudaMalloc(&d_dout, (size_t)max_blocks * 256 * 8);
+        for (int bps = 2; bps <= 8; bps *= 2) {
+            int blocks = sms * bps;
+            for (int mix = 0; mix < 2; ++mix) {
+                for (int rep = 0; rep < 2; ++rep) {
+                    cudaEventRecord(e0);
+                    if (mix == 0) k_dfma<0><<<blocks, 256>>>(d_dout, 1.5, 77, d_cycles); else k_dfma<1><<<blocks, 256>>>(d_dout, 1.5, 77, d_cycles);
+                    cudaEventRecord(e1); cudaEventSynchronize(e1);
+                }
+                float ms; cudaEventElapsedTime(&ms, e0, e1);
+                double ops = (double)blocks * 256 * ITERS * 8;
+                printf("{\"test\": \"%s\", \"blocks_per_sm\": %d, \"g_dfma_per_s\": %.1f, \"g_imad_wide_per_s\": %.1f, \"ms\": %.4f}\n",
+                       mix ? "dfma_plus_imad_wide" : "dfma", bps, ops / ms / 1e6, mix ? ops / ms / 1e6 : 0.0, ms);
+            }
         }
     }
     for (int bps = 1; bps <= 4; bps *= 2) {
