@@ -172,6 +172,23 @@ int32_t b200zk_msm(b200zk_ctx* ctx, const void* coeffs, const void* bases, size_
     return b200zk_msm_dev(ctx, ctx->io_a.p, ctx->io_b.p, len, out_g1);
 }
 
+// Sum of `count` G1 points (Jacobian {x,y,z}, any z) on the host: the combine step of a
+// point-range sharded MSM after the partial sums have been all-gathered (O(#GPUs) additions).
+int32_t b200zk_g1_sum(const void* points_g1, size_t count, void* out_g1) {
+    if (!out_g1 || (count && !points_g1)) return B200ZK_EINVAL;
+    using namespace host;
+    HXyzz acc = hx_identity();
+    const uint64_t* p = (const uint64_t*)points_g1;
+    for (size_t i = 0; i < count; ++i, p += 12) {
+        HFq x = HFq::from_limbs(p), y = HFq::from_limbs(p + 4), z = HFq::from_limbs(p + 8);
+        if (z.is_zero()) continue;
+        HFq zz = z.sqr();
+        acc = hx_add(acc, HXyzz{x, y, zz, zz * z});
+    }
+    write_g1(hx_to_affine(acc), out_g1);
+    return B200ZK_OK;
+}
+
 // ---- best_fft ---------------------------------------------------------------------
 int32_t b200zk_fft_dev(b200zk_ctx* ctx, void* d_a, const void* omega_host, uint32_t log_n) {
     if (!ctx || !d_a || !omega_host || log_n > 30) return B200ZK_EINVAL;

@@ -1,0 +1,136 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, torch.distributed
+for the plumbing (NCCL on GPUs, gloo in the CPU tests).
+
+* `ShardedCommit`  — one best_multiexp / ParamsKZG::commit split by point range: rank g holds
+  bases[lo_g, hi_g) resident on its GPU, multiplies its slice of the scalars, and the G partial
+  G1 points (96 bytes each) are all-gathered and added.  EC addition is not an NCCL reduce op,
+  hence gather-then-add; the exchange is latency-bound (G x 96 B).
+* `FourStepNTT`    — one best_fft of size N = R*C split over G ranks: rank g owns a block of C/G
+  columns, does the R-point column transforms and the inter-step twiddles locally, an all-to-all
+  transposes blocks so that rank g owns R/G full rows, then does the C-point row transforms.
+  Output element k = k_r + R*k_c ends up on the rank that owns row k_r (digit-reversed
+  distribution, which is what a row-sharded quotient evaluation consumes).
+
+The local arithmetic is injected (`engine`), so the same host logic runs on the GPU backend and,
+in tests/test_sharded_cpu.py, on a CPU engine under gloo with world size 2.
+"""
+import numpy as np
+
+
+def shard_range(n, world, rank):
+    """Contiguous point range [lo, hi) of rank `rank` (sizes differ by at most one)."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def _torch():
+    import torch
+    import torch.distributed as dist
+    return torch, dist
+
+
+def all_gather_u64(arr, device=None):
+    """All-gather equal-sized uint64 arrays; returns (world, *arr.shape).  Works for gloo (CPU
+    tensors) and NCCL (device = torch.device('cuda', i))."""
+    torch, dist = _torch()
+    a = np.ascontiguousarray(arr, dtype=np.uint64)
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return a[None]
+    t = torch.from_numpy(a.view(np.int64).copy())
+    if device is not None:
+        t = t.to(device)
+    outs = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, t)
+    return np.stack([o.cpu().numpy().view(np.uint64) for o in outs])
+
+
+def all_to_all_u64(blocks, device=None):
+    """blocks[j] goes to rank j; returns the list of blocks received (one per rank)."""
+    torch, dist = _torch()
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [np.ascontiguousarray(blocks[0], dtype=np.uint64)]
+    send = [torch.from_numpy(np.ascontiguousarray(b, dtype=np.uint64).view(np.int64).copy()) for b in blocks]
+    if device is not None:
+        send = [s.to(device) for s in send]
+    recv = [torch.empty_like(s) for s in send]
+    if dist.get_backend() == "gloo":                     # gloo has no all_to_all: pairwise exchange
+        rank, world = dist.get_rank(), dist.get_world_size()
+        recv[rank] = send[rank].clone()
+        for step in range(1, world):
+            dst, src = (rank + step) % world, (rank - step) % world
+            req = dist.isend(send[dst], dst)
+            dist.recv(recv[src], src)
+            req.wait()
+    else:
+        dist.all_to_all(recv, send)
+    return [r.cpu().numpy().view(np.uint64) for r in recv]
+
+
+class ShardedCommit:
+    """Point-range sharded MSM.  engine.msm(scalars) -> (12,) uint64 partial G1 over this rank's bases;
+    engine.g1_sum(points (G,12)) -> (12,) uint64."""
+
+    def __init__(self, engine, device=None):
+        self.engine, self.device = engine, device
+
+    def commit(self, local_scalars):
+        partial = self.engine.msm(local_scalars)
+        gathered = all_gather_u64(partial, self.device)
+        return self.engine.g1_sum(gathered)
+
+
+class GpuCommitEngine:
+    """ShardedCommit engine over a device-resident SRS slice (ParamsKZG of the local range)."""
+
+    def __init__(self, zk, params, lagrange=False):
+        self.zk, self.params, self.lagrange = zk, params, lagrange
+
+    def msm(self, scalars):
+        if hasattr(scalars, "ptr"):                       # DeviceBuffer
+            return self.params.commit_dev(scalars, self.params.n, self.lagrange)
+        return self.params.commit_lagrange(scalars) if self.lagrange else self.params.commit(scalars)
+
+    def g1_sum(self, points):
+        import ctypes
+        pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 12)
+        out = np.zeros(12, dtype=np.uint64)
+        rc = self.zk.lib().b200zk_g1_sum(pts.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(pts.shape[0]),
+                                         out.ctypes.data_as(ctypes.c_void_p))
+        if rc:
+            raise self.zk.B200zkError(f"b200zk_g1_sum failed: {rc}")
+        return out
+
+
+class FourStepNTT:
+    """Row/column sharded four-step NTT of size N = R*C over `world` ranks (R, C powers of two,
+    world divides both).
+
+    engine.col_step(block, omega_n, log_r, log_c, col0) : block is (R, C/G, 4): R-point transforms down
+        the columns followed by the twiddle omega_n^(c_global * k_r); returns the same shape.
+    engine.row_step(rows, omega_c, log_c)               : rows is (R/G, C, 4): C-point transform of each row.
+    """
+
+    def __init__(self, engine, log_n, log_r, rank, world, device=None):
+        self.engine, self.log_n, self.log_r, self.log_c = engine, log_n, log_r, log_n - log_r
+        self.rank, self.world, self.device = rank, world, device
+        self.R, self.C = 1 << log_r, 1 << (log_n - log_r)
+        assert self.R % world == 0 and self.C % world == 0
+
+    def local_columns(self, full):
+        """This rank's input block (R, C/G, 4) cut out of a natural-order array (tests / host callers)."""
+        cg = self.C // self.world
+        return np.ascontiguousarray(np.asarray(full).reshape(self.R, self.C, 4)[:, self.rank * cg:(self.rank + 1) * cg])
+
+    def forward(self, block, omega_n, omega_c):
+        """block: (R, C/G, 4) columns owned by this rank.  Returns (R/G, C, 4): rows k_r in this rank's
+        row range, entry [k_r_local, k_c] = X[k_r + R * k_c]."""
+        cg, rg = self.C // self.world, self.R // self.world
+        y = self.engine.col_step(block, omega_n, self.log_r, self.log_c, self.rank * cg)
+        send = [np.ascontiguousarray(y[j * rg:(j + 1) * rg]) for j in range(self.world)]      # (R/G, C/G, 4) per peer
+        recv = all_to_all_u64(send, self.device)
+        rows = np.concatenate([r.reshape(rg, cg, 4) for r in recv], axis=1)                   # (R/G, C, 4)
+        return self.engine.row_step(rows, omega_c, self.log_c)
+
+    def gather_natural(self, rows):
+        """All-gather the row blocks and restore natural order (tests only)."""
+        allr = all_gather_u64(rows, self.device).reshape(self.R, self.C, 4)                    # [k_r][k_c]
+        return np.ascontiguousarray(np.transpose(allr, (1, 0, 2))).reshape(self.R * self.C, 4) # k = k_r + R*k_c

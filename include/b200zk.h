@@ -71,6 +71,9 @@ int32_t b200zk_host_free(b200zk_ctx* ctx, void* hptr);
  * CPU path returns, in normalised representation.  len == 0 gives the identity. */
 int32_t b200zk_msm(b200zk_ctx* ctx, const void* coeffs, const void* bases, size_t len, void* out_g1);
 int32_t b200zk_msm_dev(b200zk_ctx* ctx, const void* d_coeffs, const void* d_bases, size_t len, void* out_g1_host);
+/* Host-side sum of `count` G1 points (96 B Jacobian each): combines the per-GPU partial results of a
+ * point-range sharded best_multiexp after a 96-byte all-gather (no ctx, no device work). */
+int32_t b200zk_g1_sum(const void* points_g1, size_t count, void* out_g1);
 /* window size override for tuning (0 = automatic) */
 int32_t b200zk_msm_set_window(b200zk_ctx* ctx, int32_t c);
 
