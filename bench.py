@@ -147,8 +147,10 @@ def timed(be, dist, local, steps, fn):
     return max_over_ranks(dist, local, ms)
 
 
+CIRCUITS = {"mst": ("mst_shaped", "MST-shaped synthetic circuit k={k}: 20 advice, 8 u8 lookups, 16 permutation columns, degree 6, ext 8n"),
+            "v3": ("v3_shaped", "Merkle-v3-shaped synthetic circuit k={k}: 9 advice, no lookups, 12 permutation columns, degree 6, ext 8n")}
 WORKLOAD_TEXT = {
-    "prove": "create_proof (KZG/SHPLONK/Blake2b), MST-shaped synthetic circuit k={k}: 20 advice, 8 u8 lookups, 16 permutation columns, degree 6, ext 8n; SRS + pk resident in HBM",
+    "prove": "create_proof (KZG/SHPLONK/Blake2b), {circuit}; SRS + pk resident in HBM",
     "msm": "bn256 G1 MSM 2^{L} points (best_multiexp drop-in), uniform scalars, bases [s^i]G resident in HBM",
     "ntt": "bn256 Fr NTT 2^{L} (best_fft drop-in), uniform input",
 }
@@ -168,7 +170,7 @@ def run_gpu(args):
         k = args.k
         n = 1 << k
         synth = importlib.import_module(zk.__name__ + ".circuits_synth")
-        job = synth.mst_shaped(k, seed=1 + rank)
+        job = getattr(synth, CIRCUITS[args.circuit][0])(k, seed=1 + rank)
         params = zk.ParamsKZG.setup(be, k, random_scalars(1, 4242)[0])
         pk = zk.ProvingKey(params, job.cs, k, job.fixed, job.map_col, job.map_row)
         A = job.cs.num_advice
@@ -191,7 +193,7 @@ def run_gpu(args):
         unit, metric, hib = "ms", "create_proof_ms", False
         h2d, d2h = int(h_adv.nbytes + h_wide.nbytes), pk.proof_size
         dtype = "u32x8 Montgomery (bn256 Fr/Fq, IMAD pipe)"
-        workload = WORKLOAD_TEXT["prove"].format(k=k)
+        workload = WORKLOAD_TEXT["prove"].format(circuit=CIRCUITS[args.circuit][1].format(k=k))
     elif args.workload == "msm":
         # N > 1: ONE MSM of 2^L points sharded by point range (strong scaling): every rank holds
         # 2^L / N bases and scalars, partial sums are all-gathered (96 B per rank) and added.
@@ -237,6 +239,30 @@ def run_gpu(args):
 
         def step_e2e():
             be._check(zk.lib().b200zk_fft(be._ctx, h_a.ctypes.data_as(ctypes.c_void_p), omega.ctypes.data_as(ctypes.c_void_p), L))
+
+        if world > 1:
+            # ONE transform of 2^L elements sharded four-step (strong scaling): column blocks ->
+            # column step -> NCCL all-to-all over NVLink -> row step (halo2-experiments_b200/sharded.py)
+            import torch
+            sharded = importlib.import_module(zk.__name__ + ".sharded")
+            dev = torch.device("cuda", local)
+            log_r = min(10, L // 2)
+            fs = sharded.FourStepNTTDevice(zk, be, L, log_r, rank, world, dev)
+            blk_host = random_scalars((1 << L) // world, 300 + rank).reshape(1 << log_r, -1, 4)
+            block = torch.from_numpy(blk_host.view(np.int64)).to(dev)
+            omega_c = zk.EvaluationDomain(be, 2, L - log_r).omega
+            pinned = torch.from_numpy(blk_host.view(np.int64)).pin_memory()
+
+            def step_dev():
+                fs.forward(block, omega, omega_c)
+
+            def step_e2e():
+                block.copy_(pinned, non_blocking=False)
+                rows = fs.forward(block, omega, omega_c)
+                pinned.view(rows.shape).copy_(rows)
+
+            n = (1 << L) // world                                   # per-rank elements; value multiplies by world
+            line["scaling"] = "strong"
 
         unit, metric, hib = "GB/s", "ntt_gb_per_s", True
         units_per_step = 64.0 * n / 1e9
@@ -329,7 +355,7 @@ def cpu_sample(args):
         zk = load_package()
         synth = importlib.import_module(zk.__name__ + ".circuits_synth")
         ks = min(args.k, args.cpu_k)
-        job = synth.mst_shaped(ks, seed=1)
+        job = getattr(synth, CIRCUITS[args.circuit][0])(ks, seed=1)
         g, gl = orc.params_setup(ks, orc.random_fr(1, 4242)[0])
         pk = OP.keygen_pk(job.cs, ks, job.fixed, job.map_col, job.map_row)
         wide = np.random.Generator(np.random.PCG64(99)).integers(0, 1 << 64, size=(OP.rng_draws_needed(job.cs, ks), 8), dtype=np.uint64)
@@ -376,7 +402,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     if args.workload == "prove":
         v, unit, metric, hib = dt * 1e3 * scale, "ms", "create_proof_ms", False
-        workload = WORKLOAD_TEXT["prove"].format(k=args.k)
+        workload = WORKLOAD_TEXT["prove"].format(circuit=CIRCUITS[args.circuit][1].format(k=args.k))
         sample = f"{desc}: {dt:.1f} s per step measured, x{scale:g} linear extrapolation to k={args.k}"
     else:
         v = units / dt
@@ -399,6 +425,7 @@ def main():
     ap.add_argument("--impl", default="b200zk", choices=["b200zk", "reference"])
     ap.add_argument("--workload", default="prove", choices=["prove", "msm", "ntt"])
     ap.add_argument("--k", type=int, default=20, help="prove: circuit size")
+    ap.add_argument("--circuit", default="mst", choices=sorted(CIRCUITS), help="prove: circuit shape")
     ap.add_argument("--cpu-k", type=int, default=14, help="prove: size of the bounded CPU sample")
     ap.add_argument("--log-n", type=int, default=24, help="msm / ntt size")
     ap.add_argument("--cpu-log-n", type=int, default=None, help="msm / ntt: size of the bounded CPU sample")

@@ -197,6 +197,19 @@ int32_t b200zk_fft_dev(b200zk_ctx* ctx, void* d_a, const void* omega_host, uint3
     return ntt_run(ctx, (const fe_t*)d_a, 1u << log_n, (fe_t*)d_a, log_n, omega, nullptr, nullptr);
 }
 
+int32_t b200zk_fft_colstep_dev(b200zk_ctx* ctx, void* d_block, uint32_t log_r, uint32_t log_cg, uint32_t col0,
+                               const void* omega_n, uint32_t log_n) {
+    if (!ctx || !d_block || !omega_n || log_n > 30 || log_r + log_cg > log_n) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ntt_colstep_run(ctx, (fe_t*)d_block, log_r, log_cg, col0, HFr::from_limbs(omega_n), log_n);
+}
+
+int32_t b200zk_fft_rows_dev(b200zk_ctx* ctx, void* d_rows, uint32_t nrows, const void* omega_c, uint32_t log_c) {
+    if (!ctx || !d_rows || !omega_c || log_c > 30) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ntt_rows_run(ctx, (fe_t*)d_rows, nrows, HFr::from_limbs(omega_c), log_c);
+}
+
 int32_t b200zk_fft(b200zk_ctx* ctx, void* a, const void* omega, uint32_t log_n) {
     if (!ctx || !a || !omega || log_n > 30) return B200ZK_EINVAL;
     ZK_CUDA(ctx, cudaSetDevice(ctx->device));

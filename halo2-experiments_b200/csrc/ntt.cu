@@ -96,6 +96,7 @@ int32_t ntt_run(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, u
         }
         a.roots = plan.roots; a.log_roots = s.log_roots;
         a.tw_lo = plan.tw_lo; a.tw_hi = plan.tw_hi; a.tw_lo_bits = s.tw_lo_bits;
+        a.tw_shift = log_n - q.log_m - q.log_l; a.l_offset = 0;
         size_t smem = sizeof(fe_t) << (q.log_m + q.log_tw);
         uint32_t tile = 1u << (q.log_m + q.log_tw);
         uint32_t threads = tile / 2 < NTT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : NTT_THREADS;
@@ -103,6 +104,64 @@ int32_t ntt_run(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, u
         ctx->launches++;
     }
     ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+// Column step of a four-step NTT of size N = R * C sharded by column blocks:
+// d_block is this rank's [R][Cg] block (row-major, Cg = 2^log_cg columns starting at global column
+// col0).  In place: R-point transform down every column, then the twiddle omega_n^((col0 + c) * k_r).
+int32_t ntt_colstep_run(b200zk_ctx* ctx, fe_t* d_block, uint32_t log_r, uint32_t log_cg, uint32_t col0,
+                        const host::HFr& omega_n, uint32_t log_n) {
+    if (log_r == 0 || log_r > NTT_MAX_LOG_M || log_r > log_n) return fail(ctx, B200ZK_EINVAL, "ntt_colstep", "row count must be 2^1..2^10");
+    // dedicated plan: roots of order R, two-level table of omega_n
+    std::array<uint64_t, 5> key = {((uint64_t)log_r << 32) | ((uint64_t)1 << 62) | log_n, omega_n.v[0], omega_n.v[1], omega_n.v[2], omega_n.v[3]};
+    auto it = ctx->ntt_plans.find(key);
+    if (it == ctx->ntt_plans.end()) {
+        NttPlan plan;
+        plan.shape = NttShape{};
+        plan.shape.log_n = log_n; plan.shape.log_roots = log_r; plan.shape.tw_lo_bits = (log_n + 1) / 2;
+        size_t n_roots = (size_t)1 << (log_r - 1), n_lo = (size_t)1 << plan.shape.tw_lo_bits, n_hi = ((size_t)1 << log_n) >> plan.shape.tw_lo_bits;
+        if (n_hi == 0) n_hi = 1;
+        ZK_CUDA(ctx, cudaMalloc(&plan.roots, n_roots * sizeof(fe_t)));
+        ZK_CUDA(ctx, cudaMalloc(&plan.tw_lo, n_lo * sizeof(fe_t)));
+        ZK_CUDA(ctx, cudaMalloc(&plan.tw_hi, n_hi * sizeof(fe_t)));
+        host::HFr w_r = omega_n.pow_u64(1ull << (log_n - log_r));
+        ntt_pow_table_kernel<<<(unsigned)((n_roots + 127) / 128), 128, 0, ctx->stream>>>(plan.roots, to_dev(w_r), (uint32_t)n_roots, 0);
+        ntt_pow_table_kernel<<<(unsigned)((n_lo + 127) / 128), 128, 0, ctx->stream>>>(plan.tw_lo, to_dev(omega_n), (uint32_t)n_lo, 0);
+        ntt_pow_table_kernel<<<(unsigned)((n_hi + 127) / 128), 128, 0, ctx->stream>>>(plan.tw_hi, to_dev(omega_n), (uint32_t)n_hi, plan.shape.tw_lo_bits);
+        ctx->launches += 3;
+        it = ctx->ntt_plans.emplace(key, plan).first;
+    }
+    const NttPlan& plan = it->second;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZK_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(fe_t) << NTT_TILE_CAP_LOG)));
+        attr_set = true;
+    }
+    NttPassArgs a{};
+    a.in = d_block; a.out = d_block;
+    a.log_n = log_r + log_cg;                       // local array size (addressing only)
+    a.log_m = log_r; a.log_l = log_cg; a.is_last = 0;
+    uint32_t cap = NTT_TILE_CAP_LOG - log_r;
+    a.log_tw = std::min(std::min(NTT_MAX_LOG_TW, cap), log_cg);
+    a.n_in = 1u << (log_r + log_cg);
+    a.roots = plan.roots; a.log_roots = log_r;
+    a.tw_lo = plan.tw_lo; a.tw_hi = plan.tw_hi; a.tw_lo_bits = plan.shape.tw_lo_bits;
+    a.tw_shift = 0; a.l_offset = col0;              // exponent (col0 + c) * k_r < C * R = N
+    uint32_t tile = 1u << (a.log_m + a.log_tw);
+    uint32_t threads = tile / 2 < NTT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : NTT_THREADS;
+    ntt_pass_kernel<<<1u << (log_cg - a.log_tw), threads, sizeof(fe_t) << (a.log_m + a.log_tw), ctx->stream>>>(a);
+    ctx->launches++;
+    ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+// Row step: `nrows` independent natural-order transforms of size 2^log_c on contiguous rows, in place.
+int32_t ntt_rows_run(b200zk_ctx* ctx, fe_t* d_rows, uint32_t nrows, const host::HFr& omega_c, uint32_t log_c) {
+    for (uint32_t r = 0; r < nrows; ++r) {
+        fe_t* row = d_rows + ((size_t)r << log_c);
+        ZK_TRY(ntt_run(ctx, row, 1u << log_c, row, log_c, omega_c, nullptr, nullptr));
+    }
     return B200ZK_OK;
 }
 

@@ -44,6 +44,8 @@ struct NttPassArgs {
     const fe_t* tw_lo;      // omega^i,            i < 2^tw_lo_bits
     const fe_t* tw_hi;      // omega^(j << lo_bits), j < N >> tw_lo_bits
     uint32_t tw_lo_bits;
+    uint32_t tw_shift;      // inter-pass twiddle exponent = ((l + l_offset) * k) << tw_shift
+    uint32_t l_offset;      // global column index of local column 0 (sharded four-step column step)
 };
 
 ZK_D uint32_t bitrev32(uint32_t v, uint32_t bits) {
@@ -143,7 +145,7 @@ ZK_D void ntt_pass_block(const NttPassArgs& a, uint32_t bid, uint32_t nthreads, 
             uint32_t l = l0 + c;
             g = ((size_t)h << (a.log_m + a.log_l)) + ((size_t)k << a.log_l) + l;
             // w_{ML}^{l k} = omega^{l k N/(ML)}
-            uint64_t E = ((uint64_t)l * k) << (a.log_n - a.log_m - a.log_l);
+            uint64_t E = ((uint64_t)(l + a.l_offset) * k) << a.tw_shift;
             if (E) v = Fr::mul(v, ntt_twiddle(a, (uint32_t)E));
         } else {
             // out index = k_1 + M_1 * rev(rho') + (M_1 * mid) * k ; mid digit order is preserved

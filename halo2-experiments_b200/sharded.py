@@ -100,6 +100,74 @@ class GpuCommitEngine:
         return out
 
 
+class GpuNttEngine:
+    """FourStepNTT engine over one Backend with host (numpy) blocks: upload, kernel, download.
+    Used to check the kernels with the ranks emulated one after another on a single GPU."""
+
+    def __init__(self, zk, backend, log_n):
+        self.zk, self.be, self.log_n = zk, backend, log_n
+
+    def col_step(self, block, omega_n, log_r, log_c, col0):
+        import ctypes
+        block = np.ascontiguousarray(block, dtype=np.uint64)
+        log_cg = int(np.log2(block.shape[1]))
+        d = self.be.to_device(block)
+        try:
+            self.be._check(self.zk.lib().b200zk_fft_colstep_dev(self.be._ctx, d.ptr, ctypes.c_uint32(log_r), ctypes.c_uint32(log_cg),
+                                                              ctypes.c_uint32(col0), np.ascontiguousarray(omega_n).ctypes.data_as(ctypes.c_void_p),
+                                                              ctypes.c_uint32(self.log_n)))
+            return d.download(block.shape)
+        finally:
+            d.free()
+
+    def row_step(self, rows, omega_c, log_c):
+        import ctypes
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        d = self.be.to_device(rows)
+        try:
+            self.be._check(self.zk.lib().b200zk_fft_rows_dev(self.be._ctx, d.ptr, ctypes.c_uint32(rows.shape[0]),
+                                                           np.ascontiguousarray(omega_c).ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(log_c)))
+            return d.download(rows.shape)
+        finally:
+            d.free()
+
+
+class FourStepNTTDevice:
+    """The same four-step transform with the data resident in HBM: blocks are torch CUDA tensors
+    (int64 views of the u64 limbs, torch owns the memory), the kernels run through the C ABI on the
+    tensors' device pointers and the transpose is one NCCL all_to_all_single over NVLink."""
+
+    def __init__(self, zk, backend, log_n, log_r, rank, world, device):
+        import ctypes
+        self.ct = ctypes
+        self.zk, self.be, self.log_n, self.log_r, self.log_c = zk, backend, log_n, log_r, log_n - log_r
+        self.rank, self.world, self.device = rank, world, device
+        self.R, self.C = 1 << log_r, 1 << (log_n - log_r)
+        assert self.R % world == 0 and self.C % world == 0
+
+    def forward(self, block, omega_n, omega_c):
+        """block: torch int64 CUDA tensor (R, C/G, 4), overwritten.  Returns (R/G, C, 4)."""
+        torch, dist = _torch()
+        ct, lib = self.ct, self.zk.lib()
+        cg, rg = self.C // self.world, self.R // self.world
+        torch.cuda.synchronize(self.device)
+        self.be._check(lib.b200zk_fft_colstep_dev(self.be._ctx, ct.c_void_p(block.data_ptr()), ct.c_uint32(self.log_r),
+                                                 ct.c_uint32(int(np.log2(cg))), ct.c_uint32(self.rank * cg),
+                                                 np.ascontiguousarray(omega_n).ctypes.data_as(ct.c_void_p), ct.c_uint32(self.log_n)))
+        self.be.sync()
+        if self.world > 1:
+            recv = torch.empty_like(block)                       # (G, rg, cg, 4) chunks by source rank
+            dist.all_to_all_single(recv, block)
+            rows = recv.view(self.world, rg, cg, 4).permute(1, 0, 2, 3).contiguous().view(rg, self.C, 4)
+        else:
+            rows = block.view(rg, self.C, 4)
+        torch.cuda.synchronize(self.device)
+        self.be._check(lib.b200zk_fft_rows_dev(self.be._ctx, ct.c_void_p(rows.data_ptr()), ct.c_uint32(rg),
+                                              np.ascontiguousarray(omega_c).ctypes.data_as(ct.c_void_p), ct.c_uint32(self.log_c)))
+        self.be.sync()
+        return rows
+
+
 class FourStepNTT:
     """Row/column sharded four-step NTT of size N = R*C over `world` ranks (R, C powers of two,
     world divides both).

@@ -82,6 +82,14 @@ int32_t b200zk_msm_set_window(b200zk_ctx* ctx, int32_t c);
 int32_t b200zk_fft(b200zk_ctx* ctx, void* a, const void* omega, uint32_t log_n);
 int32_t b200zk_fft_dev(b200zk_ctx* ctx, void* d_a, const void* omega_host, uint32_t log_n);
 
+/* Building blocks of one best_fft of size N = R*C sharded over several GPUs (four-step, SURVEY.md
+ * 8(e)): colstep = this rank's [R][Cg] column block (Cg = 2^log_cg columns from global column
+ * col0): R-point transforms down the columns + twiddle omega_n^((col0+c)*k_r), in place, R <= 2^10;
+ * rows = nrows contiguous natural-order transforms of size 2^log_c (after the all-to-all). */
+int32_t b200zk_fft_colstep_dev(b200zk_ctx* ctx, void* d_block, uint32_t log_r, uint32_t log_cg, uint32_t col0,
+                               const void* omega_n, uint32_t log_n);
+int32_t b200zk_fft_rows_dev(b200zk_ctx* ctx, void* d_rows, uint32_t nrows, const void* omega_c, uint32_t log_c);
+
 /* ---- poly::EvaluationDomain<Fr> (src/poly/domain.rs) ------------------------
  * b200zk_domain_create(j, k) = EvaluationDomain::new(j, k). */
 int32_t b200zk_domain_create(b200zk_ctx* ctx, uint32_t j, uint32_t k, b200zk_domain** out);

@@ -75,6 +75,7 @@ void emu_ntt(const fe_t* in, uint32_t n_in, fe_t* out, uint32_t log_n, const fe_
         if (post) memcpy(a.post, post, 96);
         a.roots = roots.data(); a.log_roots = s.log_roots;
         a.tw_lo = lo.data(); a.tw_hi = hi.data(); a.tw_lo_bits = s.tw_lo_bits;
+        a.tw_shift = log_n - q.log_m - q.log_l; a.l_offset = 0;
         std::vector<half_t> sm((size_t)2 << (q.log_m + q.log_tw));
         for (uint32_t b = 0; b < q.blocks; ++b) ntt_pass_block(a, b, nthreads, sm.data());
     }

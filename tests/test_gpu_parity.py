@@ -237,3 +237,29 @@ def test_best_multiexp_skewed_columns(backend, orc, kind):
         S[: n // 8] = orc.random_fr(n // 8, 3)           # a dense stretch on top
     got = backend.best_multiexp(S, g)
     assert np.array_equal(_affine(got), orc.g1_batch_normalize(orc.best_multiexp(S, g))[0])
+
+
+@pytest.mark.parametrize("log_n,log_r,world", [(10, 4, 2), (12, 6, 4), (16, 8, 8), (20, 10, 8)])
+def test_four_step_sharded_ntt_kernels(zk, backend, orc, log_n, log_r, world):
+    """Column step / row step kernels of the sharded four-step NTT, with the `world` ranks emulated
+    one after another on one GPU and the all-to-all done on the host; result = best_fft."""
+    import importlib
+    from oracle import pyref
+    sharded = importlib.import_module(zk.__name__ + ".sharded")
+    N, R, C = 1 << log_n, 1 << log_r, 1 << (log_n - log_r)
+    a = orc.random_fr(N, 300 + log_n)
+    w = pyref.omega_for_k(log_n)
+    omega_n = orc.ints_to_mont([w])[0]
+    omega_c = orc.ints_to_mont([pow(w, R, pyref.R_MOD)])[0]
+    eng = sharded.GpuNttEngine(zk, backend, log_n)
+    cg, rg = C // world, R // world
+    Y = np.zeros((R, C, 4), dtype=np.uint64)
+    for g in range(world):
+        fs = sharded.FourStepNTT(eng, log_n, log_r, g, world)
+        Y[:, g * cg:(g + 1) * cg] = eng.col_step(fs.local_columns(a), omega_n, log_r, log_n - log_r, g * cg)
+    Z = np.zeros((R, C, 4), dtype=np.uint64)
+    for g in range(world):
+        Z[g * rg:(g + 1) * rg] = eng.row_step(Y[g * rg:(g + 1) * rg], omega_c, log_n - log_r)
+    got = np.ascontiguousarray(np.transpose(Z, (1, 0, 2))).reshape(N, 4)          # X[k_r + R k_c] = Z[k_r][k_c]
+    want = orc.best_fft(a, omega_n, log_n) if log_n <= 16 else backend.best_fft(a, omega_n, log_n)
+    assert np.array_equal(got, want)
