@@ -56,9 +56,21 @@ static int32_t build_plan(b200zk_ctx* ctx, uint32_t log_n, const host::HFr& omeg
     return B200ZK_OK;
 }
 
+static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, uint32_t log_n,
+                             const host::HFr& omega, const host::HFr* pre, const host::HFr* post, uint32_t batch);
+
 int32_t ntt_run(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, uint32_t log_n,
                 const host::HFr& omega, const host::HFr* pre, const host::HFr* post) {
+    return ntt_run_batch(ctx, d_in, n_in, d_out, log_n, omega, pre, post, 1);
+}
+
+// `batch` independent transforms of size 2^log_n on contiguous arrays (batch > 1: no pre/post hooks,
+// n_in = 2^log_n): every pass is one launch over all of them.
+static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, uint32_t log_n,
+                             const host::HFr& omega, const host::HFr* pre, const host::HFr* post, uint32_t batch) {
     if (log_n > 3 * NTT_MAX_LOG_M) return fail(ctx, B200ZK_EINVAL, "ntt_run", "log_n too large");
+    if (batch == 0) return B200ZK_OK;
+    if (batch > 1 && (pre || post || ((uint64_t)batch << log_n) > 0xFFFFFFFFull)) return fail(ctx, B200ZK_EINVAL, "ntt_run", "bad batch");
     std::array<uint64_t, 5> key = {log_n, omega.v[0], omega.v[1], omega.v[2], omega.v[3]};
     auto it = ctx->ntt_plans.find(key);
     if (it == ctx->ntt_plans.end()) {
@@ -71,7 +83,7 @@ int32_t ntt_run(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, u
     size_t N = (size_t)1 << log_n;
     fe_t* scratch = nullptr;
     if (s.npass > 1) {
-        ZK_TRY(ws_reserve(ctx, ctx->ntt_scratch, N * sizeof(fe_t)));
+        ZK_TRY(ws_reserve(ctx, ctx->ntt_scratch, N * batch * sizeof(fe_t)));
         scratch = (fe_t*)ctx->ntt_scratch.p;
     }
     static bool attr_set = false;
@@ -87,7 +99,8 @@ int32_t ntt_run(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, u
         a.out = q.is_last ? d_out : scratch;
         a.log_n = log_n; a.log_m = q.log_m; a.log_l = q.log_l; a.log_tw = q.log_tw; a.is_last = q.is_last;
         a.log_m1 = q.log_m1; a.log_mid = q.log_mid;
-        a.n_in = p == 0 ? n_in : (uint32_t)N;
+        a.n_in = batch > 1 ? (uint32_t)(N * batch) : (p == 0 ? n_in : (uint32_t)N);
+        a.batch_tiles = (batch > 1 && q.is_last) ? q.blocks : 0;
         a.use_pre = (p == 0 && pre) ? 1 : 0;
         a.use_post = (q.is_last && post) ? 1 : 0;
         for (int i = 0; i < 3; ++i) {
@@ -100,7 +113,7 @@ int32_t ntt_run(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, u
         size_t smem = sizeof(fe_t) << (q.log_m + q.log_tw);
         uint32_t tile = 1u << (q.log_m + q.log_tw);
         uint32_t threads = tile / 2 < NTT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : NTT_THREADS;
-        ntt_pass_kernel<<<q.blocks, threads, smem, ctx->stream>>>(a);
+        ntt_pass_kernel<<<q.blocks * batch, threads, smem, ctx->stream>>>(a);
         ctx->launches++;
     }
     ZK_CUDA(ctx, cudaGetLastError());
@@ -158,11 +171,7 @@ int32_t ntt_colstep_run(b200zk_ctx* ctx, fe_t* d_block, uint32_t log_r, uint32_t
 
 // Row step: `nrows` independent natural-order transforms of size 2^log_c on contiguous rows, in place.
 int32_t ntt_rows_run(b200zk_ctx* ctx, fe_t* d_rows, uint32_t nrows, const host::HFr& omega_c, uint32_t log_c) {
-    for (uint32_t r = 0; r < nrows; ++r) {
-        fe_t* row = d_rows + ((size_t)r << log_c);
-        ZK_TRY(ntt_run(ctx, row, 1u << log_c, row, log_c, omega_c, nullptr, nullptr));
-    }
-    return B200ZK_OK;
+    return ntt_run_batch(ctx, d_rows, 1u << log_c, d_rows, log_c, omega_c, nullptr, nullptr, nrows);
 }
 
 int32_t fr_scale_periodic(b200zk_ctx* ctx, fe_t* d_a, size_t n, const fe_t* d_m, uint32_t period) {

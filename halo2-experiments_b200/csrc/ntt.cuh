@@ -46,6 +46,7 @@ struct NttPassArgs {
     uint32_t tw_lo_bits;
     uint32_t tw_shift;      // inter-pass twiddle exponent = ((l + l_offset) * k) << tw_shift
     uint32_t l_offset;      // global column index of local column 0 (sharded four-step column step)
+    uint32_t batch_tiles;   // last pass of a batch of independent transforms: tiles per transform (0 = single)
 };
 
 ZK_D uint32_t bitrev32(uint32_t v, uint32_t bits) {
@@ -86,12 +87,15 @@ ZK_D void ntt_pass_block(const NttPassArgs& a, uint32_t bid, uint32_t nthreads, 
     // non-last: bid -> (h, l0); element (m, c) lives at  h*M*L + m*L + l0 + c
     // last:     bid -> (k1_0, rho'); row c is  rho = (k1_0 + c) << log_mid | rho'
     uint32_t h = 0, l0 = 0, k1_0 = 0, rho_mid = 0;
+    size_t batch_base = 0;
     if (!a.is_last) {
         uint32_t tiles_per_h = L >> a.log_tw;
         h = bid / tiles_per_h; l0 = (bid % tiles_per_h) << a.log_tw;
     } else {
         uint32_t mid = 1u << a.log_mid;
-        rho_mid = bid % mid; k1_0 = (bid / mid) << a.log_tw;
+        uint32_t bl = bid;
+        if (a.batch_tiles) { batch_base = (size_t)(bid / a.batch_tiles) << a.log_n; bl = bid % a.batch_tiles; }
+        rho_mid = bl % mid; k1_0 = (bl / mid) << a.log_tw;
     }
 
     // ---- load -------------------------------------------------------------
@@ -105,7 +109,7 @@ ZK_D void ntt_pass_block(const NttPassArgs& a, uint32_t bid, uint32_t nthreads, 
         } else {
             c = idx >> a.log_m; m = idx & (M - 1);
             size_t rho = ((size_t)(k1_0 + c) << a.log_mid) | rho_mid;
-            g = (rho << a.log_m) + m;
+            g = batch_base + (rho << a.log_m) + m;
         }
         fe_t v;
         if (g < a.n_in) {
@@ -152,6 +156,7 @@ ZK_D void ntt_pass_block(const NttPassArgs& a, uint32_t bid, uint32_t nthreads, 
             // because P <= 3 passes use a single middle digit (asserted on the host).
             g = (size_t)(k1_0 + c) + ((size_t)rho_mid << a.log_m1) + ((size_t)k << (a.log_m1 + a.log_mid));
             if (a.use_post) v = Fr::mul(v, a.post[g % 3]);
+            g += batch_base;
         }
         a.out[g] = v;
     }
