@@ -147,6 +147,54 @@ def _build(k, seed, n_state, n_bytes, n_rc, with_sum_gate=True):
     return job
 
 
+def generic_shapes(k, seed=4):
+    """Regression job for the shapes of the reference's other experiments:
+    a degree-17 gate like SafeAccumulator's range_check(v, 16) times a selector
+    (/root/reference/src/chips/safe_accumulator.rs:118,158-159 -> extended domain 16n, permutation
+    chunks of 15 columns) and a two-expression *dynamic* lookup into an advice table column like
+    LessThan v1 (/root/reference/src/chips/less_than.rs:62-88), with products inside the lookup
+    expressions and rotations on both sides."""
+    n = 1 << k
+    rng = np.random.Generator(np.random.PCG64(seed))
+    cs = ConstraintSystem(4, 3, 1)
+    Q_RANGE, TAB, Q_LK = 0, 1, 2
+    cs.enable_equality(ADVICE, 0)
+    cs.enable_equality(ADVICE, 1)
+    cs.enable_equality(INSTANCE, 0)
+    cs.enable_equality(FIXED, TAB)
+    a0 = cs.query_advice(0, 0)
+    prod = a0
+    for i in range(1, 16):
+        prod = prod * (a0 - i)
+    cs.create_gate([cs.query_fixed(Q_RANGE, 0) * prod])                                  # degree 17
+    ql = cs.query_fixed(Q_LK, 0)
+    cs.lookup([(ql * cs.query_advice(1, 0), cs.query_advice(3, 0)),                       # dynamic (advice) table
+               (ql * cs.query_advice(2, 1), cs.query_fixed(TAB, 0))])
+    assert cs.degree() == 17 and cs.blinding_factors() == 5
+    bf = cs.blinding_factors()
+    usable = n - (bf + 1)
+    job = Job(cs, k)
+    rows = np.arange(n)
+    act_next = (rows < usable - 1).astype(np.int64)
+    T = min(64, usable)
+    tab_a = np.where(rows < T, rows * 3, 0)              # advice table column: (3t, 7t) pairs, row 0 = (0, 0)
+    tab_f = np.where(rows < T, rows * 7, 0)
+    job.fixed = [mont_from_small((rows < usable).astype(np.int64)), mont_from_small(tab_f), mont_from_small(act_next)]
+    v0 = rng.integers(0, 16, size=n, dtype=np.int64)
+    pick = rng.integers(0, T, size=n, dtype=np.int64)
+    a1 = pick * 3 * act_next                            # rows with q_lookup = 0 look up (0, 0)
+    a2 = np.zeros(n, dtype=np.int64)
+    a2[1:] = (pick * 7 * act_next)[:-1]                  # queried at rotation +1
+    job.advice = [mont_from_small(v0), mont_from_small(a1), mont_from_small(a2), mont_from_small(tab_a)]
+    job.instances = [[int(v0[0]), int(v0[1])]]
+    asm = PermutationAssembly(len(cs.permutation), n)
+    pidx = {col: i for i, col in enumerate(cs.permutation)}
+    for r in range(2):
+        asm.copy(pidx[(INSTANCE, 0)], r, pidx[(ADVICE, 0)], r)
+    job.map_col, job.map_row = asm.map_col, asm.map_row
+    return job
+
+
 def mst_shaped(k, seed=1):
     """A = 20 advice, 8 lookups, 16 permutation columns, d = 6 (MST row)."""
     return _build(k, seed, n_state=5, n_bytes=8, n_rc=10)

@@ -39,7 +39,7 @@ struct b200zk_ctx {
     int sm_count = 148;
     int msm_force_c = 0;
     std::map<std::array<uint64_t, 5>, b200zk::NttPlan> ntt_plans;     // key: log_n + omega limbs
-    b200zk::Workspace ntt_scratch, msm_ws, msm_ws2, io_a, io_b, poly_ws, poly_heads, setup_ws, lookup_ws;
+    b200zk::Workspace ntt_scratch, msm_ws, msm_ws2, io_a, io_b, poly_ws, poly_heads, poly_batch, setup_ws, lookup_ws;
     b200zk::affine_t* d_gen_table = nullptr;                          // fixed-base table of the G1 generator (setup.cu)
     void* pinned = nullptr;                                            // small pinned staging (results)
 };
@@ -98,6 +98,7 @@ int32_t msm_run(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases,
 int32_t batch_invert_run(b200zk_ctx* ctx, fe_t* d_a, size_t n, int field /* 0 Fr, 1 Fq */);
 int32_t recurrence_run(b200zk_ctx* ctx, const fe_t* d_a, fe_t* d_y, size_t n, const host::HFr& b, host::HFr* head_out);
 int32_t prefix_product_run(b200zk_ctx* ctx, const fe_t* d_p, fe_t* d_z, size_t n, const host::HFr& z0);
+int32_t eval_batch_run(b200zk_ctx* ctx, const fe_t* const* h_polys, const host::HFr* h_points, size_t Q, size_t n, host::HFr* out);
 
 // setup.cu -------------------------------------------------------------------
 // ParamsKZG::setup bases on the device: g[i] = [s^i]G, g_lagrange[i] = [l_i(s)]G

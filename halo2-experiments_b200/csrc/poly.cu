@@ -80,6 +80,48 @@ int32_t recurrence_run(b200zk_ctx* ctx, const fe_t* d_a, fe_t* d_y, size_t n, co
     return B200ZK_OK;
 }
 
+// ---- batched Horner: Q independent (polynomial, point) evaluations in two launches -------------
+__global__ void __launch_bounds__(POLY_THREADS) recur_local_batch_kernel(const fe_t* const* polys, const fe_t* points, size_t n, size_t m,
+                                                                         size_t C, fe_t* heads) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t q = blockIdx.y;
+    if (c >= C) return;
+    fe_t b = points[q];
+    recur_local_chunk(polys[q], nullptr, n, m, c, b, heads + q * C);
+}
+__global__ void __launch_bounds__(SCAN_THREADS) recur_carries_batch_kernel(fe_t* heads, fe_t* carries, size_t n, size_t m, size_t C, const fe_t* points) {
+    __shared__ fe_t sm[2 * SCAN_THREADS];
+    size_t q = blockIdx.x;
+    fe_t b = points[q];
+    recur_carries_block(heads + q * C, carries + q * C, n, m, b, blockDim.x, sm);
+}
+
+// out[q] = polys[q](points[q]) for Q polynomials of n coefficients (device pointers in a host array)
+int32_t eval_batch_run(b200zk_ctx* ctx, const fe_t* const* h_polys, const host::HFr* h_points, size_t Q, size_t n, host::HFr* out) {
+    if (Q == 0) return B200ZK_OK;
+    if (n == 0) { for (size_t q = 0; q < Q; ++q) out[q] = host::HFr::zero(); return B200ZK_OK; }
+    const size_t C = (n + CHUNK - 1) / CHUNK;
+    size_t bytes = 2 * Q * C * sizeof(fe_t) + Q * (sizeof(fe_t) + sizeof(void*)) + 512;
+    ZK_TRY(ws_reserve(ctx, ctx->poly_batch, bytes));
+    fe_t* heads = (fe_t*)ctx->poly_batch.p;
+    fe_t* carries = heads + Q * C;
+    fe_t* d_points = carries + Q * C;
+    const fe_t** d_polys = (const fe_t**)(d_points + Q);
+    cudaStream_t st = ctx->stream;
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_points, h_points, Q * sizeof(fe_t), cudaMemcpyHostToDevice, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_polys, h_polys, Q * sizeof(void*), cudaMemcpyHostToDevice, st));
+    dim3 grid(nblocks(C, POLY_THREADS), (unsigned)Q);
+    recur_local_batch_kernel<<<grid, POLY_THREADS, 0, st>>>(d_polys, d_points, n, CHUNK, C, heads);
+    recur_carries_batch_kernel<<<(unsigned)Q, SCAN_THREADS, 0, st>>>(heads, carries, n, CHUNK, C, d_points);
+    ctx->launches += 2;
+    ZK_CUDA(ctx, cudaGetLastError());
+    std::vector<fe_t> tmp(Q);
+    ZK_CUDA(ctx, cudaMemcpy2DAsync(tmp.data(), sizeof(fe_t), heads, C * sizeof(fe_t), sizeof(fe_t), Q, cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    for (size_t q = 0; q < Q; ++q) out[q] = host::HFr::from_limbs(tmp[q].l);
+    return B200ZK_OK;
+}
+
 __global__ void __launch_bounds__(POLY_THREADS) pow_table_kernel(fe_t* out, const fe_t base, uint32_t count, uint32_t shift) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) out[i] = Fr::pow_u64(base, (unsigned long long)i << shift);

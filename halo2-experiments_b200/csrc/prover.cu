@@ -622,6 +622,35 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     std::vector<Query> queries;
     int32_t rc = B200ZK_OK;
     auto finish = [&](int32_t r) { delete open_timer; return r; };
+    const HFr x_next = rotate_omega(dom, x, 1), x_prev = rotate_omega(dom, x, -1), x_last = rotate_omega(dom, x, -(int)(bf + 1));
+    // vanishing::evaluate: h_poly = sum_i (x^n)^i h_piece_i
+    fold_pieces_kernel<<<nb(n), PK_THREADS, 0, st>>>(h, q, n, to_dev(xn), h_poly);
+    ctx->launches++;
+    // multiopen queries in upstream order (step 15); every evaluation written in step 14 is one of
+    // them, so all of them are evaluated here in ONE batched launch pair and served from the cache.
+    for (size_t i = 0; i < cs.adv_q.size(); i += 2) queries.push_back({advice_polys + (size_t)cs.adv_q[i] * n, rotate_omega(dom, x, cs.adv_q[i + 1])});
+    for (uint32_t s = 0; s < S; ++s) { queries.push_back({perm_polys + (size_t)s * n, x}); queries.push_back({perm_polys + (size_t)s * n, x_next}); }
+    for (uint32_t s = S; s-- > 0;) if (s + 1 < S) queries.push_back({perm_polys + (size_t)s * n, x_last});
+    for (uint32_t l = 0; l < L; ++l) {
+        queries.push_back({LK(l, 6), x}); queries.push_back({LK(l, 4), x}); queries.push_back({LK(l, 5), x});
+        queries.push_back({LK(l, 4), x_prev}); queries.push_back({LK(l, 6), x_next});
+    }
+    for (size_t i = 0; i < cs.fix_q.size(); i += 2) queries.push_back({pk->fixed_polys + (size_t)cs.fix_q[i] * n, rotate_omega(dom, x, cs.fix_q[i + 1])});
+    for (uint32_t j = 0; j < pk->P; ++j) queries.push_back({pk->perm_polys + (size_t)j * n, x});
+    queries.push_back({h_poly, x});
+    queries.push_back({random_poly, x});
+    {
+        std::vector<const fe_t*> bp; std::vector<HFr> bx;
+        std::set<std::pair<const fe_t*, std::array<uint64_t, 4>>> seen;
+        for (auto& qy : queries) {
+            std::array<uint64_t, 4> key = {qy.point.v[0], qy.point.v[1], qy.point.v[2], qy.point.v[3]};
+            if (seen.insert({qy.poly, key}).second) { bp.push_back(qy.poly); bx.push_back(qy.point); }
+        }
+        std::vector<HFr> vals(bp.size());
+        rc = eval_batch_run(ctx, bp.data(), bx.data(), bp.size(), n, vals.data());
+        if (rc != B200ZK_OK) return finish(rc);
+        for (size_t i = 0; i < bp.size(); ++i) eval_cache[{bp[i], {bx[i].v[0], bx[i].v[1], bx[i].v[2], bx[i].v[3]}}] = vals[i];
+    }
     for (size_t i = 0; i < cs.adv_q.size() && rc == B200ZK_OK; i += 2) {
         HFr e; rc = eval_at(advice_polys + (size_t)cs.adv_q[i] * n, rotate_omega(dom, x, cs.adv_q[i + 1]), &e);
         tr.write_scalar(e);
@@ -631,15 +660,12 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         tr.write_scalar(e);
     }
     if (rc != B200ZK_OK) return finish(rc);
-    fold_pieces_kernel<<<nb(n), PK_THREADS, 0, st>>>(h, q, n, to_dev(xn), h_poly);
-    ctx->launches++;
     {
         HFr e; rc = eval_at(random_poly, x, &e); tr.write_scalar(e);
     }
     for (uint32_t j = 0; j < pk->P && rc == B200ZK_OK; ++j) {
         HFr e; rc = eval_at(pk->perm_polys + (size_t)j * n, x, &e); tr.write_scalar(e);
     }
-    const HFr x_next = rotate_omega(dom, x, 1), x_prev = rotate_omega(dom, x, -1), x_last = rotate_omega(dom, x, -(int)(bf + 1));
     for (uint32_t s = 0; s < S && rc == B200ZK_OK; ++s) {
         const fe_t* zp = perm_polys + (size_t)s * n;
         HFr e;
@@ -658,20 +684,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     }
     if (rc != B200ZK_OK) return finish(rc);
 
-    // ---- step 15: multiopen queries in upstream order
-    for (size_t i = 0; i < cs.adv_q.size(); i += 2) queries.push_back({advice_polys + (size_t)cs.adv_q[i] * n, rotate_omega(dom, x, cs.adv_q[i + 1])});
-    for (uint32_t s = 0; s < S; ++s) { queries.push_back({perm_polys + (size_t)s * n, x}); queries.push_back({perm_polys + (size_t)s * n, x_next}); }
-    for (uint32_t s = S; s-- > 0;) if (s + 1 < S) queries.push_back({perm_polys + (size_t)s * n, x_last});
-    for (uint32_t l = 0; l < L; ++l) {
-        queries.push_back({LK(l, 6), x}); queries.push_back({LK(l, 4), x}); queries.push_back({LK(l, 5), x});
-        queries.push_back({LK(l, 4), x_prev}); queries.push_back({LK(l, 6), x_next});
-    }
-    for (size_t i = 0; i < cs.fix_q.size(); i += 2) queries.push_back({pk->fixed_polys + (size_t)cs.fix_q[i] * n, rotate_omega(dom, x, cs.fix_q[i + 1])});
-    for (uint32_t j = 0; j < pk->P; ++j) queries.push_back({pk->perm_polys + (size_t)j * n, x});
-    queries.push_back({h_poly, x});
-    queries.push_back({random_poly, x});
-
-    // ---- ProverSHPLONK::create_proof
+    // ---- step 15: ProverSHPLONK::create_proof over `queries` (built above)
     const HFr sy = tr.squeeze_challenge();
     // construct_intermediate_sets
     struct CommSet { const fe_t* poly; std::set<HFr, FrLess> pts; };

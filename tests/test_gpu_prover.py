@@ -52,7 +52,8 @@ def _run(zk, backend, orc, job, check_verify=True):
     return got
 
 
-@pytest.mark.parametrize("name,k", [("small", 5), ("small", 6), ("v3_shaped", 6), ("small", 8), ("mst_shaped", 9), ("v3_shaped", 11)])
+@pytest.mark.parametrize("name,k", [("small", 5), ("small", 6), ("v3_shaped", 6), ("small", 8), ("mst_shaped", 9), ("v3_shaped", 11),
+                                    ("generic_shapes", 6), ("generic_shapes", 10)])
 def test_proof_bytes_match_oracle(zk, backend, orc, name, k):
     job = getattr(_synth(zk), name)(k)
     _run(zk, backend, orc, job, check_verify=(k <= 9))

@@ -24,11 +24,11 @@ def _prove(orc, job, seed_s=77):
     return s, g, pk, proof, trace
 
 
-@pytest.mark.parametrize("name,k", [("small", 5), ("v3_shaped", 6), ("small", 7)])
+@pytest.mark.parametrize("name,k", [("small", 5), ("v3_shaped", 6), ("small", 7), ("generic_shapes", 5)])
 def test_oracle_proof_verifies(zk, orc, name, k):
     job = _job(zk, name, k)
     cs = job.cs
-    assert cs.blinding_factors() == 5 and cs.degree() == 6
+    assert cs.blinding_factors() == 5 and cs.degree() == (17 if name == "generic_shapes" else 6)
     s, g, pk, proof, trace = _prove(orc, job)
     A, L, S, q = cs.num_advice, len(cs.lookups), cs.num_permutation_sets(), cs.degree() - 1
     n_evals = len(cs.advice_queries) + len(cs.fixed_queries) + 1 + len(cs.permutation) + (3 * S - 1) + 5 * L
