@@ -27,6 +27,42 @@ int32_t ws_reserve(b200zk_ctx* ctx, Workspace& w, size_t bytes) {
     return B200ZK_OK;
 }
 
+// Fixed-base tables for ParamsKZG commits: every MSM of create_proof is over `g` or `g_lagrange`,
+// so 2^(c j) * base_i is precomputed once per params object (W * n * 64 B per basis; 0.9 GiB at
+// k = 20) when it fits comfortably in HBM.  B200ZK_MSM_PRECOMPUTE=0 disables it.
+int32_t params_build_tables(b200zk_params* p) {
+    b200zk_ctx* ctx = p->ctx;
+    const char* e = getenv("B200ZK_MSM_PRECOMPUTE");
+    if (e && e[0] == '0') return B200ZK_OK;
+    const size_t n = (size_t)1 << p->k;
+    if (p->k < 6) return B200ZK_OK;                               // tiny params: not worth it
+    MsmPre pre{msm_pre_shape(n), (uint32_t)n};
+    if ((size_t)pre.shape.nwin * n >= ((size_t)1 << 31)) return B200ZK_OK;
+    const size_t per_basis = (size_t)pre.shape.nwin * n * sizeof(affine_t);
+    const size_t nbases = p->d_g_lagrange ? 2 : 1;
+    size_t free_b = 0, total_b = 0;
+    ZK_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    if (per_basis * nbases > free_b / 5 * 2 || per_basis * nbases > ((size_t)48 << 30)) return B200ZK_OK;
+    if (cudaMalloc(&p->d_g_pre, per_basis) != cudaSuccess) { p->d_g_pre = nullptr; cudaGetLastError(); return B200ZK_OK; }
+    if (p->d_g_lagrange && cudaMalloc(&p->d_gl_pre, per_basis) != cudaSuccess) {
+        cudaFree(p->d_g_pre); p->d_g_pre = nullptr; p->d_gl_pre = nullptr; cudaGetLastError(); return B200ZK_OK;
+    }
+    p->pre = pre;
+    ZK_TRY(msm_precompute_run(ctx, p->d_g, n, pre.shape.c, pre.shape.nwin, p->d_g_pre));
+    if (p->d_g_lagrange) ZK_TRY(msm_precompute_run(ctx, p->d_g_lagrange, n, pre.shape.c, pre.shape.nwin, p->d_gl_pre));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+int32_t params_commit_run(b200zk_params* p, const fe_t* d_poly, size_t len, bool lagrange, host::HAffine* out) {
+    const affine_t* bases = lagrange ? p->d_g_lagrange : p->d_g;
+    if (!bases) return fail(p->ctx, B200ZK_EINVAL, "commit", "basis not loaded");
+    if (len > ((size_t)1 << p->k)) return fail(p->ctx, B200ZK_EINVAL, "commit", "polynomial longer than the SRS");
+    const affine_t* table = lagrange ? p->d_gl_pre : p->d_g_pre;
+    if (table) return msm_run_ex(p->ctx, d_poly, table, len, &p->pre, out);
+    return msm_run(p->ctx, d_poly, bases, len, out);
+}
+
 }  // namespace b200zk
 
 static void write_g1(const host::HAffine& a, void* out_g1) {
@@ -381,6 +417,8 @@ int32_t b200zk_params_load(b200zk_ctx* ctx, uint32_t k, const void* g, const voi
         cudaFree(p->d_g); cudaFree(p->d_g_lagrange); delete p;
         return fail(ctx, B200ZK_ECUDA, "params_load", cudaGetErrorString(e));
     }
+    int32_t rc = params_build_tables(p);
+    if (rc != B200ZK_OK) { b200zk_params_destroy(p); return rc; }
     *out = p;
     return B200ZK_OK;
 }
@@ -389,7 +427,7 @@ void b200zk_params_destroy(b200zk_params* p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
-    cudaFree(p->d_g); cudaFree(p->d_g_lagrange);
+    cudaFree(p->d_g); cudaFree(p->d_g_lagrange); cudaFree(p->d_g_pre); cudaFree(p->d_gl_pre);
     delete p;
 }
 
@@ -409,9 +447,11 @@ int32_t b200zk_params_read(b200zk_params* p, void* g_out, void* g_lagrange_out) 
 
 int32_t b200zk_commit_dev(b200zk_params* p, const void* d_poly, size_t len, int32_t lagrange, void* out_g1_host) {
     if (!p || !out_g1_host || (len && !d_poly) || len > ((size_t)1 << p->k)) return B200ZK_EINVAL;
-    const affine_t* bases = lagrange ? p->d_g_lagrange : p->d_g;
-    if (!bases) return fail(p->ctx, B200ZK_EINVAL, "commit", "basis not loaded");
-    return b200zk_msm_dev(p->ctx, d_poly, bases, len, out_g1_host);
+    ZK_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    host::HAffine r;
+    ZK_TRY(params_commit_run(p, (const fe_t*)d_poly, len, lagrange != 0, &r));
+    write_g1(r, out_g1_host);
+    return B200ZK_OK;
 }
 
 static int32_t commit_host(b200zk_params* p, const void* poly, size_t len, int32_t lagrange, void* out_g1) {
@@ -438,7 +478,8 @@ int32_t b200zk_params_setup(b200zk_ctx* ctx, uint32_t k, const void* s_fr, b200z
     int32_t rc = e == cudaSuccess ? params_setup_run(ctx, k, HFr::from_limbs(s_fr), p->d_g, p->d_g_lagrange)
                                   : fail(ctx, B200ZK_ENOMEM, "params_setup", cudaGetErrorString(e));
     if (rc == B200ZK_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, B200ZK_ECUDA, "params_setup", "sync failed");
-    if (rc != B200ZK_OK) { cudaFree(p->d_g); cudaFree(p->d_g_lagrange); delete p; return rc; }
+    if (rc == B200ZK_OK) rc = params_build_tables(p);
+    if (rc != B200ZK_OK) { b200zk_params_destroy(p); return rc; }
     *out = p;
     return B200ZK_OK;
 }

@@ -52,11 +52,22 @@ struct b200zk_domain {
     b200zk::fe_t* d_t_evaluations;           // 2^(extended_k - k), already inverted
 };
 
+namespace b200zk {
+struct MsmPre {                 // fixed-base table geometry (msm.cu)
+    MsmShape shape;
+    uint32_t stride;            // points per window = the params' n
+};
+}  // namespace b200zk
+
 struct b200zk_params {
     b200zk_ctx* ctx;
     uint32_t k;
     b200zk::affine_t* d_g;
     b200zk::affine_t* d_g_lagrange;
+    // fixed-base tables T[j*n + i] = 2^(c j) * base_i (null when they would not fit in memory)
+    b200zk::affine_t* d_g_pre;
+    b200zk::affine_t* d_gl_pre;
+    b200zk::MsmPre pre;
 };
 
 namespace b200zk {
@@ -93,6 +104,13 @@ int32_t fr_scale_periodic(b200zk_ctx* ctx, fe_t* d_a, size_t n, const fe_t* d_m,
 
 // msm.cu ---------------------------------------------------------------------
 int32_t msm_run(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, host::HAffine* out);
+// fixed-base variant: d_bases is a table built by msm_precompute_run (pre != null)
+int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, const MsmPre* pre, host::HAffine* out);
+int32_t msm_precompute_run(b200zk_ctx* ctx, const affine_t* d_bases, size_t n, uint32_t c, uint32_t nwin, affine_t* d_table);
+// commit over a params basis, through the fixed-base table when it exists
+int32_t params_commit_run(b200zk_params* p, const fe_t* d_poly, size_t len, bool lagrange, host::HAffine* out);
+// builds the fixed-base tables of a params object if memory allows (capi.cu)
+int32_t params_build_tables(b200zk_params* p);
 
 // poly.cu --------------------------------------------------------------------
 int32_t batch_invert_run(b200zk_ctx* ctx, fe_t* d_a, size_t n, int field /* 0 Fr, 1 Fq */);

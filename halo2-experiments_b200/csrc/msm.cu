@@ -48,9 +48,33 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_combine_bucket_kernel(con
 __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_reduce_kernel(const MsmArgs a) {
     msm_reduce_thread(a, blockIdx.x * blockDim.x + threadIdx.x);
 }
+__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_reduce_bits_kernel(const MsmArgs a) {
+    msm_reduce_bits_thread(a, blockIdx.x * blockDim.x + threadIdx.x);
+}
 __global__ void __launch_bounds__(MSM_FOLD_THREADS) msm_fold_kernel(const MsmArgs a) {
     __shared__ xyzz_t sm[MSM_FOLD_THREADS];
     msm_fold_block(a, blockIdx.x, blockDim.x, sm);
+}
+
+// fixed-base table: next window = 2^c * previous window (c doublings), normalised to affine
+__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_pre_shift_kernel(const affine_t* prev, size_t n, uint32_t c, xyzz_t* out, fe_t* zzz) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine_t p = prev[i];
+    xyzz_t acc = xyzz_from_affine(p);
+    for (uint32_t k = 0; k < c; ++k) acc = xyzz_dbl(acc);
+    out[i] = acc;
+    zzz[i] = acc.zzz;
+}
+__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_pre_normalize_kernel(const xyzz_t* in, const fe_t* zzz_inv, size_t n, affine_t* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    xyzz_t p = in[i];
+    fe_t iz = zzz_inv[i];
+    affine_t r;
+    if (Fq::is_zero(p.zz)) { r.x = Fq::zero(); r.y = Fq::zero(); }
+    else { fe_t t = Fq::mul(p.zz, iz); r.x = Fq::mul(p.x, Fq::sqr(t)); r.y = Fq::mul(p.y, iz); }
+    out[i] = r;
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -65,19 +89,40 @@ static void run_scan(b200zk_ctx* ctx, ScanArgs s) {
     ctx->launches += 3;
 }
 
-int32_t msm_run(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, host::HAffine* out) {
+// table[j*n + i] = 2^(c j) * bases[i] for j < nwin; table[0..n) is a copy of the bases.
+int32_t msm_precompute_run(b200zk_ctx* ctx, const affine_t* d_bases, size_t n, uint32_t c, uint32_t nwin, affine_t* d_table) {
+    cudaStream_t st = ctx->stream;
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_table, d_bases, n * sizeof(affine_t), cudaMemcpyDeviceToDevice, st));
+    ZK_TRY(ws_reserve(ctx, ctx->setup_ws, n * (sizeof(xyzz_t) + sizeof(fe_t))));
+    xyzz_t* xyzz = (xyzz_t*)ctx->setup_ws.p;
+    fe_t* zzz = (fe_t*)(xyzz + n);
+    for (uint32_t j = 1; j < nwin; ++j) {
+        msm_pre_shift_kernel<<<nb(n, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(d_table + (size_t)(j - 1) * n, n, c, xyzz, zzz);
+        ctx->launches++;
+        ZK_TRY(batch_invert_run(ctx, zzz, n, 1));
+        msm_pre_normalize_kernel<<<nb(n, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(xyzz, zzz, n, d_table + (size_t)j * n);
+        ctx->launches++;
+    }
+    ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+// d_bases: the n points (pre == null), or the fixed-base table of a params object with
+// `pre->stride` points per window (pre != null; then n <= stride).
+int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, const MsmPre* pre, host::HAffine* out) {
     if (n == 0) { *out = {host::HFq::zero(), host::HFq::zero()}; return B200ZK_OK; }
     if (n >= ((size_t)1 << 31)) return fail(ctx, B200ZK_EINVAL, "msm_run", "len must be < 2^31");
-    MsmShape s = msm_plan_shape(n, ctx->msm_force_c);
+    MsmShape s = pre ? pre->shape : msm_plan_shape(n, ctx->msm_force_c);
     const uint32_t B = (uint32_t)s.nbuckets;
+    const uint32_t nsums = pre ? s.c : s.nwin;              // results handed to the host
     // workspace layout
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     size_t o_counts = take((size_t)B * 4 + 4), o_offsets = take(((size_t)B + 1) * 4), o_cursor = take((size_t)B * 4);
     size_t o_entries = take(n * s.nwin * 4);
     size_t o_buckets = take((size_t)B * sizeof(xyzz_t));
-    size_t o_partials = take(((size_t)s.nwin << s.log_t) * sizeof(xyzz_t));
-    size_t o_wsum = take(s.nwin * sizeof(xyzz_t));
+    size_t o_partials = take(((size_t)nsums << s.log_t) * sizeof(xyzz_t));
+    size_t o_wsum = take(nsums * sizeof(xyzz_t));
     const uint32_t scan_items = MSM_SCAN_THREADS * MSM_SCAN_PER_THREAD;
     size_t o_bsums = take((size_t)((B + scan_items - 1) / scan_items) * 4);
     size_t o_toff1 = take(((size_t)B + 1) * 4), o_toff2 = take(((size_t)B + 1) * 4);
@@ -86,6 +131,7 @@ int32_t msm_run(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases,
     MsmArgs a{};
     a.scalars = d_scalars; a.bases = d_bases; a.n = (uint32_t)n;
     a.c = s.c; a.nwin = s.nwin; a.log_t = s.log_t;
+    a.pre = pre ? 1 : 0; a.pre_stride = pre ? pre->stride : 0; a.nbuckets = B;
     a.counts = (uint32_t*)(base + o_counts); a.offsets = (uint32_t*)(base + o_offsets); a.cursor = (uint32_t*)(base + o_cursor);
     a.entries = (uint32_t*)(base + o_entries);
     a.buckets = (xyzz_t*)(base + o_buckets); a.partials = (xyzz_t*)(base + o_partials); a.window_sums = (xyzz_t*)(base + o_wsum);
@@ -131,15 +177,20 @@ int32_t msm_run(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases,
         msm_combine_bucket_kernel<<<nb(B, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(t3);
         ctx->launches += 3;
     }
-    size_t nred = (size_t)s.nwin << s.log_t;
-    msm_reduce_kernel<<<nb(nred, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
-    msm_fold_kernel<<<s.nwin, MSM_FOLD_THREADS, 0, st>>>(a);
+    size_t nred = (size_t)nsums << s.log_t;
+    if (pre) msm_reduce_bits_kernel<<<nb(nred, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
+    else msm_reduce_kernel<<<nb(nred, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
+    msm_fold_kernel<<<nsums, MSM_FOLD_THREADS, 0, st>>>(a);
     ctx->launches += 2;
     ZK_CUDA(ctx, cudaGetLastError());
-    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, a.window_sums, s.nwin * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, a.window_sums, nsums * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
     ZK_CUDA(ctx, cudaStreamSynchronize(st));
-    *out = msm_finish(ctx->pinned, s.nwin, s.c);
+    *out = pre ? msm_finish_bits(ctx->pinned, s.c) : msm_finish(ctx->pinned, s.nwin, s.c);
     return B200ZK_OK;
+}
+
+int32_t msm_run(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, host::HAffine* out) {
+    return msm_run_ex(ctx, d_scalars, d_bases, n, nullptr, out);
 }
 
 }  // namespace b200zk

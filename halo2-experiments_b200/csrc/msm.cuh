@@ -36,6 +36,11 @@ struct MsmArgs {
     uint32_t c;                 // window bits
     uint32_t nwin;              // W = ceil(255 / c)
     uint32_t log_t;             // reduce: 2^log_t chunks per window
+    // Fixed-base mode (SRS commits): `bases` is the table T[j*pre_stride + i] = 2^(c j) * P_i, so the
+    // digit of window j selects a pre-shifted point and ALL windows share one set of 2^(c-1) buckets.
+    uint32_t pre;               // 0 = per-window buckets, 1 = fixed-base table
+    uint32_t pre_stride;        // points per window in the table (the params' n)
+    uint32_t nbuckets;          // W << (c-1), or 1 << (c-1) in fixed-base mode
     uint32_t* counts;           // [W << (c-1)]
     uint32_t* offsets;          // [(W << (c-1)) + 1]
     uint32_t* cursor;           // [W << (c-1)]
@@ -62,20 +67,23 @@ template <class F> ZK_D void msm_for_each_digit(const MsmArgs& a, uint32_t i, F 
         uint32_t d = msm_window_bits(s, j * a.c, a.c) + carry;
         uint32_t sign = 0;
         if (d > half) { d = (1u << a.c) - d; sign = 1; carry = 1; } else carry = 0;
-        if (d != 0) f(j * half + d - 1, sign);
+        if (d != 0) {
+            if (a.pre) f(d - 1, sign, j * a.pre_stride + i);
+            else f(j * half + d - 1, sign, i);
+        }
     }
 }
 
 ZK_D void msm_count_thread(const MsmArgs& a, uint32_t i) {
     if (i >= a.n) return;
-    msm_for_each_digit(a, i, [&](uint32_t key, uint32_t) { zk_atomic_add(&a.counts[key], 1u); });
+    msm_for_each_digit(a, i, [&](uint32_t key, uint32_t, uint32_t) { zk_atomic_add(&a.counts[key], 1u); });
 }
 
 ZK_D void msm_scatter_thread(const MsmArgs& a, uint32_t i) {
     if (i >= a.n) return;
-    msm_for_each_digit(a, i, [&](uint32_t key, uint32_t sign) {
+    msm_for_each_digit(a, i, [&](uint32_t key, uint32_t sign, uint32_t point) {
         uint32_t pos = zk_atomic_add(&a.cursor[key], 1u);
-        a.entries[pos] = (i << 1) | sign;
+        a.entries[pos] = (point << 1) | sign;
     });
 }
 
@@ -176,7 +184,7 @@ ZK_D void scan_final_block(const ScanArgs& s, uint32_t bid, uint32_t T, uint32_t
 // ---- bucket accumulation ---------------------------------------------------------------------
 // Fast path (every bucket has at most L entries): one thread per bucket.
 ZK_D void msm_accumulate_thread(const MsmArgs& a, uint32_t key) {
-    if (key >= (a.nwin << (a.c - 1))) return;
+    if (key >= a.nbuckets) return;
     uint32_t b = a.offsets[key], e = a.offsets[key + 1];
     xyzz_t acc = xyzz_identity();
     for (uint32_t k = b; k < e; ++k) {
@@ -258,6 +266,20 @@ ZK_D void msm_reduce_thread(const MsmArgs& a, uint32_t gid) {
         xyzz_add(acc, running);
     }
     if (b0 != 0) { xyzz_t s = xyzz_mul_small(running, b0); xyzz_add(acc, s); }
+    a.partials[gid] = acc;
+}
+
+// Fixed-base mode: sum_v v * B_v over ONE bucket set (v = b + 1 <= 2^(c-1)) by bit decomposition:
+//   sum_v v B_v = sum_{t < c} 2^t * S_t,   S_t = sum of the buckets whose multiplier has bit t set.
+// gid -> (bit t, chunk); every S_t is a plain parallel sum (no serial running-sum chain), the c
+// values go back to the host which applies the powers of two (c - 1 doublings).
+ZK_D void msm_reduce_bits_thread(const MsmArgs& a, uint32_t gid) {
+    if (gid >= (a.c << a.log_t)) return;
+    uint32_t t = gid >> a.log_t, chunk = gid & ((1u << a.log_t) - 1);
+    uint32_t m = (1u << (a.c - 1)) >> a.log_t, b0 = chunk * m;
+    xyzz_t acc = xyzz_identity();
+    for (uint32_t b = b0; b < b0 + m; ++b)
+        if (((b + 1) >> t) & 1) xyzz_add(acc, a.buckets[b]);
     a.partials[gid] = acc;
 }
 

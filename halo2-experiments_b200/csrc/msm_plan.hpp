@@ -31,6 +31,33 @@ inline MsmShape msm_plan_shape(size_t n, int force_c = 0) {
     return s;
 }
 
+// Fixed-base mode (bases known ahead: the SRS): one bucket set shared by all windows, so the
+// window can be wider — accumulate work is n * ceil(255 / c) additions, the reduce costs
+// c * 2^(c-2) additions once.  c ~ log2(n) - 2.
+inline MsmShape msm_pre_shape(size_t n_table) {
+    MsmShape s{};
+    uint32_t lg = 0; while (((size_t)1 << (lg + 1)) <= n_table) ++lg;
+    uint32_t c = lg > 2 ? lg - 2 : 2;
+    if (c < 8) c = 8;
+    if (c > 22) c = 22;
+    if (const char* e = getenv("B200ZK_MSM_PRE_C")) { long v = strtol(e, nullptr, 10); if (v >= 4 && v <= 24) c = (uint32_t)v; }
+    s.c = c;
+    s.nwin = (255 + c - 1) / c;
+    uint32_t log_b = c - 1;
+    s.log_t = log_b > 5 ? log_b - 5 : 0;                // 32 buckets per reduce thread
+    s.nbuckets = (size_t)1 << (c - 1);
+    return s;
+}
+
+// sum_t 2^t * bit_sums[t]  -> affine  (fixed-base mode; c XYZZ points)
+inline host::HAffine msm_finish_bits(const void* bit_sums, uint32_t c) {
+    using namespace host;
+    const HXyzz* s = (const HXyzz*)bit_sums;
+    HXyzz acc = hx_identity();
+    for (uint32_t t = c; t-- > 0;) { acc = hx_dbl(acc); acc = hx_add(acc, s[t]); }
+    return hx_to_affine(acc);
+}
+
 // sum_j 2^(c j) * window_sums[j]  -> affine.  window_sums: nwin XYZZ points (device format).
 inline host::HAffine msm_finish(const void* window_sums, uint32_t nwin, uint32_t c) {
     using namespace host;

@@ -298,7 +298,7 @@ static HFr rotate_omega(const b200zk_domain* d, const HFr& x, int rot) {
 // ParamsKZG::commit / commit_lagrange on a device polynomial
 static int32_t commit_dev(b200zk_pk* pk, const fe_t* d_poly, size_t len, bool lagrange, HAffine* out) {
     PhaseTimer t(pk, PH_MSM);
-    return msm_run(pk->ctx, d_poly, lagrange ? pk->params->d_g_lagrange : pk->params->d_g, len, out);
+    return params_commit_run(pk->params, d_poly, len, lagrange, out);
 }
 static int32_t lagrange_to_coeff(b200zk_pk* pk, fe_t* d_a) {
     PhaseTimer t(pk, PH_NTT);

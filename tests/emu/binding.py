@@ -114,3 +114,13 @@ def from_u512(wide):
     out = np.zeros((wide.shape[0], 4), dtype=np.uint64)
     lib().emu_from_u512(_p(wide), _p(out), ctypes.c_size_t(wide.shape[0]))
     return out
+
+
+def msm_pre(scalars, bases, c, seg_len=3):
+    """Fixed-base (precomputed window table) MSM path; len(scalars) <= len(bases) = table stride."""
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+    out = np.zeros(8, dtype=np.uint64)
+    lib().emu_msm_pre(_p(scalars), _p(bases), ctypes.c_uint32(scalars.shape[0]), ctypes.c_uint32(bases.shape[0]),
+                      ctypes.c_uint32(c), ctypes.c_uint32(seg_len), _p(out))
+    return out

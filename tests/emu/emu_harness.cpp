@@ -90,6 +90,7 @@ void emu_msm(const fe_t* scalars, const affine_t* bases, uint32_t n, int force_c
     std::vector<xyzz_t> buckets(s.nbuckets), partials((size_t)s.nwin << s.log_t), wsum(s.nwin);
     MsmArgs a{};
     a.scalars = scalars; a.bases = bases; a.n = n; a.c = s.c; a.nwin = s.nwin; a.log_t = s.log_t;
+    a.pre = 0; a.pre_stride = 0; a.nbuckets = (uint32_t)s.nbuckets;
     a.counts = counts.data(); a.offsets = offsets.data(); a.cursor = cursor.data(); a.entries = entries.data();
     a.buckets = buckets.data(); a.partials = partials.data(); a.window_sums = wsum.data();
     for (uint32_t i = 0; i < n; ++i) msm_count_thread(a, i);
@@ -126,6 +127,60 @@ void emu_msm(const fe_t* scalars, const affine_t* bases, uint32_t n, int force_c
     std::vector<xyzz_t> smx(8);
     for (uint32_t j = 0; j < s.nwin; ++j) msm_fold_block(a, j, 8, smx.data());
     host::HAffine r = msm_finish(wsum.data(), s.nwin, s.c);
+    memcpy(out_affine64, &r, 64);
+}
+
+// Fixed-base mode of msm.cu: table T[j*stride + i] = 2^(c j) * base_i (built here with the host
+// curve code), one bucket set, bit-decomposition reduce.  n <= stride scalars.
+void emu_msm_pre(const fe_t* scalars, const affine_t* bases, uint32_t n, uint32_t stride, uint32_t c, uint32_t seg_len, uint32_t* out_affine64) {
+    MsmShape s{};
+    s.c = c; s.nwin = (255 + c - 1) / c; s.log_t = (c - 1) > 2 ? (c - 1) - 2 : 0; s.nbuckets = (size_t)1 << (c - 1);
+    std::vector<affine_t> table((size_t)s.nwin * stride);
+    for (uint32_t i = 0; i < stride; ++i) {
+        host::HAffine p; memcpy(&p, &bases[i], 64);
+        host::HXyzz cur = host::hx_from_affine(p);
+        for (uint32_t j = 0; j < s.nwin; ++j) {
+            host::HAffine q = host::hx_to_affine(cur);
+            memcpy(&table[(size_t)j * stride + i], &q, 64);
+            for (uint32_t d = 0; d < c; ++d) cur = host::hx_dbl(cur);
+        }
+    }
+    const uint32_t B = (uint32_t)s.nbuckets;
+    std::vector<uint32_t> counts(B, 0), offsets(B + 1), cursor(B), entries((size_t)n * s.nwin + 1);
+    std::vector<xyzz_t> buckets(B), partials((size_t)s.c << s.log_t), wsum(s.c);
+    MsmArgs a{};
+    a.scalars = scalars; a.bases = table.data(); a.n = n; a.c = s.c; a.nwin = s.nwin; a.log_t = s.log_t;
+    a.pre = 1; a.pre_stride = stride; a.nbuckets = B;
+    a.counts = counts.data(); a.offsets = offsets.data(); a.cursor = cursor.data(); a.entries = entries.data();
+    a.buckets = buckets.data(); a.partials = partials.data(); a.window_sums = wsum.data();
+    for (uint32_t i = 0; i < n; ++i) msm_count_thread(a, i);
+    auto scan = [&](ScanArgs sa) {
+        const uint32_t T = 4, items = T * MSM_SCAN_PER_THREAD;
+        const uint32_t nb = (sa.total + items - 1) / items;
+        std::vector<uint32_t> bs(nb), sm(2 * T);
+        sa.blocksums = bs.data();
+        for (uint32_t b = 0; b < nb; ++b) scan_blocksum_block(sa, b, T, sm.data());
+        scan_top_block(sa, nb, T, sm.data());
+        for (uint32_t b = 0; b < nb; ++b) scan_final_block(sa, b, T, sm.data());
+    };
+    scan(ScanArgs{a.counts, a.offsets, a.cursor, nullptr, nullptr, B, 0, 0});
+    for (uint32_t i = 0; i < n; ++i) msm_scatter_thread(a, i);
+    uint32_t L = seg_len;
+    size_t t1_bound = (size_t)n * s.nwin / L + B, t2_bound = t1_bound / L + B;
+    std::vector<uint32_t> toff1(B + 1), toff2(B + 1);
+    std::vector<xyzz_t> p1(t1_bound), p2(t2_bound);
+    scan(ScanArgs{a.counts, toff1.data(), nullptr, nullptr, nullptr, B, 0, L});
+    MsmTaskArgs t1{a.offsets, toff1.data(), B, toff1.data() + B, L, nullptr, p1.data()};
+    for (uint32_t t = 0; t < t1_bound; ++t) msm_accumulate_task_thread(a, t1, t);
+    scan(ScanArgs{toff1.data(), toff2.data(), nullptr, nullptr, nullptr, B, 1, L});
+    MsmTaskArgs t2{toff1.data(), toff2.data(), B, toff2.data() + B, L, p1.data(), p2.data()};
+    for (uint32_t t = 0; t < t2_bound; ++t) msm_combine_task_thread(t2, t);
+    MsmTaskArgs t3{toff2.data(), nullptr, B, nullptr, 0, p2.data(), a.buckets};
+    for (uint32_t b = 0; b < B; ++b) msm_combine_bucket_thread(t3, b);
+    for (uint32_t g = 0; g < (s.c << s.log_t); ++g) msm_reduce_bits_thread(a, g);
+    std::vector<xyzz_t> smx(4);
+    for (uint32_t t = 0; t < s.c; ++t) msm_fold_block(a, t, 4, smx.data());
+    host::HAffine r = msm_finish_bits(wsum.data(), s.c);
     memcpy(out_affine64, &r, 64);
 }
 

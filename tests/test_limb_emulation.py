@@ -207,3 +207,20 @@ def test_msm_task_balanced_accumulation(orc, seg_len):
         S = orc.ints_to_mont(ss)
         got = emu.msm(S, bases, force_c=5, fast_max=0, seg_len=seg_len)
         assert np.array_equal(got, orc.g1_batch_normalize(orc.best_multiexp(S, bases))[0]), name
+
+
+@pytest.mark.parametrize("c", [4, 5, 7])
+def test_msm_fixed_base_table_path(orc, c):
+    """Fixed-base mode: one bucket set over a table of 2^(cj) multiples, bit-decomposition reduce."""
+    rnd = random.Random(500 + c)
+    n = 40
+    ks = [rnd.randrange(P.R_MOD) for _ in range(n)]
+    bases = orc.g1_fixed_base_mul(orc.ints_to_mont(ks))
+    bases[3] = 0                                                       # identity base
+    for name, ss, m in (("uniform", [rnd.randrange(P.R_MOD) for _ in range(n)], n),
+                        ("edge", [0, 1, P.R_MOD - 1, 1 << 253, (1 << 254) % P.R_MOD] + [rnd.randrange(P.R_MOD) for _ in range(n - 5)], n),
+                        ("bytes", [rnd.randrange(256) for _ in range(n)], n),
+                        ("short", [rnd.randrange(P.R_MOD) for _ in range(17)], 17)):    # commit of a shorter polynomial
+        S = orc.ints_to_mont(ss)
+        got = emu.msm_pre(S, bases, c)
+        assert np.array_equal(got, orc.g1_batch_normalize(orc.best_multiexp(S, bases[:m]))[0]), name
