@@ -37,9 +37,11 @@ inline MsmShape msm_plan_shape(size_t n, int force_c = 0) {
 inline MsmShape msm_pre_shape(size_t n_table) {
     MsmShape s{};
     uint32_t lg = 0; while (((size_t)1 << (lg + 1)) <= n_table) ++lg;
-    uint32_t c = lg > 2 ? lg - 2 : 2;
+    // measured (profiles/r01_msm_fixed_base_window_sweep.txt): c = 16 is best up to 2^19 points,
+    // 17 from 2^20; wider windows lose to the c * 2^(c-2) additions of the reduce
+    uint32_t c = lg >= 20 ? 17 : 16;
+    if (lg < 12) c = lg + 4;
     if (c < 8) c = 8;
-    if (c > 22) c = 22;
     if (const char* e = getenv("B200ZK_MSM_PRE_C")) { long v = strtol(e, nullptr, 10); if (v >= 4 && v <= 24) c = (uint32_t)v; }
     s.c = c;
     s.nwin = (255 + c - 1) / c;
