@@ -34,9 +34,62 @@ def mont_from_ints(vals):
     return out
 
 
-def mont_from_small(arr, lut_fn=lambda v: v):
-    """Vectorised: arr of small non-negative ints; value = lut_fn(key) converted via a LUT."""
+_R_LIMBS = np.array([(R_MOD >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)], dtype=np.uint64)
+_CHUNK_LUTS = None
+
+
+def _add_mod_r(a, b):
+    """Vectorised (a + b) mod r on (n,4) uint64 limb arrays with a, b < r (no field multiplication)."""
+    out = np.empty_like(a)
+    carry = np.zeros(a.shape[0], dtype=np.uint64)
+    for j in range(4):
+        s = a[:, j] + b[:, j]
+        c1 = s < a[:, j]
+        s2 = s + carry
+        c2 = s2 < s
+        out[:, j] = s2
+        carry = (c1 | c2).astype(np.uint64)
+    # r < 2^254, so a + b < 2^255 never carries out; subtract r where out >= r
+    ge = np.ones(a.shape[0], dtype=bool)
+    decided = np.zeros(a.shape[0], dtype=bool)
+    for j in (3, 2, 1, 0):
+        gt, lt = out[:, j] > _R_LIMBS[j], out[:, j] < _R_LIMBS[j]
+        ge = np.where(~decided & lt, False, ge)
+        decided |= gt | lt
+    borrow = np.zeros(a.shape[0], dtype=np.uint64)
+    sub = np.empty_like(out)
+    for j in range(4):
+        d = out[:, j] - _R_LIMBS[j]
+        b1 = out[:, j] < _R_LIMBS[j]
+        d2 = d - borrow
+        b2 = d < borrow
+        sub[:, j] = d2
+        borrow = (b1 | b2).astype(np.uint64)
+    out[ge] = sub[ge]
+    return out
+
+
+def mont_from_u64(arr):
+    """Montgomery form of non-negative integers < 2^64, vectorised: the value is split into four
+    16-bit chunks, each chunk position has a 65536-entry table of Montgomery forms (Python ints,
+    built once), and the four table rows are added mod r with limb arithmetic."""
+    global _CHUNK_LUTS
+    if _CHUNK_LUTS is None:
+        _CHUNK_LUTS = [mont_from_ints([(d << (16 * p)) for d in range(65536)]) for p in range(4)]
+    v = np.asarray(arr).astype(np.uint64)
+    acc = _CHUNK_LUTS[0][(v & np.uint64(0xFFFF)).astype(np.int64)]
+    for p in range(1, 4):
+        chunk = ((v >> np.uint64(16 * p)) & np.uint64(0xFFFF)).astype(np.int64)
+        if chunk.any():
+            acc = _add_mod_r(acc, _CHUNK_LUTS[p][chunk])
+    return acc
+
+
+def mont_from_small(arr, lut_fn=None):
+    """arr of non-negative ints < 2^63.  With lut_fn the value is lut_fn(key) (few distinct keys)."""
     arr = np.asarray(arr, dtype=np.int64)
+    if lut_fn is None:
+        return mont_from_u64(arr)
     keys, inv = np.unique(arr, return_inverse=True)
     lut = mont_from_ints([lut_fn(int(k)) for k in keys])
     return lut[inv]
@@ -124,7 +177,7 @@ def _build(k, seed, n_state, n_bytes, n_rc, with_sum_gate=True):
         # state2[r+1] = state2[r] + rc0[r]  (running sum of small constants stays small)
         rc0 = rc_small[0] if n_rc else np.zeros(n, dtype=np.int64)
         cum = np.concatenate([[7], 7 + np.cumsum(rc0[:-1].astype(np.int64))])   # < 2^55 for k <= 24
-        adv[ST + 2] = mont_from_ints(cum)
+        adv[ST + 2] = mont_from_u64(cum)
     for c in range(3, n_state):
         adv[ST + c] = random_field(n, rng)                       # dense, Poseidon-state-like
     adv[5 + n_state] = random_field(n, rng)                      # partial_sbox: dense

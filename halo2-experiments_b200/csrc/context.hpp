@@ -21,6 +21,7 @@ struct NttPlan {
     fe_t* roots = nullptr;
     fe_t* tw_lo = nullptr;
     fe_t* tw_hi = nullptr;
+    fe_t* tw_full = nullptr;    // omega^E for all E < N (multi-pass plans up to 2^24)
 };
 
 struct Workspace {

@@ -25,6 +25,13 @@ __global__ void fr_scale_periodic_kernel(fe_t* a, size_t n, const fe_t* m, uint3
     for (; i < n; i += stride) { fe_t x = a[i], y = m[i & (period - 1)]; a[i] = Fr::mul(x, y); }
 }
 
+__global__ void ntt_tw_full_kernel(fe_t* out, size_t n, const fe_t* lo, const fe_t* hi, uint32_t bits) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe_t a = lo[i & ((1u << bits) - 1)], b = hi[i >> bits];
+    out[i] = Fr::mul(a, b);
+}
+
 static fe_t to_dev(const host::HFr& x) { fe_t r; memcpy(r.l, x.v, 32); return r; }
 
 static int32_t build_plan(b200zk_ctx* ctx, uint32_t log_n, const host::HFr& omega, NttPlan& plan) {
@@ -35,7 +42,7 @@ static int32_t build_plan(b200zk_ctx* ctx, uint32_t log_n, const host::HFr& omeg
         long v = strtol(e, nullptr, 10);
         return (v < (long)lo || v > (long)hi) ? dflt : (uint32_t)v;
     };
-    plan.shape = ntt_plan_shape(log_n, tune("B200ZK_NTT_MAX_M", NTT_MAX_LOG_M, 2, NTT_MAX_LOG_M),
+    plan.shape = ntt_plan_shape(log_n, tune("B200ZK_NTT_MAX_M", NTT_MAX_LOG_M, 2, 12),
                                 tune("B200ZK_NTT_MAX_TW", NTT_MAX_LOG_TW, 0, 5), tune("B200ZK_NTT_TILE_CAP", NTT_TILE_CAP_LOG, 6, 12));
     const NttShape& s = plan.shape;
     size_t n_roots = (size_t)1 << (s.log_roots ? s.log_roots - 1 : 0);
@@ -52,6 +59,18 @@ static int32_t build_plan(b200zk_ctx* ctx, uint32_t log_n, const host::HFr& omeg
     launch(plan.roots, w_r, n_roots, 0);
     launch(plan.tw_lo, omega, n_lo, 0);
     launch(plan.tw_hi, omega, n_hi, s.tw_lo_bits);
+    // full inter-pass twiddle table: one scattered 32-byte read instead of two reads and a field
+    // multiplication per element and pass (the kernel is IMAD-bound, not bandwidth-bound)
+    const char* e = getenv("B200ZK_NTT_FULL_TW");
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (s.npass > 1 && log_n <= 26 && (sizeof(fe_t) << log_n) * 8 < free_b && !(e && e[0] == '0')) {
+        size_t N = (size_t)1 << log_n;
+        if (cudaMalloc(&plan.tw_full, N * sizeof(fe_t)) == cudaSuccess) {
+            ntt_tw_full_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(plan.tw_full, N, plan.tw_lo, plan.tw_hi, s.tw_lo_bits);
+            ctx->launches++;
+        } else { plan.tw_full = nullptr; cudaGetLastError(); }
+    }
     ZK_CUDA(ctx, cudaGetLastError());
     return B200ZK_OK;
 }
@@ -110,6 +129,7 @@ static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, f
         a.roots = plan.roots; a.log_roots = s.log_roots;
         a.tw_lo = plan.tw_lo; a.tw_hi = plan.tw_hi; a.tw_lo_bits = s.tw_lo_bits;
         a.tw_shift = log_n - q.log_m - q.log_l; a.l_offset = 0;
+        a.tw_full = plan.tw_full;
         size_t smem = sizeof(fe_t) << (q.log_m + q.log_tw);
         uint32_t tile = 1u << (q.log_m + q.log_tw);
         uint32_t threads = tile / 2 < NTT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : NTT_THREADS;

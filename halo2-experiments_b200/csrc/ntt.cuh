@@ -43,6 +43,7 @@ struct NttPassArgs {
     uint32_t log_roots;
     const fe_t* tw_lo;      // omega^i,            i < 2^tw_lo_bits
     const fe_t* tw_hi;      // omega^(j << lo_bits), j < N >> tw_lo_bits
+    const fe_t* tw_full;    // optional: omega^E for every E < N (saves the lo*hi multiplication)
     uint32_t tw_lo_bits;
     uint32_t tw_shift;      // inter-pass twiddle exponent = ((l + l_offset) * k) << tw_shift
     uint32_t l_offset;      // global column index of local column 0 (sharded four-step column step)
@@ -72,6 +73,7 @@ ZK_D void tile_st(half_t* sm, uint32_t tile_elems, uint32_t idx, const fe_t& v) 
 // omega^E for E < N via the two-level table
 ZK_D fe_t ntt_twiddle(const NttPassArgs& a, uint32_t E) {
     uint32_t lo = E & ((1u << a.tw_lo_bits) - 1), hi = E >> a.tw_lo_bits;
+    if (a.tw_full) return a.tw_full[E];
     if (hi == 0) return a.tw_lo[lo];
     if (lo == 0) return a.tw_hi[hi];
     return Fr::mul(a.tw_lo[lo], a.tw_hi[hi]);

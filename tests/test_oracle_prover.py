@@ -88,3 +88,14 @@ def test_permute_expression_pair_cpp_matches_python(orc):
     assert sorted(orc.mont_to_ints(s1)) == sorted(table) and orc.mont_to_ints(a1) == sorted(inp)
     with pytest.raises(ValueError):
         orc.permute_expression_pair(orc.ints_to_mont([1, 2, 99]), orc.ints_to_mont([1, 2, 3]), 3)
+
+
+def test_frontend_montgomery_conversion(zk, orc):
+    """circuits_synth.mont_from_u64 (vectorised, no field multiplication) == x * 2^256 mod r."""
+    import importlib
+    synth = importlib.import_module(zk.__name__ + ".circuits_synth")
+    rng = np.random.Generator(np.random.PCG64(1))
+    vals = np.concatenate([rng.integers(0, 1 << 63, size=3000, dtype=np.int64), np.array([0, 1, 65535, 65536, (1 << 62) + 12345, (1 << 63) - 1])])
+    got = synth.mont_from_u64(vals)
+    assert np.array_equal(got, orc.ints_to_mont([int(v) for v in vals]))
+    assert np.array_equal(synth.mont_from_small(vals), got)
