@@ -204,6 +204,9 @@ struct b200zk_pk {
     size_t arena_bytes = 0;
     uint32_t* d_err = nullptr;
     float phase_ms[7] = {0, 0, 0, 0, 0, 0, 0};
+    struct TimerEv { cudaEvent_t e0, e1; int slot; };
+    std::vector<TimerEv> timer_events;                // pool, grown on demand
+    size_t timer_used = 0;
     std::vector<void*> owned;
     std::map<std::string, std::pair<const void*, size_t>> dbg;     // buffers of the last proof, for b200zk_pk_debug_buffer
 };
@@ -247,17 +250,29 @@ static size_t arena_need(const b200zk_pk* pk) {
     return elems * sizeof(fe_t) + (size_t)draws * 64 + (64 << 10);
 }
 
+// Per-phase device time without extra synchronisation: event pairs from a pool owned by the pk are
+// recorded around each phase and summed once at the end of the proof (phase_timers_collect).
 struct PhaseTimer {
-    b200zk_ctx* ctx; float* acc; cudaEvent_t e0, e1;
-    PhaseTimer(b200zk_pk* pk, int slot) : ctx(pk->ctx), acc(&pk->phase_ms[slot]) {
-        e0 = ctx->events[48 + 2 * slot]; e1 = ctx->events[49 + 2 * slot];
-        cudaEventRecord(e0, ctx->stream);
+    b200zk_pk* pk; size_t idx;
+    PhaseTimer(b200zk_pk* pk_, int slot) : pk(pk_) {
+        idx = pk->timer_used++;
+        if (idx >= pk->timer_events.size()) {
+            cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+            pk->timer_events.push_back({a, b, slot});
+        }
+        pk->timer_events[idx].slot = slot;
+        cudaEventRecord(pk->timer_events[idx].e0, pk->ctx->stream);
     }
-    ~PhaseTimer() {
-        cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1);
-        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); *acc += ms;
-    }
+    ~PhaseTimer() { cudaEventRecord(pk->timer_events[idx].e1, pk->ctx->stream); }
 };
+static void phase_timers_collect(b200zk_pk* pk) {
+    cudaStreamSynchronize(pk->ctx->stream);
+    for (size_t i = 0; i < pk->timer_used; ++i) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, pk->timer_events[i].e0, pk->timer_events[i].e1) == cudaSuccess) pk->phase_ms[pk->timer_events[i].slot] += ms;
+    }
+    pk->timer_used = 0;
+}
 enum { PH_MSM = 0, PH_NTT = 1, PH_QUOT = 2, PH_LOOKUP = 3, PH_PERM = 4, PH_OPEN = 5, PH_OTHER = 6 };
 
 static int cmp_canonical(const HFr& a, const HFr& b) {
@@ -343,6 +358,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     const size_t usable = n - (bf + 1);
     const uint32_t rot_scale = 1u << (dom->extended_k - dom->k);
     for (float& f : pk->phase_ms) f = 0;
+    pk->timer_used = 0;
     ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     ZK_CUDA(ctx, cudaMemsetAsync(pk->d_err, 0, 4, st));
     host::Transcript tr;
@@ -789,6 +805,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         ZK_TRY(commit_dev(pk, t0, n - 1, false, &pt));
         tr.write_point(pt);
     }
+    phase_timers_collect(pk);
     proof_out = tr.proof();
     return B200ZK_OK;
 }
@@ -839,6 +856,7 @@ void b200zk_pk_destroy(b200zk_pk* pk) {
     cudaSetDevice(pk->ctx->device);
     cudaStreamSynchronize(pk->ctx->stream);
     for (void* p : pk->owned) cudaFree(p);
+    for (auto& t : pk->timer_events) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     if (pk->dom) b200zk_domain_destroy(pk->dom);
     delete pk;
 }
