@@ -148,7 +148,15 @@ def timed(be, dist, local, steps, fn):
 
 
 CIRCUITS = {"mst": ("mst_shaped", "MST-shaped synthetic circuit k={k}: 20 advice, 8 u8 lookups, 16 permutation columns, degree 6, ext 8n"),
-            "v3": ("v3_shaped", "Merkle-v3-shaped synthetic circuit k={k}: 9 advice, no lookups, 12 permutation columns, degree 6, ext 8n")}
+            "v3": ("v3_shaped", "Merkle-v3-shaped synthetic circuit k={k}: 9 advice, no lookups, 12 permutation columns, degree 6, ext 8n"),
+            "mst_real": ("merkle_sum_tree_job", "the reference's MerkleSumTreeCircuit (Poseidon width 5, LtChip, 16-level path = 2^16 leaves) padded to k={k}: 20 advice, 15 fixed, 8 u8 lookups, 16 permutation columns, degree 6, ext 8n; witness rows mostly empty"),
+            "v3_real": ("merkle_v3_job", "the reference's MerkleTreeV3Circuit (Poseidon width 3, 13-level path) at k={k}: 7 advice, 10 fixed, 10 permutation columns, degree 6, ext 8n")}
+
+
+def build_job(zk, circuit, k, seed):
+    """Dense synthetic circuits come from circuits_synth, the reference's real circuits from chips."""
+    mod = importlib.import_module(zk.__name__ + (".chips" if circuit.endswith("_real") else ".circuits_synth"))
+    return getattr(mod, CIRCUITS[circuit][0])(k, seed=seed)
 WORKLOAD_TEXT = {
     "prove": "create_proof (KZG/SHPLONK/Blake2b), {circuit}; SRS + pk resident in HBM",
     "msm": "bn256 G1 MSM 2^{L} points (best_multiexp drop-in), uniform scalars, bases [s^i]G resident in HBM",
@@ -170,7 +178,7 @@ def run_gpu(args):
         k = args.k
         n = 1 << k
         synth = importlib.import_module(zk.__name__ + ".circuits_synth")
-        job = getattr(synth, CIRCUITS[args.circuit][0])(k, seed=1 + rank)
+        job = build_job(zk, args.circuit, k, 1 + rank)
         params = zk.ParamsKZG.setup(be, k, random_scalars(1, 4242)[0])
         pk = zk.ProvingKey(params, job.cs, k, job.fixed, job.map_col, job.map_row)
         A = job.cs.num_advice
@@ -353,9 +361,8 @@ def cpu_sample(args):
     if args.workload == "prove":
         from oracle import prover as OP
         zk = load_package()
-        synth = importlib.import_module(zk.__name__ + ".circuits_synth")
         ks = min(args.k, args.cpu_k)
-        job = getattr(synth, CIRCUITS[args.circuit][0])(ks, seed=1)
+        job = build_job(zk, args.circuit, ks, 1)
         g, gl = orc.params_setup(ks, orc.random_fr(1, 4242)[0])
         pk = OP.keygen_pk(job.cs, ks, job.fixed, job.map_col, job.map_row)
         wide = np.random.Generator(np.random.PCG64(99)).integers(0, 1 << 64, size=(OP.rng_draws_needed(job.cs, ks), 8), dtype=np.uint64)

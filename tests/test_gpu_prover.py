@@ -82,3 +82,31 @@ def test_lookup_failure_is_reported(zk, backend, orc):
         pk_cpu = OP.keygen_pk(job.cs, job.k, job.fixed, job.map_col, job.map_row)
         OP.create_proof(g, gl, pk_cpu, job.advice, job.instances, wide, job.transcript_repr)
     pk.close(); params.close()
+
+
+def _frontend(zk):
+    return importlib.import_module(zk.__name__ + ".frontend"), importlib.import_module(zk.__name__ + ".chips")
+
+
+def test_real_merkle_sum_tree_k9(zk, backend, orc):
+    """BASELINE config 1 on the GPU: the reference's MerkleSumTreeCircuit (Poseidon width 5, LtChip,
+    u8 lookups) with test_full_prover's inputs at k = 9, proof bytes identical to the oracle and
+    accepted by the verifier restatement."""
+    fe, chips = _frontend(zk)
+    leaf, elements, indices = (10, 100), [(1, 10), (5, 50), (6, 60), (9, 90), (9, 90)], [0] * 5
+    root = chips.compute_merkle_sum_root(leaf, elements, indices)
+    circuit = chips.MerkleSumTreeCircuit(leaf[0], leaf[1], [e[0] for e in elements], [e[1] for e in elements], indices, 500)
+    job = fe.synthesize_job(circuit, 9, [[leaf[0], leaf[1], root[0], 500]])
+    _run(zk, backend, orc, job, check_verify=True)
+
+
+@pytest.mark.parametrize("k,levels", [(10, 5), (14, 13)])
+def test_real_merkle_v3(zk, backend, orc, k, levels):
+    """BASELINE config 2: Poseidon Merkle tree v3 full prove (k = 14), bytes identical to the CPU path."""
+    fe, chips = _frontend(zk)
+    rng = np.random.Generator(np.random.PCG64(k))
+    elements = [int(x) for x in rng.integers(1, 1 << 62, size=levels)]
+    indices = [int(x) for x in rng.integers(0, 2, size=levels)]
+    root = chips.compute_merkle_root(99, elements, indices)
+    job = fe.synthesize_job(chips.MerkleTreeV3Circuit(99, elements, indices), k, [[99, root]])
+    _run(zk, backend, orc, job, check_verify=(k <= 10))
