@@ -9,14 +9,20 @@
 // Calculation::Horner:  acc <- acc * factor + pop().
 //   custom gates : every gate polynomial followed by FOLD(acc0, y)
 //   lookups      : input expressions with FOLD(acc0, theta), table expressions with FOLD(acc1, theta)
-// Upstream's graph evaluator orders and deduplicates the same arithmetic differently; the value
-// per row is the same field element, hence bit-exact.
+// Like upstream's GraphEvaluator (which interns every Calculation once), repeated sub-expressions
+// are evaluated once per row: the host (ex_share_common in prover.cu) hash-conses the expression
+// trees, and a shared node is computed at its first use, kept with TEE(slot) and re-read with
+// TMP(slot).  In the Merkle Sum Tree circuit the five (state + rc)^5 terms of Pow5Chip's
+// "full round" gate appear in five polynomials each, and the compressed-selector products
+// q(1-q)(2-q).. in every polynomial they gate: 281 -> ~150 multiplications per row.
+// Upstream orders the same arithmetic differently; the value per row is the same field element,
+// hence bit-exact.
 #pragma once
 #include "field.cuh"
 
 namespace b200zk {
 
-enum : uint32_t { EX_CONST = 0, EX_FIXED = 1, EX_ADVICE = 2, EX_INSTANCE = 3, EX_NEG = 4, EX_ADD = 5, EX_MUL = 6, EX_SCALE = 7, EX_FOLD = 8 };
+enum : uint32_t { EX_CONST = 0, EX_FIXED = 1, EX_ADVICE = 2, EX_INSTANCE = 3, EX_NEG = 4, EX_ADD = 5, EX_MUL = 6, EX_SCALE = 7, EX_FOLD = 8, EX_TEE = 9, EX_TMP = 10 };
 enum : uint32_t { EXF_THETA = 0, EXF_BETA = 1, EXF_GAMMA = 2, EXF_Y = 3 };
 // output modes
 enum : uint32_t {
@@ -26,6 +32,7 @@ enum : uint32_t {
 };
 
 static constexpr int EX_STACK = 16;
+static constexpr int EX_TMPS = 24;          // shared sub-expression slots per row
 
 struct ExprArgs {
     const uint32_t* prog;
@@ -54,6 +61,7 @@ ZK_D fe_t expr_load(const fe_t* const* cols, const int32_t* q, uint32_t qi, uint
 
 ZK_D void expr_eval_row(const ExprArgs& a, uint32_t idx) {
     fe_t stk[EX_STACK];
+    fe_t tmp[EX_TMPS];
     int sp = 0;
     fe_t acc0 = Fr::zero(), acc1 = Fr::zero();
     for (uint32_t pc = 0; pc < a.prog_len; ++pc) {
@@ -74,6 +82,8 @@ ZK_D void expr_eval_row(const ExprArgs& a, uint32_t idx) {
                 else acc1 = Fr::add(Fr::mul(acc1, f), v);
                 break;
             }
+            case EX_TEE: tmp[arg] = stk[sp - 1]; break;
+            case EX_TMP: stk[sp++] = tmp[arg]; break;
             default: break;
         }
     }

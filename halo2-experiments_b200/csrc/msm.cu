@@ -15,11 +15,50 @@ static constexpr uint32_t MSM_FOLD_THREADS = 128;
 // bucket: 5.09 ms -> 4.6 ms for a dense 2^20 MSM, profiles/r01_sweep_tunables.jsonl)
 static constexpr uint32_t MSM_FAST_MAX = 16;
 
+// Digit pass, one scalar per lane, the W windows walked in lockstep by the warp.  Same keys and
+// entries as msm_count_thread / msm_scatter_thread (msm.cuh), with two warp-level shortcuts that
+// matter for real witness columns:
+//   * a warp whose 32 scalars are all zero leaves at once (advice columns of a padded circuit);
+//   * when all 32 lanes hit the same bucket in a window — grand-product columns are 1 on every
+//     unused row, sorted lookup columns are long runs of one value — one lane adds 32 to the
+//     counter / claims 32 slots instead of 32 atomics serialising on one address
+//     (1.1 ms -> count and 1.8 ms -> scatter for a z column of the Merkle Sum Tree circuit at k = 20).
+template <bool SCATTER> __device__ __forceinline__ void msm_digit_pass_warp(const MsmArgs& a, uint32_t i) {
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31;
+    fe_t s = i < a.n ? a.scalars[i] : Fr::zero();
+    if (!__any_sync(FULL, !Fr::is_zero(s))) return;
+    s = Fr::from_mont(s);
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (a.c - 1);
+    for (uint32_t j = 0; j < a.nwin; ++j) {
+        uint32_t d = msm_window_bits(s, j * a.c, a.c) + carry;
+        uint32_t sign = 0;
+        if (d > half) { d = (1u << a.c) - d; sign = 1; carry = 1; } else carry = 0;
+        const uint32_t key = d == 0 ? 0xffffffffu : (a.pre ? d - 1 : j * half + d - 1);
+        const uint32_t entry = ((a.pre ? j * a.pre_stride + i : i) << 1) | sign;
+        const uint32_t k0 = __shfl_sync(FULL, key, 0);
+        if (__all_sync(FULL, key == k0)) {
+            if (k0 == 0xffffffffu) continue;
+            if (SCATTER) {
+                uint32_t pos = 0;
+                if (lane == 0) pos = atomicAdd(&a.cursor[k0], 32u);
+                pos = __shfl_sync(FULL, pos, 0);
+                a.entries[pos + lane] = entry;
+            } else if (lane == 0) {
+                atomicAdd(&a.counts[k0], 32u);
+            }
+        } else if (key != 0xffffffffu) {
+            if (SCATTER) a.entries[atomicAdd(&a.cursor[key], 1u)] = entry;
+            else atomicAdd(&a.counts[key], 1u);
+        }
+    }
+}
 __global__ void __launch_bounds__(MSM_DIGIT_THREADS) msm_count_kernel(const MsmArgs a) {
-    msm_count_thread(a, blockIdx.x * blockDim.x + threadIdx.x);
+    msm_digit_pass_warp<false>(a, blockIdx.x * blockDim.x + threadIdx.x);
 }
 __global__ void __launch_bounds__(MSM_DIGIT_THREADS) msm_scatter_kernel(const MsmArgs a) {
-    msm_scatter_thread(a, blockIdx.x * blockDim.x + threadIdx.x);
+    msm_digit_pass_warp<true>(a, blockIdx.x * blockDim.x + threadIdx.x);
 }
 __global__ void __launch_bounds__(MSM_SCAN_THREADS) scan_blocksum_kernel(const ScanArgs s) {
     __shared__ uint32_t sm[2 * MSM_SCAN_THREADS];
@@ -157,25 +196,39 @@ int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bas
         msm_accumulate_kernel<<<nb(B, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
         ctx->launches++;
     } else {
-        // three balanced levels with segment length L ~ cbrt(largest bucket)
-        uint32_t L = (uint32_t)std::ceil(std::cbrt((double)maxcnt));
-        if (L < seg_min) L = seg_min;
-        if (L < 2) L = 2;
+        // Balanced levels of at most L items per task: entries -> partials (accumulate_task), then
+        // partials -> partials (combine_task) until no bucket has more than L of them, then one
+        // thread per bucket sums what is left.  A uniform 2^20 column takes two levels; the single
+        // bucket holding the ~2^20 ones of a grand-product column takes five, every one of them
+        // with >= maxcnt / L^level independent tasks (a cube-root split left 10^4 threads with
+        // 100-long serial chains: 2.85 ms for one such bucket).
+        uint32_t L = seg_min < 2 ? 2 : seg_min;
+        // level k has at most n*W / L^k + B * (1 + 1/L + ...) tasks: both ping-pong buffers hold n*W/L + 2B
         const size_t t1_bound = n * (size_t)s.nwin / L + B;
-        const size_t t2_bound = t1_bound / L + B;
-        ZK_TRY(ws_reserve(ctx, ctx->msm_ws2, (t1_bound + t2_bound) * sizeof(xyzz_t) + 512));
-        xyzz_t* partial1 = (xyzz_t*)ctx->msm_ws2.p;
-        xyzz_t* partial2 = partial1 + t1_bound;
-        uint32_t *toff1 = (uint32_t*)(base + o_toff1), *toff2 = (uint32_t*)(base + o_toff2);
-        run_scan(ctx, ScanArgs{a.counts, toff1, nullptr, bsums, nullptr, B, 0, L});
-        MsmTaskArgs t1{a.offsets, toff1, B, toff1 + B, L, nullptr, partial1};
+        const size_t pcap = t1_bound + B;
+        ZK_TRY(ws_reserve(ctx, ctx->msm_ws2, 2 * pcap * sizeof(xyzz_t) + (size_t)(B + 1) * 4 + 1024));
+        xyzz_t* pbuf[2] = {(xyzz_t*)ctx->msm_ws2.p, (xyzz_t*)ctx->msm_ws2.p + pcap};
+        uint32_t* toff[3] = {(uint32_t*)(base + o_toff1), (uint32_t*)(base + o_toff2), (uint32_t*)(pbuf[1] + pcap)};
+        run_scan(ctx, ScanArgs{a.counts, toff[0], nullptr, bsums, nullptr, B, 0, L});
+        MsmTaskArgs t1{a.offsets, toff[0], B, toff[0] + B, L, nullptr, pbuf[0]};
         msm_accumulate_task_kernel<<<nb(t1_bound, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a, t1);
-        run_scan(ctx, ScanArgs{toff1, toff2, nullptr, bsums, nullptr, B, 1, L});
-        MsmTaskArgs t2{toff1, toff2, B, toff2 + B, L, partial1, partial2};
-        msm_combine_task_kernel<<<nb(t2_bound, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(t2);
-        MsmTaskArgs t3{toff2, nullptr, B, nullptr, 0, partial2, a.buckets};
+        ctx->launches++;
+        uint32_t cur = 0, cur_t = 0;                            // partials in pbuf[cur], their offsets in toff[cur_t]
+        uint64_t m = ((uint64_t)maxcnt + L - 1) / L;            // most partials any bucket holds
+        size_t bound = t1_bound;
+        while (m > L) {
+            const uint32_t nxt_t = (cur_t + 1) % 3, nxt = cur ^ 1;
+            bound = bound / L + B;                              // <= pcap, see above
+            run_scan(ctx, ScanArgs{toff[cur_t], toff[nxt_t], nullptr, bsums, nullptr, B, 1, L});
+            MsmTaskArgs t2{toff[cur_t], toff[nxt_t], B, toff[nxt_t] + B, L, pbuf[cur], pbuf[nxt]};
+            msm_combine_task_kernel<<<nb(bound, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(t2);
+            ctx->launches++;
+            cur = nxt; cur_t = nxt_t;
+            m = (m + L - 1) / L;
+        }
+        MsmTaskArgs t3{toff[cur_t], nullptr, B, nullptr, 0, pbuf[cur], a.buckets};
         msm_combine_bucket_kernel<<<nb(B, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(t3);
-        ctx->launches += 3;
+        ctx->launches++;
     }
     size_t nred = (size_t)nsums << s.log_t;
     if (pre) msm_reduce_bits_kernel<<<nb(nred, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);

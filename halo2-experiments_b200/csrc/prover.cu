@@ -9,6 +9,7 @@
 #include "prover_kernels.cuh"
 #include "transcript.hpp"
 #include <algorithm>
+#include <array>
 #include <map>
 #include <new>
 #include <set>
@@ -343,6 +344,86 @@ static ExprArgs expr_args(const b200zk_pk* pk, uint32_t prog_off, uint32_t prog_
     for (int i = 0; i < 4; ++i) a.factors[i] = to_dev(ch[i]);
     a.mode = mode; a.out0 = out0; a.out1 = out1;
     return a;
+}
+
+// ------------------------------------------------------------------ common sub-expressions
+// One evaluator program = a list of expressions (postfix ranges of cs.prog), each followed by a
+// FOLD word.  The trees are hash-consed (ADD / MUL operands unordered); a node that the emission
+// reaches more than once and that contains at least one multiplication is computed once and kept
+// in a TEE/TMP slot (expr.cuh).  When more than EX_TMPS nodes qualify, those saving the most
+// multiplications win.
+struct ExFold { uint32_t off, len, fold_word; };
+
+static bool ex_share_common(const std::vector<uint32_t>& src, const std::vector<ExFold>& items, std::vector<uint32_t>& out) {
+    struct Node { uint32_t op, arg; int l, r; uint32_t muls; };
+    std::vector<Node> nodes;
+    std::map<std::array<int64_t, 4>, int> intern;
+    auto make = [&](uint32_t op, uint32_t arg, int l, int r) {
+        int a = l, b = r;
+        if ((op == EX_ADD || op == EX_MUL) && a > b) std::swap(a, b);
+        std::array<int64_t, 4> key{(int64_t)op, (int64_t)arg, a, b};
+        auto it = intern.find(key);
+        if (it != intern.end()) return it->second;
+        uint32_t muls = (op == EX_MUL || op == EX_SCALE ? 1u : 0u) + (l >= 0 ? nodes[l].muls : 0u) + (r >= 0 ? nodes[r].muls : 0u);
+        nodes.push_back({op, arg, l, r, muls});
+        intern[key] = (int)nodes.size() - 1;
+        return (int)nodes.size() - 1;
+    };
+    std::vector<int> roots;
+    for (auto& it : items) {
+        std::vector<int> st;
+        for (uint32_t i = it.off; i < it.off + it.len; ++i) {
+            uint32_t op = src[i] & 0xff, arg = src[i] >> 8;
+            if (op <= EX_INSTANCE) st.push_back(make(op, arg, -1, -1));
+            else if (op == EX_NEG || op == EX_SCALE) { if (st.empty()) return false; st.back() = make(op, arg, st.back(), -1); }
+            else if (op == EX_ADD || op == EX_MUL) {
+                if (st.size() < 2) return false;
+                int r = st.back(); st.pop_back();
+                st.back() = make(op, 0, st.back(), r);
+            } else return false;
+        }
+        if (st.size() != 1) return false;
+        roots.push_back(st[0]);
+    }
+    // how often the emission asks for each node when shared nodes are expanded once
+    std::vector<uint32_t> req(nodes.size(), 0);
+    std::vector<int> work;
+    for (int root : roots) {
+        work.push_back(root);
+        while (!work.empty()) {
+            int id = work.back(); work.pop_back();
+            if (++req[id] == 1) { if (nodes[id].l >= 0) work.push_back(nodes[id].l); if (nodes[id].r >= 0) work.push_back(nodes[id].r); }
+        }
+    }
+    std::vector<int> cand;
+    for (size_t id = 0; id < nodes.size(); ++id) if (req[id] >= 2 && nodes[id].muls >= 1) cand.push_back((int)id);
+    std::sort(cand.begin(), cand.end(), [&](int a, int b) {
+        uint64_t sa = (uint64_t)(req[a] - 1) * nodes[a].muls, sb = (uint64_t)(req[b] - 1) * nodes[b].muls;
+        return sa != sb ? sa > sb : a < b;
+    });
+    if (cand.size() > (size_t)EX_TMPS) cand.resize(EX_TMPS);
+    std::vector<int> slot(nodes.size(), -1);
+    for (size_t i = 0; i < cand.size(); ++i) slot[cand[i]] = (int)i;
+    std::vector<char> done(nodes.size(), 0);
+    // iterative postfix emission: (node, phase)
+    for (size_t k = 0; k < roots.size(); ++k) {
+        std::vector<std::pair<int, int>> stk{{roots[k], 0}};
+        while (!stk.empty()) {
+            auto [id, phase] = stk.back(); stk.pop_back();
+            const Node& nd = nodes[id];
+            if (phase == 0) {
+                if (slot[id] >= 0 && done[id]) { out.push_back(EX_TMP | ((uint32_t)slot[id] << 8)); continue; }
+                stk.push_back({id, 1});
+                if (nd.r >= 0) stk.push_back({nd.r, 0});
+                if (nd.l >= 0) stk.push_back({nd.l, 0});
+            } else {
+                out.push_back(nd.op | (nd.arg << 8));
+                if (slot[id] >= 0) { out.push_back(EX_TEE | ((uint32_t)slot[id] << 8)); done[id] = 1; }
+            }
+        }
+        out.push_back(items[k].fold_word);
+    }
+    return true;
 }
 
 // ------------------------------------------------------------------ create_proof
@@ -948,22 +1029,25 @@ int32_t b200zk_pk_create(b200zk_params* params, const uint32_t* cs_blob, size_t 
     // programs: gates with FOLD(acc0, y); lookups with FOLD(acc0/acc1, theta)
     {
         std::vector<uint32_t> prog;
-        for (auto& g : cs.gates) {
-            prog.insert(prog.end(), cs.prog.begin() + g.first, cs.prog.begin() + g.first + g.second);
-            prog.push_back(EX_FOLD | ((0u << 4 | EXF_Y) << 8));
+        {
+            std::vector<ExFold> items;
+            for (auto& g : cs.gates) items.push_back({g.first, g.second, EX_FOLD | ((0u << 4 | EXF_Y) << 8)});
+            if (!ex_share_common(cs.prog, items, prog)) return bail(fail(ctx, B200ZK_EINVAL, "pk_create", "malformed expression program"));
         }
         pk->gates_len = (uint32_t)prog.size();
         for (auto& lk : cs.lookups) {
             uint32_t off = (uint32_t)prog.size();
-            for (auto& e : lk.ins) { prog.insert(prog.end(), cs.prog.begin() + e.first, cs.prog.begin() + e.first + e.second); prog.push_back(EX_FOLD | ((0u << 4 | EXF_THETA) << 8)); }
-            for (auto& e : lk.tabs) { prog.insert(prog.end(), cs.prog.begin() + e.first, cs.prog.begin() + e.first + e.second); prog.push_back(EX_FOLD | ((1u << 4 | EXF_THETA) << 8)); }
+            std::vector<ExFold> items;
+            for (auto& e : lk.ins) items.push_back({e.first, e.second, EX_FOLD | ((0u << 4 | EXF_THETA) << 8)});
+            for (auto& e : lk.tabs) items.push_back({e.first, e.second, EX_FOLD | ((1u << 4 | EXF_THETA) << 8)});
+            if (!ex_share_common(cs.prog, items, prog)) return bail(fail(ctx, B200ZK_EINVAL, "pk_create", "malformed expression program"));
             pk->lookup_prog.push_back({off, (uint32_t)prog.size() - off});
         }
         // stack depth check
         int depth = 0, maxd = 0;
         for (uint32_t w : prog) {
             uint32_t op = w & 0xff;
-            if (op <= EX_INSTANCE) ++depth; else if (op == EX_ADD || op == EX_MUL || op == EX_FOLD) --depth;
+            if (op <= EX_INSTANCE || op == EX_TMP) ++depth; else if (op == EX_ADD || op == EX_MUL || op == EX_FOLD) --depth;
             maxd = std::max(maxd, depth);
             if (depth < 0) return bail(fail(ctx, B200ZK_EINVAL, "pk_create", "malformed expression program"));
         }

@@ -213,7 +213,7 @@ def test_params_setup_large_consistency(zk, backend, orc):
     d.close(); params.close()
 
 
-@pytest.mark.parametrize("kind", ["bits", "bytes", "u40", "one-bucket", "mixed"])
+@pytest.mark.parametrize("kind", ["bits", "bytes", "u40", "one-bucket", "mixed", "z-like", "sorted-runs"])
 def test_best_multiexp_skewed_columns(backend, orc, kind):
     """Witness-like columns (bits, bytes, small integers) put thousands of points in a few buckets:
     exercises the task-balanced accumulation path."""
@@ -229,14 +229,28 @@ def test_best_multiexp_skewed_columns(backend, orc, kind):
         vals = rng.integers(0, 1 << 40, size=n)
     elif kind == "one-bucket":
         vals = np.full(n, 3)
+    elif kind == "z-like":                               # grand product of a padded circuit: 1 on the unused rows
+        vals = np.ones(n, dtype=np.int64)
+    elif kind == "sorted-runs":                          # permuted lookup column: sorted bytes in long runs
+        vals = np.sort(rng.integers(0, 256, size=n))
     else:
         vals = np.where(rng.integers(0, 4, size=n) == 0, rng.integers(0, 1 << 62, size=n), rng.integers(0, 2, size=n))
     lut_keys, inv = np.unique(vals, return_inverse=True)
     S = orc.ints_to_mont([int(v) for v in lut_keys])[inv]
     if kind == "mixed":
         S[: n // 8] = orc.random_fr(n // 8, 3)           # a dense stretch on top
+    if kind == "z-like":
+        S[:700] = orc.random_fr(700, 5)                  # the active rows
+        S[n - 6:] = orc.random_fr(6, 6)                  # blinding rows
     got = backend.best_multiexp(S, g)
-    assert np.array_equal(_affine(got), orc.g1_batch_normalize(orc.best_multiexp(S, g))[0])
+    want = orc.g1_batch_normalize(orc.best_multiexp(S, g))[0]
+    assert np.array_equal(_affine(got), want)
+    if kind in ("z-like", "sorted-runs", "one-bucket"):  # same column through the fixed-base (SRS commit) path
+        import importlib
+        zk = importlib.import_module(type(backend).__module__)
+        params = zk.ParamsKZG.load(backend, k, g, None)
+        assert np.array_equal(_affine(params.commit(S)), want)
+        params.close()
 
 
 @pytest.mark.parametrize("log_n,log_r,world", [(10, 4, 2), (12, 6, 4), (16, 8, 8), (20, 10, 8)])
