@@ -23,7 +23,7 @@ for `b200zk_pk_create` / `b200zk_create_proof`:
                       constraints and instance cells — what the reference's negative tests assert
                       (/root/reference/src/circuits/merkle_sum_tree.rs:229-343).
 
-Host-side Python integers only; no GPU and no oracle involved.
+Host-side Python integers only; nothing here runs on the GPU or imports test infrastructure.
 """
 import numpy as np
 
