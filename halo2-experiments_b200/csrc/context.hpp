@@ -22,6 +22,7 @@ struct NttPlan {
     fe_t* tw_lo = nullptr;
     fe_t* tw_hi = nullptr;
     fe_t* tw_full = nullptr;    // omega^E for all E < N (multi-pass plans up to 2^24)
+    bool warp = false;          // passes run on ntt_warp_pass_kernel (ntt_warp.cuh)
 };
 
 struct Workspace {

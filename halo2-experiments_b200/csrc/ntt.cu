@@ -1,6 +1,7 @@
 // Launch side of the NTT (see ntt.cuh for the algorithm and the reference mapping).
 #include "context.hpp"
 #include "ntt.cuh"
+#include "ntt_warp.cuh"
 
 namespace b200zk {
 
@@ -12,6 +13,18 @@ static constexpr uint32_t NTT_TILE_CAP_LOG = 12;   // 4096 elements = 128 KiB of
 __global__ void __launch_bounds__(NTT_THREADS, 1) ntt_pass_kernel(const NttPassArgs a) {
     extern __shared__ half_t ntt_sm[];
     ntt_pass_block(a, blockIdx.x, blockDim.x, ntt_sm);
+}
+
+// one warp per 256-element tile; 8 KB of warp-private shared memory each
+__global__ void __launch_bounds__(32 * NTT_WARPS_PER_BLOCK, 4) ntt_warp_pass_kernel(const NttPassArgs a, uint32_t ntiles) {
+    __shared__ half_t sm[NTT_WARPS_PER_BLOCK][512];
+    const uint32_t w = threadIdx.x >> 5, wid = blockIdx.x * NTT_WARPS_PER_BLOCK + w;
+    if (wid < ntiles) ntt_pass_warp(a, wid, threadIdx.x & 31, sm[w]);
+}
+__global__ void __launch_bounds__(32 * NTT_WARPS_PER_BLOCK, 3) ntt_warp_pass_kernel_occ3(const NttPassArgs a, uint32_t ntiles) {
+    __shared__ half_t sm[NTT_WARPS_PER_BLOCK][512];
+    const uint32_t w = threadIdx.x >> 5, wid = blockIdx.x * NTT_WARPS_PER_BLOCK + w;
+    if (wid < ntiles) ntt_pass_warp(a, wid, threadIdx.x & 31, sm[w]);
 }
 
 __global__ void ntt_pow_table_kernel(fe_t* out, const fe_t base, uint32_t count, uint32_t shift) {
@@ -42,8 +55,10 @@ static int32_t build_plan(b200zk_ctx* ctx, uint32_t log_n, const host::HFr& omeg
         long v = strtol(e, nullptr, 10);
         return (v < (long)lo || v > (long)hi) ? dflt : (uint32_t)v;
     };
-    plan.shape = ntt_plan_shape(log_n, tune("B200ZK_NTT_MAX_M", NTT_MAX_LOG_M, 2, 12),
-                                tune("B200ZK_NTT_MAX_TW", NTT_MAX_LOG_TW, 0, 5), tune("B200ZK_NTT_TILE_CAP", NTT_TILE_CAP_LOG, 6, 12));
+    plan.warp = ntt_warp_eligible(log_n, tune("B200ZK_NTT_WARP_MAX", 21, 0, 24));
+    plan.shape = plan.warp ? ntt_plan_shape_warp(log_n)
+                           : ntt_plan_shape(log_n, tune("B200ZK_NTT_MAX_M", NTT_MAX_LOG_M, 2, 12),
+                                            tune("B200ZK_NTT_MAX_TW", NTT_MAX_LOG_TW, 0, 5), tune("B200ZK_NTT_TILE_CAP", NTT_TILE_CAP_LOG, 6, 12));
     const NttShape& s = plan.shape;
     size_t n_roots = (size_t)1 << (s.log_roots ? s.log_roots - 1 : 0);
     size_t n_lo = (size_t)1 << s.tw_lo_bits, n_hi = ((size_t)1 << log_n) >> s.tw_lo_bits;
@@ -133,7 +148,14 @@ static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, f
         size_t smem = sizeof(fe_t) << (q.log_m + q.log_tw);
         uint32_t tile = 1u << (q.log_m + q.log_tw);
         uint32_t threads = tile / 2 < NTT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : NTT_THREADS;
-        ntt_pass_kernel<<<q.blocks * batch, threads, smem, ctx->stream>>>(a);
+        if (plan.warp) {
+            const uint32_t ntiles = q.blocks * batch;
+            static const bool occ3 = getenv("B200ZK_NTT_WARP_OCC3") != nullptr;
+            if (occ3) ntt_warp_pass_kernel_occ3<<<(ntiles + NTT_WARPS_PER_BLOCK - 1) / NTT_WARPS_PER_BLOCK, 32 * NTT_WARPS_PER_BLOCK, 0, ctx->stream>>>(a, ntiles);
+            else ntt_warp_pass_kernel<<<(ntiles + NTT_WARPS_PER_BLOCK - 1) / NTT_WARPS_PER_BLOCK, 32 * NTT_WARPS_PER_BLOCK, 0, ctx->stream>>>(a, ntiles);
+        } else {
+            ntt_pass_kernel<<<q.blocks * batch, threads, smem, ctx->stream>>>(a);
+        }
         ctx->launches++;
     }
     ZK_CUDA(ctx, cudaGetLastError());
