@@ -96,7 +96,7 @@ int32_t ws_reserve(b200zk_ctx* ctx, Workspace& w, size_t bytes);
 // read as zero).  pre/post: three host Fr multipliers indexed by position mod 3, or null.
 // d_out may alias d_in.
 int32_t ntt_run(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, uint32_t log_n,
-                const host::HFr& omega, const host::HFr* pre, const host::HFr* post);
+                const host::HFr& omega, const host::HFr* pre, const host::HFr* post, const fe_t* d_pre_tab = nullptr);
 // four-step sharded NTT building blocks (ntt.cu)
 int32_t ntt_colstep_run(b200zk_ctx* ctx, fe_t* d_block, uint32_t log_r, uint32_t log_cg, uint32_t col0,
                         const host::HFr& omega_n, uint32_t log_n);

@@ -44,8 +44,9 @@ struct ExprArgs {
     const int32_t* q_fixed;             // (column, rotation) pairs
     const int32_t* q_advice;
     const int32_t* q_instance;
-    uint32_t log_size;                  // rows = 2^log_size
-    uint32_t rot_scale;                 // 1 on the Lagrange domain, 2^(extended_k - k) on the extended one
+    uint32_t log_size;                  // rotations wrap inside blocks of 2^log_size rows (= n: one coset / the Lagrange domain)
+    uint32_t rows;                      // rows evaluated: n, or C * n on the quotient cosets
+    uint32_t rot_scale;                 // 1
     fe_t factors[4];                    // theta, beta, gamma, y
     uint32_t mode;
     fe_t* out0;
@@ -55,7 +56,7 @@ struct ExprArgs {
 ZK_D fe_t expr_load(const fe_t* const* cols, const int32_t* q, uint32_t qi, uint32_t idx, const ExprArgs& a) {
     int32_t col = q[2 * qi], rot = q[2 * qi + 1];
     uint32_t mask = (1u << a.log_size) - 1;
-    uint32_t r = (idx + (uint32_t)(rot * (int32_t)a.rot_scale)) & mask;      // rem_euclid for a power-of-two size
+    uint32_t r = (idx & ~mask) | ((idx + (uint32_t)(rot * (int32_t)a.rot_scale)) & mask);   // rem_euclid inside the coset
     return cols[col][r];
 }
 

@@ -91,20 +91,22 @@ static int32_t build_plan(b200zk_ctx* ctx, uint32_t log_n, const host::HFr& omeg
 }
 
 static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, uint32_t log_n,
-                             const host::HFr& omega, const host::HFr* pre, const host::HFr* post, uint32_t batch);
+                             const host::HFr& omega, const host::HFr* pre, const host::HFr* post, uint32_t batch,
+                             const fe_t* d_pre_tab = nullptr);
 
 int32_t ntt_run(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, uint32_t log_n,
-                const host::HFr& omega, const host::HFr* pre, const host::HFr* post) {
-    return ntt_run_batch(ctx, d_in, n_in, d_out, log_n, omega, pre, post, 1);
+                const host::HFr& omega, const host::HFr* pre, const host::HFr* post, const fe_t* d_pre_tab) {
+    return ntt_run_batch(ctx, d_in, n_in, d_out, log_n, omega, pre, post, 1, d_pre_tab);
 }
 
 // `batch` independent transforms of size 2^log_n on contiguous arrays (batch > 1: no pre/post hooks,
 // n_in = 2^log_n): every pass is one launch over all of them.
 static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, uint32_t log_n,
-                             const host::HFr& omega, const host::HFr* pre, const host::HFr* post, uint32_t batch) {
+                             const host::HFr& omega, const host::HFr* pre, const host::HFr* post, uint32_t batch,
+                             const fe_t* d_pre_tab) {
     if (log_n > 3 * NTT_MAX_LOG_M) return fail(ctx, B200ZK_EINVAL, "ntt_run", "log_n too large");
     if (batch == 0) return B200ZK_OK;
-    if (batch > 1 && (pre || post || ((uint64_t)batch << log_n) > 0xFFFFFFFFull)) return fail(ctx, B200ZK_EINVAL, "ntt_run", "bad batch");
+    if (batch > 1 && (pre || post || d_pre_tab || ((uint64_t)batch << log_n) > 0xFFFFFFFFull)) return fail(ctx, B200ZK_EINVAL, "ntt_run", "bad batch");
     std::array<uint64_t, 5> key = {log_n, omega.v[0], omega.v[1], omega.v[2], omega.v[3]};
     auto it = ctx->ntt_plans.find(key);
     if (it == ctx->ntt_plans.end()) {
@@ -136,6 +138,7 @@ static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, f
         a.n_in = batch > 1 ? (uint32_t)(N * batch) : (p == 0 ? n_in : (uint32_t)N);
         a.batch_tiles = (batch > 1 && q.is_last) ? q.blocks : 0;
         a.use_pre = (p == 0 && pre) ? 1 : 0;
+        a.pre_tab = p == 0 ? d_pre_tab : nullptr;
         a.use_post = (q.is_last && post) ? 1 : 0;
         for (int i = 0; i < 3; ++i) {
             if (pre) a.pre[i] = to_dev(pre[i]);

@@ -39,6 +39,7 @@ struct NttPassArgs {
     uint32_t n_in;          // first pass: elements beyond n_in read as zero (n_in = N otherwise)
     uint32_t use_pre, use_post;
     fe_t pre[3], post[3];   // multiplied by index mod 3 on load (first pass) / store (last pass)
+    const fe_t* pre_tab;    // optional, first pass: element g is multiplied by pre_tab[g] on load (coset powers)
     const fe_t* roots;      // w_R^j, j < R/2, R = 2^log_roots >= M  (w_R = omega^(N/R))
     uint32_t log_roots;
     const fe_t* tw_lo;      // omega^i,            i < 2^tw_lo_bits
@@ -117,6 +118,7 @@ ZK_D void ntt_pass_block(const NttPassArgs& a, uint32_t bid, uint32_t nthreads, 
         if (g < a.n_in) {
             v = a.in[g];
             if (a.use_pre) { uint32_t r3 = (uint32_t)(g % 3); if (r3) v = Fr::mul(v, a.pre[r3]); }
+            if (a.pre_tab) v = Fr::mul(v, a.pre_tab[g]);
         } else {
             v = Fr::zero();
         }

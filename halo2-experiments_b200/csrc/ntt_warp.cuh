@@ -91,6 +91,7 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
         if (g < a.n_in) {
             x[e] = a.in[g];
             if (a.use_pre) { uint32_t r3 = (uint32_t)(g % 3); if (r3) x[e] = Fr::mul(x[e], a.pre[r3]); }
+            if (a.pre_tab) x[e] = Fr::mul(x[e], a.pre_tab[g]);
         } else {
             x[e] = Fr::zero();
         }

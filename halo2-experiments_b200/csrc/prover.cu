@@ -28,7 +28,7 @@ static fe_t to_dev(const HFr& x) { fe_t r; memcpy(r.l, x.v, 32); return r; }
 // ------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(PK_THREADS) expr_kernel(const ExprArgs a) {
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < (1u << a.log_size)) expr_eval_row(a, idx);
+    if (idx < a.rows) expr_eval_row(a, idx);
 }
 __global__ void __launch_bounds__(PK_THREADS) from_u512_kernel(const uint32_t* wide, fe_t* out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -52,15 +52,19 @@ __global__ void __launch_bounds__(PK_THREADS) lookup_num_kernel(const LookupProd
 }
 __global__ void __launch_bounds__(PK_THREADS) quot_perm_a_kernel(const QuotPermAArgs a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < (1u << a.log_ext)) quot_perm_a_row(a, i);
+    if (i < a.rows) quot_perm_a_row(a, i);
 }
 __global__ void __launch_bounds__(PK_THREADS) quot_perm_b_kernel(const QuotPermBArgs a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < (1u << a.log_ext)) quot_perm_b_row(a, i);
+    if (i < a.rows) quot_perm_b_row(a, i);
 }
 __global__ void __launch_bounds__(PK_THREADS) quot_lookup_kernel(const QuotLookupArgs a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < (1u << a.log_ext)) quot_lookup_row(a, i);
+    if (i < a.rows) quot_lookup_row(a, i);
+}
+__global__ void __launch_bounds__(PK_THREADS) coset_interpolate_kernel(const fe_t* g, const fe_t* inv_pow, const fe_t* vinv, uint32_t C, size_t n, fe_t* out) {
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) coset_interpolate_row(g, inv_pow, vinv, C, n, out, r);
 }
 __global__ void __launch_bounds__(PK_THREADS) fold_pieces_kernel(const fe_t* pieces, uint32_t npieces, size_t n, const fe_t xn, fe_t* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -192,8 +196,11 @@ struct b200zk_pk {
     fe_t *fixed_values = nullptr, *fixed_polys = nullptr, *fixed_cosets = nullptr;
     fe_t *perm_values = nullptr, *perm_polys = nullptr, *perm_cosets = nullptr;
     fe_t *l0 = nullptr, *l_last = nullptr, *l_active = nullptr;
-    fe_t *omega_pows = nullptr, *ew_lo = nullptr, *ew_hi = nullptr;
-    uint32_t ew_bits = 0;
+    fe_t* omega_pows = nullptr;
+    // quotient cosets c_j = zeta * extended_omega^j, j < q (see prover_kernels.cuh): ext_n = q * n
+    fe_t *coset_pow = nullptr, *coset_pow_inv = nullptr;      // c_j^r and c_j^-r, [q][n]
+    fe_t *coset_fac = nullptr, *vinv = nullptr;               // extended_omega^j [q]; inverse Vandermonde of c_j^n [q*q]
+    std::vector<HFr> coset_t;                                  // 1 / (c_j^n - 1): the vanishing polynomial on coset j
     // device program data
     uint32_t* d_prog = nullptr;                       // gates program | lookup programs
     uint32_t gates_len = 0;
@@ -321,10 +328,13 @@ static int32_t lagrange_to_coeff(b200zk_pk* pk, fe_t* d_a) {
     HFr post[3] = {pk->dom->ifft_divisor, pk->dom->ifft_divisor, pk->dom->ifft_divisor};
     return ntt_run(pk->ctx, d_a, pk->n, d_a, pk->dom->k, pk->dom->omega_inv, nullptr, post);
 }
+// coeff_to_extended restricted to the q cosets the quotient needs: coset j = size-n NTT of a_r * c_j^r
 static int32_t coeff_to_extended(b200zk_pk* pk, const fe_t* d_coeffs, fe_t* d_out) {
     PhaseTimer t(pk, PH_NTT);
-    HFr pre[3] = {HFr::one(), pk->dom->g_coset, pk->dom->g_coset_inv};
-    return ntt_run(pk->ctx, d_coeffs, pk->n, d_out, pk->dom->extended_k, pk->dom->extended_omega, pre, nullptr);
+    const size_t n = pk->n;
+    for (uint32_t j = 0; j < pk->q; ++j)
+        ZK_TRY(ntt_run(pk->ctx, d_coeffs, pk->n, d_out + j * n, pk->dom->k, pk->dom->omega, nullptr, nullptr, pk->coset_pow + j * n));
+    return B200ZK_OK;
 }
 static int32_t eval_dev(b200zk_pk* pk, const fe_t* d_poly, size_t len, const HFr& x, HFr* out) {
     return recurrence_run(pk->ctx, d_poly, nullptr, len, x, out);
@@ -339,8 +349,9 @@ static ExprArgs expr_args(const b200zk_pk* pk, uint32_t prog_off, uint32_t prog_
     a.advice = pk->d_ptrs + (extended ? pt.advice_cosets() : pt.advice_values());
     a.instance = pk->d_ptrs + (extended ? pt.inst_cosets() : pt.inst_values());
     a.q_fixed = pk->d_q_fix; a.q_advice = pk->d_q_adv; a.q_instance = pk->d_q_inst;
-    a.log_size = extended ? pk->dom->extended_k : pk->dom->k;
-    a.rot_scale = extended ? (1u << (pk->dom->extended_k - pk->dom->k)) : 1u;
+    a.log_size = pk->dom->k;
+    a.rows = extended ? pk->ext_n : pk->n;
+    a.rot_scale = 1u;
     for (int i = 0; i < 4; ++i) a.factors[i] = to_dev(ch[i]);
     a.mode = mode; a.out0 = out0; a.out1 = out1;
     return a;
@@ -437,7 +448,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     const size_t n = pk->n, ext = pk->ext_n;
     const uint32_t A = cs.A, I = cs.I, F = cs.F, L = pk->L, S = pk->S, bf = cs.bf;
     const size_t usable = n - (bf + 1);
-    const uint32_t rot_scale = 1u << (dom->extended_k - dom->k);
+    const uint32_t rot_scale = 1u;                               // rotations stay inside a coset (prover_kernels.cuh)
     for (float& f : pk->phase_ms) f = 0;
     pk->timer_used = 0;
     ZK_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -649,7 +660,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         if (S) {
             QuotPermAArgs qa{};
             qa.h = h; qa.y = to_dev(y); qa.l0 = pk->l0; qa.l_last = pk->l_last; qa.nsets = S;
-            qa.log_ext = dom->extended_k; qa.rot_scale = rot_scale; qa.last_rot = -(int32_t)(bf + 1);
+            qa.rows = (uint32_t)ext; qa.log_ext = dom->k; qa.rot_scale = rot_scale; qa.last_rot = -(int32_t)(bf + 1);
             for (uint32_t s = 0; s < S; ++s) qa.z[s] = perm_cosets + (size_t)s * ext;
             quot_perm_a_kernel<<<nb(ext), PK_THREADS, 0, st>>>(qa);
             ctx->launches++;
@@ -658,8 +669,8 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
                 uint32_t c0 = s * pk->chunk, c1 = std::min<uint32_t>(c0 + pk->chunk, pk->P);
                 QuotPermBArgs qb{};
                 qb.h = h; qb.y = to_dev(y); qb.beta = to_dev(beta); qb.gamma = to_dev(gamma); qb.l_active = pk->l_active;
-                qb.z = perm_cosets + (size_t)s * ext; qb.ncols = c1 - c0; qb.log_ext = dom->extended_k; qb.rot_scale = rot_scale;
-                qb.ew_lo = pk->ew_lo; qb.ew_hi = pk->ew_hi; qb.ew_bits = pk->ew_bits;
+                qb.z = perm_cosets + (size_t)s * ext; qb.ncols = c1 - c0; qb.rows = (uint32_t)ext; qb.log_ext = dom->k; qb.rot_scale = rot_scale;
+                qb.omega_pows = pk->omega_pows; qb.coset_fac = pk->coset_fac;
                 for (uint32_t j = c0; j < c1; ++j) {
                     qb.values[j - c0] = column_cosets(cs.perm[j].first, cs.perm[j].second);
                     qb.sigma[j - c0] = pk->perm_cosets + (size_t)j * ext;
@@ -679,7 +690,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         PhaseTimer t(pk, PH_QUOT);
         ExprArgs ea = expr_args(pk, pk->lookup_prog[l].first, pk->lookup_prog[l].second, true, EXM_LOOKUP_PROD, ch, tv, nullptr);
         expr_kernel<<<nb(ext), PK_THREADS, 0, st>>>(ea);
-        QuotLookupArgs ql{h, to_dev(y), to_dev(beta), to_dev(gamma), pk->l0, pk->l_last, pk->l_active, zc, ac, sc, tv, dom->extended_k, rot_scale};
+        QuotLookupArgs ql{h, to_dev(y), to_dev(beta), to_dev(gamma), pk->l0, pk->l_last, pk->l_active, zc, ac, sc, tv, dom->k, rot_scale, (uint32_t)ext};
         quot_lookup_kernel<<<nb(ext), PK_THREADS, 0, st>>>(ql);
         ctx->launches += 2;
     }
@@ -687,11 +698,18 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
 
     // ---- step 12: vanishing construct
     {
+        // divide by the vanishing polynomial (constant c_j^n - 1 on coset j), per-coset iNTT, then
+        // the q x q interpolation across cosets gives the coefficients of h piece by piece
         PhaseTimer t(pk, PH_NTT);
-        ZK_TRY(fr_scale_periodic(ctx, h, ext, dom->d_t_evaluations, rot_scale));
-        HFr dv = dom->extended_ifft_divisor;
-        HFr post[3] = {dv, dv * dom->g_coset_inv, dv * dom->g_coset};
-        ZK_TRY(ntt_run(ctx, h, (uint32_t)ext, h, dom->extended_k, dom->extended_omega_inv, nullptr, post));
+        for (uint32_t j = 0; j < pk->q; ++j) {
+            HFr f = dom->ifft_divisor * pk->coset_t[j];
+            HFr post[3] = {f, f, f};
+            ZK_TRY(ntt_run(ctx, h + j * n, (uint32_t)n, h + j * n, dom->k, dom->omega_inv, nullptr, post));
+        }
+        coset_interpolate_kernel<<<nb(n), PK_THREADS, 0, st>>>(h, pk->coset_pow_inv, pk->vinv, pk->q, n, lk_cosets);
+        ctx->launches++;
+        ZK_CUDA(ctx, cudaGetLastError());
+        h = lk_cosets;                                            // q pieces of n coefficients
     }
     const uint32_t q = pk->q;
     rng_take(q);                                                  // h_blinds
@@ -958,12 +976,15 @@ int32_t b200zk_pk_create(b200zk_params* params, const uint32_t* cs_blob, size_t 
     int32_t rc = b200zk_domain_create(ctx, cs.degree, cs.k, &pk->dom);
     if (rc != B200ZK_OK) return bail(rc);
     const b200zk_domain* dom = pk->dom;
-    pk->n = 1u << cs.k; pk->ext_n = 1u << dom->extended_k;
+    pk->n = 1u << cs.k;
     pk->P = (uint32_t)cs.perm.size(); pk->L = (uint32_t)cs.lookups.size();
     pk->chunk = cs.degree - 2;
     pk->S = (pk->P + pk->chunk - 1) / pk->chunk;
     pk->q = dom->quotient_poly_degree;
-    if (pk->chunk > ZK_MAXC || pk->S > ZK_MAXC) return bail(fail(ctx, B200ZK_EINVAL, "pk_create", "permutation too wide for this build"));
+    pk->ext_n = pk->q * pk->n;                                    // q cosets of size n (prover_kernels.cuh)
+    if (pk->chunk > ZK_MAXC || pk->S > ZK_MAXC || pk->q > (uint32_t)ZK_MAXCOSETS || pk->q > (1u << (dom->extended_k - dom->k)) ||
+        (uint64_t)pk->q * pk->n > 0xFFFFFFFFull)
+        return bail(fail(ctx, B200ZK_EINVAL, "pk_create", "permutation too wide for this build"));
     if (pk->P && (!map_col || !map_row)) return bail(B200ZK_EINVAL);
     const size_t n = pk->n, ext = pk->ext_n;
     const uint32_t F = cs.F, P = pk->P;
@@ -975,6 +996,45 @@ int32_t b200zk_pk_create(b200zk_params* params, const uint32_t* cs_blob, size_t 
     PK_TRY(dev_alloc(pk, &pk->l0, ext)); PK_TRY(dev_alloc(pk, &pk->l_last, ext)); PK_TRY(dev_alloc(pk, &pk->l_active, ext));
     PK_TRY(dev_alloc(pk, &pk->omega_pows, n));
     PK_TRY(dev_alloc(pk, &pk->d_err, 1));
+    // quotient cosets: powers of c_j and 1/c_j, extended_omega^j, 1/(c_j^n - 1), inverse Vandermonde of c_j^n
+    {
+        const uint32_t C = pk->q;
+        PK_TRY(dev_alloc(pk, &pk->coset_pow, (size_t)C * n)); PK_TRY(dev_alloc(pk, &pk->coset_pow_inv, (size_t)C * n));
+        PK_TRY(dev_alloc(pk, &pk->coset_fac, C)); PK_TRY(dev_alloc(pk, &pk->vinv, (size_t)C * C));
+        std::vector<HFr> y(C);
+        std::vector<fe_t> fac(C);
+        HFr w = HFr::one();
+        for (uint32_t j = 0; j < C; ++j) {
+            HFr cj = dom->g_coset * w;
+            PK_TRY(powers_run(ctx, cj, n, pk->coset_pow + (size_t)j * n));
+            PK_TRY(powers_run(ctx, cj.inv(), n, pk->coset_pow_inv + (size_t)j * n));
+            y[j] = cj.pow_u64(n);
+            pk->coset_t.push_back((y[j] - HFr::one()).inv());
+            fac[j] = to_dev(w);
+            w = w * dom->extended_omega;
+        }
+        // V[j][t] = y_j^t; vinv = V^-1 by Gauss-Jordan (C <= 32; the y_j are distinct, so V is regular)
+        std::vector<std::vector<HFr>> m(C, std::vector<HFr>(2 * C, HFr::zero()));
+        for (uint32_t j = 0; j < C; ++j) { HFr p = HFr::one(); for (uint32_t t = 0; t < C; ++t) { m[j][t] = p; p = p * y[j]; } m[j][C + j] = HFr::one(); }
+        for (uint32_t c = 0; c < C; ++c) {
+            uint32_t piv = c;
+            while (piv < C && m[piv][c] == HFr::zero()) ++piv;
+            if (piv == C) return bail(fail(ctx, B200ZK_EINVAL, "pk_create", "internal: singular coset Vandermonde"));
+            std::swap(m[c], m[piv]);
+            HFr inv = m[c][c].inv();
+            for (auto& v : m[c]) v = v * inv;
+            for (uint32_t r = 0; r < C; ++r) {
+                if (r == c || m[r][c] == HFr::zero()) continue;
+                HFr f = m[r][c];
+                for (uint32_t k2 = 0; k2 < 2 * C; ++k2) m[r][k2] = m[r][k2] - f * m[c][k2];
+            }
+        }
+        std::vector<fe_t> vin((size_t)C * C);
+        for (uint32_t t = 0; t < C; ++t) for (uint32_t j = 0; j < C; ++j) vin[(size_t)t * C + j] = to_dev(m[t][C + j]);
+        PK_CUDA(cudaMemcpyAsync(pk->coset_fac, fac.data(), C * sizeof(fe_t), cudaMemcpyHostToDevice, st));
+        PK_CUDA(cudaMemcpyAsync(pk->vinv, vin.data(), vin.size() * sizeof(fe_t), cudaMemcpyHostToDevice, st));
+        PK_CUDA(cudaStreamSynchronize(st));
+    }
     // fixed columns
     for (uint32_t c = 0; c < F; ++c) PK_CUDA(cudaMemcpyAsync(pk->fixed_values + (size_t)c * n, fixed_columns[c], n * sizeof(fe_t), cudaMemcpyHostToDevice, st));
     PK_CUDA(cudaMemcpyAsync(pk->fixed_polys, pk->fixed_values, F * n * sizeof(fe_t), cudaMemcpyDeviceToDevice, st));
@@ -982,15 +1042,7 @@ int32_t b200zk_pk_create(b200zk_params* params, const uint32_t* cs_blob, size_t 
         PK_TRY(lagrange_to_coeff(pk, pk->fixed_polys + (size_t)c * n));
         PK_TRY(coeff_to_extended(pk, pk->fixed_polys + (size_t)c * n, pk->fixed_cosets + (size_t)c * ext));
     }
-    // omega powers, extended-omega two-level table
     PK_TRY(powers_run(ctx, dom->omega, n, pk->omega_pows));
-    pk->ew_bits = (dom->extended_k + 1) / 2;
-    {
-        size_t n_lo = (size_t)1 << pk->ew_bits, n_hi = ext >> pk->ew_bits ? ext >> pk->ew_bits : 1;
-        PK_TRY(dev_alloc(pk, &pk->ew_lo, n_lo)); PK_TRY(dev_alloc(pk, &pk->ew_hi, n_hi));
-        PK_TRY(powers_run(ctx, dom->extended_omega, n_lo, pk->ew_lo));
-        PK_TRY(powers_run(ctx, dom->extended_omega.pow_u64(n_lo), n_hi, pk->ew_hi));
-    }
     // permutation polynomials: sigma_c[r] = delta^map_col * omega^map_row
     if (P) {
         uint32_t *d_mc = nullptr, *d_mr = nullptr; fe_t* d_dp = nullptr;

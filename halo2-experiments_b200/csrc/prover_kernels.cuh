@@ -14,6 +14,14 @@
 namespace b200zk {
 
 static constexpr int ZK_MAXC = 16;      // columns per permutation set (d - 2) / number of sets handled per launch
+static constexpr int ZK_MAXCOSETS = 32; // cosets of the quotient domain (d - 1 <= 17)
+
+// The prover's "extended" arrays hold C = d - 1 cosets of the size-n domain back to back:
+// row idx = j * n + i is the evaluation at  zeta * extended_omega^j * omega^i  (j < C).  These are
+// C of the 2^(extended_k - k) cosets that make up upstream's extended domain — enough points to
+// determine h (degree < C n), so the other cosets are never computed (5 instead of 8 for the
+// degree-6 circuits of the reference).  A rotation moves inside a coset: blocks of 2^log_size rows
+// rotate independently, which is also the plain rotation of a Lagrange column (one block).
 
 // ---- Fr::random(rng) = from_u512(8 x next_u64): lo * R^2 + hi * R^3 (Montgomery products) ----
 ZK_D fe_t from_u512_row(const uint32_t* wide16) {
@@ -73,12 +81,14 @@ struct QuotPermAArgs {
     fe_t* h;
     fe_t y;
     const fe_t *l0, *l_last;
-    uint32_t nsets, log_ext, rot_scale;
+    uint32_t rows;                      // C * n
+    uint32_t nsets, log_ext, rot_scale; // log_ext = log2 of the rotation block (k)
     int32_t last_rot;                   // -(blinding_factors + 1)
     const fe_t* z[ZK_MAXC];             // permutation_product_coset per set
 };
 ZK_D uint32_t rot_idx(uint32_t idx, int32_t rot, uint32_t rot_scale, uint32_t log_size) {
-    return (idx + (uint32_t)(rot * (int32_t)rot_scale)) & ((1u << log_size) - 1);
+    const uint32_t mask = (1u << log_size) - 1;
+    return (idx & ~mask) | ((idx + (uint32_t)(rot * (int32_t)rot_scale)) & mask);
 }
 ZK_D void quot_perm_a_row(const QuotPermAArgs& a, uint32_t idx) {
     fe_t h = a.h[idx], l0 = a.l0[idx], ll = a.l_last[idx];
@@ -101,16 +111,16 @@ struct QuotPermBArgs {
     fe_t y, beta, gamma;
     const fe_t* l_active;
     const fe_t* z;
-    uint32_t ncols, log_ext, rot_scale, ew_bits;
+    uint32_t rows, ncols, log_ext, rot_scale;
     const fe_t* values[ZK_MAXC];        // column cosets
     const fe_t* sigma[ZK_MAXC];         // permutation cosets
     fe_t cdelta[ZK_MAXC];               // beta * zeta * delta^(global column index)
-    const fe_t *ew_lo, *ew_hi;          // extended_omega^idx two-level table
+    const fe_t* omega_pows;             // omega^i, i < n
+    const fe_t* coset_fac;              // extended_omega^j, j < C (device)
 };
 ZK_D void quot_perm_b_row(const QuotPermBArgs& a, uint32_t idx) {
-    uint32_t lo = idx & ((1u << a.ew_bits) - 1), hi = idx >> a.ew_bits;
-    fe_t wl = a.ew_lo[lo], wh = a.ew_hi[hi];
-    fe_t beta_term = Fr::mul(wl, wh);                                       // extended_omega^idx
+    fe_t wl = a.omega_pows[idx & ((1u << a.log_ext) - 1)], wh = a.coset_fac[idx >> a.log_ext];
+    fe_t beta_term = Fr::mul(wl, wh);                                       // extended_omega^j * omega^i = X / zeta
     fe_t left = a.z[rot_idx(idx, 1, a.rot_scale, a.log_ext)], right = a.z[idx];
     for (uint32_t j = 0; j < a.ncols; ++j) {
         fe_t v = a.values[j][idx], s = a.sigma[j][idx];
@@ -128,7 +138,7 @@ struct QuotLookupArgs {
     const fe_t *l0, *l_last, *l_active;
     const fe_t *z, *a, *s;              // product / permuted input / permuted table cosets
     const fe_t* table_value;            // (compressed input + beta)(compressed table + gamma)
-    uint32_t log_ext, rot_scale;
+    uint32_t log_ext, rot_scale, rows;
 };
 ZK_D void quot_lookup_row(const QuotLookupArgs& q, uint32_t idx) {
     fe_t h = q.h[idx], l0 = q.l0[idx], ll = q.l_last[idx], la = q.l_active[idx];
@@ -142,6 +152,21 @@ ZK_D void quot_lookup_row(const QuotLookupArgs& q, uint32_t idx) {
     h = Fr::add(Fr::mul(h, q.y), Fr::mul(a_minus_s, l0));
     h = Fr::add(Fr::mul(h, q.y), Fr::mul(Fr::mul(a_minus_s, Fr::sub(a, ap)), la));
     q.h[idx] = h;
+}
+
+// ---- vanishing::construct without the extended iNTT ----
+// g[j*n + r] are the coefficients (in Y = X / c_j) of h restricted to coset j, i.e. after the
+// per-coset iNTT.  With h(X) = sum_r X^r H_r(X^n), deg H_r < C:  H_r(c_j^n) = g[j][r] * c_j^(-r), and
+// the C coefficients of H_r — the r-th coefficient of every h piece — follow from the fixed C x C
+// inverse Vandermonde matrix of the points c_j^n:   out[t*n + r] = sum_j vinv[t*C + j] * H_r(c_j^n).
+ZK_D void coset_interpolate_row(const fe_t* g, const fe_t* inv_pow, const fe_t* vinv, uint32_t C, size_t n, fe_t* out, size_t r) {
+    fe_t v[ZK_MAXCOSETS];
+    for (uint32_t j = 0; j < C; ++j) { fe_t x = g[(size_t)j * n + r], w = inv_pow[(size_t)j * n + r]; v[j] = Fr::mul(x, w); }
+    for (uint32_t t = 0; t < C; ++t) {
+        fe_t acc = Fr::mul(v[0], vinv[t * C]);
+        for (uint32_t j = 1; j < C; ++j) acc = Fr::add(acc, Fr::mul(v[j], vinv[t * C + j]));
+        out[(size_t)t * n + r] = acc;
+    }
 }
 
 // ---- vanishing::evaluate: h_poly = sum_j (x^n)^j piece_j  (pieces contiguous, n apart) ----
