@@ -97,6 +97,8 @@ int32_t ws_reserve(b200zk_ctx* ctx, Workspace& w, size_t bytes);
 // d_out may alias d_in.
 int32_t ntt_run(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, uint32_t log_n,
                 const host::HFr& omega, const host::HFr* pre, const host::HFr* post, const fe_t* d_pre_tab = nullptr);
+int32_t ntt_run_cosets(b200zk_ctx* ctx, const fe_t* d_in, fe_t* d_out, uint32_t log_n, const host::HFr& omega,
+                       const fe_t* d_pre_tab, uint32_t batch);
 // four-step sharded NTT building blocks (ntt.cu)
 int32_t ntt_colstep_run(b200zk_ctx* ctx, fe_t* d_block, uint32_t log_r, uint32_t log_cg, uint32_t col0,
                         const host::HFr& omega_n, uint32_t log_n);

@@ -92,7 +92,7 @@ static int32_t build_plan(b200zk_ctx* ctx, uint32_t log_n, const host::HFr& omeg
 
 static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, uint32_t log_n,
                              const host::HFr& omega, const host::HFr* pre, const host::HFr* post, uint32_t batch,
-                             const fe_t* d_pre_tab = nullptr);
+                             const fe_t* d_pre_tab = nullptr, bool shared_input = false);
 
 int32_t ntt_run(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, uint32_t log_n,
                 const host::HFr& omega, const host::HFr* pre, const host::HFr* post, const fe_t* d_pre_tab) {
@@ -103,10 +103,10 @@ int32_t ntt_run(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, u
 // n_in = 2^log_n): every pass is one launch over all of them.
 static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, fe_t* d_out, uint32_t log_n,
                              const host::HFr& omega, const host::HFr* pre, const host::HFr* post, uint32_t batch,
-                             const fe_t* d_pre_tab) {
+                             const fe_t* d_pre_tab, bool shared_input) {
     if (log_n > 3 * NTT_MAX_LOG_M) return fail(ctx, B200ZK_EINVAL, "ntt_run", "log_n too large");
     if (batch == 0) return B200ZK_OK;
-    if (batch > 1 && (pre || post || d_pre_tab || ((uint64_t)batch << log_n) > 0xFFFFFFFFull)) return fail(ctx, B200ZK_EINVAL, "ntt_run", "bad batch");
+    if (batch > 1 && (pre || post || (d_pre_tab && !shared_input) || ((uint64_t)batch << log_n) > 0xFFFFFFFFull)) return fail(ctx, B200ZK_EINVAL, "ntt_run", "bad batch");
     std::array<uint64_t, 5> key = {log_n, omega.v[0], omega.v[1], omega.v[2], omega.v[3]};
     auto it = ctx->ntt_plans.find(key);
     if (it == ctx->ntt_plans.end()) {
@@ -139,6 +139,7 @@ static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, f
         a.batch_tiles = (batch > 1 && q.is_last) ? q.blocks : 0;
         a.use_pre = (p == 0 && pre) ? 1 : 0;
         a.pre_tab = p == 0 ? d_pre_tab : nullptr;
+        a.in_mask = (p == 0 && shared_input) ? (uint32_t)(N - 1) : 0;
         a.use_post = (q.is_last && post) ? 1 : 0;
         for (int i = 0; i < 3; ++i) {
             if (pre) a.pre[i] = to_dev(pre[i]);
@@ -163,6 +164,16 @@ static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, f
     }
     ZK_CUDA(ctx, cudaGetLastError());
     return B200ZK_OK;
+}
+
+// `batch` transforms of ONE input of 2^log_n elements, transform b of  in[r] * d_pre_tab[b * N + r]
+// (the quotient cosets of coeff_to_extended: pre_tab = powers of the coset generators); outputs
+// contiguous.  One launch per pass over all of them.
+int32_t ntt_run_cosets(b200zk_ctx* ctx, const fe_t* d_in, fe_t* d_out, uint32_t log_n, const host::HFr& omega,
+                       const fe_t* d_pre_tab, uint32_t batch) {
+    if (batch == 1) return ntt_run_batch(ctx, d_in, 1u << log_n, d_out, log_n, omega, nullptr, nullptr, 1, d_pre_tab, false);
+    if (d_in == d_out) return fail(ctx, B200ZK_EINVAL, "ntt_run_cosets", "in-place not supported");
+    return ntt_run_batch(ctx, d_in, 1u << log_n, d_out, log_n, omega, nullptr, nullptr, batch, d_pre_tab, true);
 }
 
 // Column step of a four-step NTT of size N = R * C sharded by column blocks:

@@ -40,6 +40,7 @@ struct NttPassArgs {
     uint32_t use_pre, use_post;
     fe_t pre[3], post[3];   // multiplied by index mod 3 on load (first pass) / store (last pass)
     const fe_t* pre_tab;    // optional, first pass: element g is multiplied by pre_tab[g] on load (coset powers)
+    uint32_t in_mask;       // first pass of a batch that shares ONE input: read in[g & in_mask] (0 = read in[g])
     const fe_t* roots;      // w_R^j, j < R/2, R = 2^log_roots >= M  (w_R = omega^(N/R))
     uint32_t log_roots;
     const fe_t* tw_lo;      // omega^i,            i < 2^tw_lo_bits
@@ -116,7 +117,7 @@ ZK_D void ntt_pass_block(const NttPassArgs& a, uint32_t bid, uint32_t nthreads, 
         }
         fe_t v;
         if (g < a.n_in) {
-            v = a.in[g];
+            v = a.in[a.in_mask ? (g & a.in_mask) : g];
             if (a.use_pre) { uint32_t r3 = (uint32_t)(g % 3); if (r3) v = Fr::mul(v, a.pre[r3]); }
             if (a.pre_tab) v = Fr::mul(v, a.pre_tab[g]);
         } else {

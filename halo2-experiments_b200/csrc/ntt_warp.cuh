@@ -89,7 +89,7 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
         if (!a.is_last) g = ((size_t)h << (a.log_m + a.log_l)) + ((size_t)m << a.log_l) + l0 + c;
         else g = batch_base + ((((size_t)(k1_0 + c) << a.log_mid) | rho_mid) << a.log_m) + m;
         if (g < a.n_in) {
-            x[e] = a.in[g];
+            x[e] = a.in[a.in_mask ? (g & a.in_mask) : g];
             if (a.use_pre) { uint32_t r3 = (uint32_t)(g % 3); if (r3) x[e] = Fr::mul(x[e], a.pre[r3]); }
             if (a.pre_tab) x[e] = Fr::mul(x[e], a.pre_tab[g]);
         } else {

@@ -331,10 +331,7 @@ static int32_t lagrange_to_coeff(b200zk_pk* pk, fe_t* d_a) {
 // coeff_to_extended restricted to the q cosets the quotient needs: coset j = size-n NTT of a_r * c_j^r
 static int32_t coeff_to_extended(b200zk_pk* pk, const fe_t* d_coeffs, fe_t* d_out) {
     PhaseTimer t(pk, PH_NTT);
-    const size_t n = pk->n;
-    for (uint32_t j = 0; j < pk->q; ++j)
-        ZK_TRY(ntt_run(pk->ctx, d_coeffs, pk->n, d_out + j * n, pk->dom->k, pk->dom->omega, nullptr, nullptr, pk->coset_pow + j * n));
-    return B200ZK_OK;
+    return ntt_run_cosets(pk->ctx, d_coeffs, d_out, pk->dom->k, pk->dom->omega, pk->coset_pow, pk->q);
 }
 static int32_t eval_dev(b200zk_pk* pk, const fe_t* d_poly, size_t len, const HFr& x, HFr* out) {
     return recurrence_run(pk->ctx, d_poly, nullptr, len, x, out);
