@@ -54,13 +54,81 @@ int32_t params_build_tables(b200zk_params* p) {
     return B200ZK_OK;
 }
 
+// c * (sum of the basis) from the 8-bit window table
+static host::HXyzz sum_table_mul(const std::vector<host::HXyzz>& tab, const host::HFr& c_mont) {
+    uint64_t limbs[4];
+    c_mont.to_canonical(limbs);
+    host::HXyzz acc = host::hx_identity();
+    for (uint32_t j = 0; j < 32; ++j) {
+        uint32_t d = (uint32_t)(limbs[j / 8] >> (8 * (j % 8))) & 0xff;
+        if (d) acc = host::hx_add(acc, tab[(size_t)j * 255 + d - 1]);
+    }
+    return acc;
+}
+
+static int32_t build_sum_table(b200zk_params* p, int which, const affine_t* bases, const affine_t* table) {
+    b200zk_ctx* ctx = p->ctx;
+    const size_t n = (size_t)1 << p->k;
+    fe_t* ones = nullptr;
+    ZK_CUDA(ctx, cudaMalloc(&ones, n * sizeof(fe_t)));
+    fe_t one;
+    memcpy(one.l, host::HFr::one().v, 32);
+    std::vector<fe_t> h(n, one);
+    cudaError_t e = cudaMemcpy(ones, h.data(), n * sizeof(fe_t), cudaMemcpyHostToDevice);
+    host::HAffine sum;
+    int32_t rc = e != cudaSuccess ? fail(ctx, B200ZK_ECUDA, "sum_table", cudaGetErrorString(e))
+                                  : (table ? msm_run_ex(ctx, ones, table, n, &p->pre, &sum) : msm_run(ctx, ones, bases, n, &sum));
+    cudaFree(ones);
+    if (rc != B200ZK_OK) return rc;
+    std::vector<host::HXyzz>& tab = p->sum_table[which];
+    tab.assign((size_t)32 * 255, host::hx_identity());
+    host::HXyzz base = sum.x.is_zero() && sum.y.is_zero() ? host::hx_identity() : host::hx_from_affine(sum);
+    for (uint32_t j = 0; j < 32; ++j) {
+        host::HXyzz acc = base;
+        for (uint32_t d = 1; d <= 255; ++d) { tab[(size_t)j * 255 + d - 1] = acc; acc = host::hx_add(acc, base); }
+        base = acc;                                                  // 256 * base
+    }
+    return B200ZK_OK;
+}
+
+// ParamsKZG::commit / commit_lagrange.  Columns of a padded circuit are constant on most rows:
+// advice columns are 0 there (the digit pass skips them), but a grand-product column z holds one
+// full-width value c on every unused row, which would put 2^k points into each of the W window
+// buckets.  When three probes of a full-length column agree on a non-zero c the commitment is
+// computed as  MSM(poly - c) + c * sum(basis):  the subtraction happens inside the digit pass and
+// turns the column sparse, sum(basis) is computed once per params.  Exact for any column (if the
+// probes mislead, MSM(poly - c) is simply dense again).
 int32_t params_commit_run(b200zk_params* p, const fe_t* d_poly, size_t len, bool lagrange, host::HAffine* out) {
+    b200zk_ctx* ctx = p->ctx;
     const affine_t* bases = lagrange ? p->d_g_lagrange : p->d_g;
-    if (!bases) return fail(p->ctx, B200ZK_EINVAL, "commit", "basis not loaded");
-    if (len > ((size_t)1 << p->k)) return fail(p->ctx, B200ZK_EINVAL, "commit", "polynomial longer than the SRS");
+    if (!bases) return fail(ctx, B200ZK_EINVAL, "commit", "basis not loaded");
+    const size_t n = (size_t)1 << p->k;
+    if (len > n) return fail(ctx, B200ZK_EINVAL, "commit", "polynomial longer than the SRS");
     const affine_t* table = lagrange ? p->d_gl_pre : p->d_g_pre;
-    if (table) return msm_run_ex(p->ctx, d_poly, table, len, &p->pre, out);
-    return msm_run(p->ctx, d_poly, bases, len, out);
+    fe_t sub;
+    bool use_sub = false;
+    static const bool const_run = !(getenv("B200ZK_MSM_CONST_RUN") && getenv("B200ZK_MSM_CONST_RUN")[0] == '0');
+    if (const_run && len == n && n >= 1024) {
+        fe_t* probe = (fe_t*)ctx->pinned;
+        const size_t at[3] = {n / 2, n / 2 + 1, n / 4 * 3};
+        for (int i = 0; i < 3; ++i) ZK_CUDA(ctx, cudaMemcpyAsync(probe + i, d_poly + at[i], sizeof(fe_t), cudaMemcpyDeviceToHost, ctx->stream));
+        ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const fe_t zero{};
+        if (!memcmp(probe, probe + 1, 32) && !memcmp(probe, probe + 2, 32) && memcmp(probe, &zero, 32)) { sub = probe[0]; use_sub = true; }
+    }
+    if (use_sub && p->sum_table[lagrange ? 1 : 0].empty()) ZK_TRY(build_sum_table(p, lagrange ? 1 : 0, bases, table));
+    host::HAffine r;
+    if (table) ZK_TRY(msm_run_ex(ctx, d_poly, table, len, &p->pre, &r, use_sub ? &sub : nullptr));
+    else ZK_TRY(msm_run_ex(ctx, d_poly, bases, len, nullptr, &r, use_sub ? &sub : nullptr));
+    if (use_sub) {
+        host::HFr c;
+        memcpy(c.v, sub.l, 32);
+        host::HXyzz acc = sum_table_mul(p->sum_table[lagrange ? 1 : 0], c);
+        if (!(r.x.is_zero() && r.y.is_zero())) acc = host::hx_add(acc, host::hx_from_affine(r));
+        r = host::hx_to_affine(acc);
+    }
+    *out = r;
+    return B200ZK_OK;
 }
 
 }  // namespace b200zk

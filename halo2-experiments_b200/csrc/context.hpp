@@ -70,6 +70,9 @@ struct b200zk_params {
     b200zk::affine_t* d_g_pre;
     b200zk::affine_t* d_gl_pre;
     b200zk::MsmPre pre;
+    // sum of all n points of each basis ([0] = g, [1] = g_lagrange) as an 8-bit fixed-window table
+    // (32 x 255 multiples), built on first use by params_commit_run for constant-run columns
+    std::vector<b200zk::host::HXyzz> sum_table[2];
 };
 
 namespace b200zk {
@@ -109,7 +112,8 @@ int32_t fr_scale_periodic(b200zk_ctx* ctx, fe_t* d_a, size_t n, const fe_t* d_m,
 // msm.cu ---------------------------------------------------------------------
 int32_t msm_run(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, host::HAffine* out);
 // fixed-base variant: d_bases is a table built by msm_precompute_run (pre != null)
-int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, const MsmPre* pre, host::HAffine* out);
+int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, const MsmPre* pre, host::HAffine* out,
+                   const fe_t* sub = nullptr);
 int32_t msm_precompute_run(b200zk_ctx* ctx, const affine_t* d_bases, size_t n, uint32_t c, uint32_t nwin, affine_t* d_table);
 // commit over a params basis, through the fixed-base table when it exists
 int32_t params_commit_run(b200zk_params* p, const fe_t* d_poly, size_t len, bool lagrange, host::HAffine* out);

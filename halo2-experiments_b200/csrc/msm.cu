@@ -27,6 +27,7 @@ template <bool SCATTER> __device__ __forceinline__ void msm_digit_pass_warp(cons
     const unsigned FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
     fe_t s = i < a.n ? a.scalars[i] : Fr::zero();
+    if (a.use_sub && i < a.n) s = Fr::sub(s, a.sub);
     if (!__any_sync(FULL, !Fr::is_zero(s))) return;
     s = Fr::from_mont(s);
     uint32_t carry = 0;
@@ -148,7 +149,8 @@ int32_t msm_precompute_run(b200zk_ctx* ctx, const affine_t* d_bases, size_t n, u
 
 // d_bases: the n points (pre == null), or the fixed-base table of a params object with
 // `pre->stride` points per window (pre != null; then n <= stride).
-int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, const MsmPre* pre, host::HAffine* out) {
+int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, const MsmPre* pre, host::HAffine* out,
+                   const fe_t* sub) {
     if (n == 0) { *out = {host::HFq::zero(), host::HFq::zero()}; return B200ZK_OK; }
     if (n >= ((size_t)1 << 31)) return fail(ctx, B200ZK_EINVAL, "msm_run", "len must be < 2^31");
     MsmShape s = pre ? pre->shape : msm_plan_shape(n, ctx->msm_force_c);
@@ -171,6 +173,8 @@ int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bas
     a.scalars = d_scalars; a.bases = d_bases; a.n = (uint32_t)n;
     a.c = s.c; a.nwin = s.nwin; a.log_t = s.log_t;
     a.pre = pre ? 1 : 0; a.pre_stride = pre ? pre->stride : 0; a.nbuckets = B;
+    a.use_sub = sub ? 1 : 0;
+    if (sub) a.sub = *sub;
     a.counts = (uint32_t*)(base + o_counts); a.offsets = (uint32_t*)(base + o_offsets); a.cursor = (uint32_t*)(base + o_cursor);
     a.entries = (uint32_t*)(base + o_entries);
     a.buckets = (xyzz_t*)(base + o_buckets); a.partials = (xyzz_t*)(base + o_partials); a.window_sums = (xyzz_t*)(base + o_wsum);
@@ -243,7 +247,7 @@ int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bas
 }
 
 int32_t msm_run(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, host::HAffine* out) {
-    return msm_run_ex(ctx, d_scalars, d_bases, n, nullptr, out);
+    return msm_run_ex(ctx, d_scalars, d_bases, n, nullptr, out, nullptr);
 }
 
 }  // namespace b200zk

@@ -41,6 +41,8 @@ struct MsmArgs {
     uint32_t pre;               // 0 = per-window buckets, 1 = fixed-base table
     uint32_t pre_stride;        // points per window in the table (the params' n)
     uint32_t nbuckets;          // W << (c-1), or 1 << (c-1) in fixed-base mode
+    uint32_t use_sub;           // scalars are taken as scalars[i] - sub (see params_commit_run: constant-run columns)
+    fe_t sub;
     uint32_t* counts;           // [W << (c-1)]
     uint32_t* offsets;          // [(W << (c-1)) + 1]
     uint32_t* cursor;           // [W << (c-1)]
@@ -61,7 +63,9 @@ ZK_D uint32_t msm_window_bits(const fe_t& s, uint32_t bit, uint32_t c) {
 // Calls f(key, sign) for every non-zero signed digit of scalar i.
 // Digits d_j in [-2^(c-1), 2^(c-1)]; key = j * 2^(c-1) + |d_j| - 1.
 template <class F> ZK_D void msm_for_each_digit(const MsmArgs& a, uint32_t i, F f) {
-    fe_t s = Fr::from_mont(a.scalars[i]);
+    fe_t s = a.scalars[i];
+    if (a.use_sub) s = Fr::sub(s, a.sub);
+    s = Fr::from_mont(s);
     uint32_t carry = 0, half = 1u << (a.c - 1);
     for (uint32_t j = 0; j < a.nwin; ++j) {
         uint32_t d = msm_window_bits(s, j * a.c, a.c) + carry;
