@@ -21,12 +21,6 @@ __global__ void __launch_bounds__(32 * NTT_WARPS_PER_BLOCK, 4) ntt_warp_pass_ker
     const uint32_t w = threadIdx.x >> 5, wid = blockIdx.x * NTT_WARPS_PER_BLOCK + w;
     if (wid < ntiles) ntt_pass_warp(a, wid, threadIdx.x & 31, sm[w]);
 }
-__global__ void __launch_bounds__(32 * NTT_WARPS_PER_BLOCK, 3) ntt_warp_pass_kernel_occ3(const NttPassArgs a, uint32_t ntiles) {
-    __shared__ half_t sm[NTT_WARPS_PER_BLOCK][512];
-    const uint32_t w = threadIdx.x >> 5, wid = blockIdx.x * NTT_WARPS_PER_BLOCK + w;
-    if (wid < ntiles) ntt_pass_warp(a, wid, threadIdx.x & 31, sm[w]);
-}
-
 __global__ void ntt_pow_table_kernel(fe_t* out, const fe_t base, uint32_t count, uint32_t shift) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) ntt_pow_table_thread(out, base, i, shift);
@@ -154,9 +148,7 @@ static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, f
         uint32_t threads = tile / 2 < NTT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : NTT_THREADS;
         if (plan.warp) {
             const uint32_t ntiles = q.blocks * batch;
-            static const bool occ3 = getenv("B200ZK_NTT_WARP_OCC3") != nullptr;
-            if (occ3) ntt_warp_pass_kernel_occ3<<<(ntiles + NTT_WARPS_PER_BLOCK - 1) / NTT_WARPS_PER_BLOCK, 32 * NTT_WARPS_PER_BLOCK, 0, ctx->stream>>>(a, ntiles);
-            else ntt_warp_pass_kernel<<<(ntiles + NTT_WARPS_PER_BLOCK - 1) / NTT_WARPS_PER_BLOCK, 32 * NTT_WARPS_PER_BLOCK, 0, ctx->stream>>>(a, ntiles);
+            ntt_warp_pass_kernel<<<(ntiles + NTT_WARPS_PER_BLOCK - 1) / NTT_WARPS_PER_BLOCK, 32 * NTT_WARPS_PER_BLOCK, 0, ctx->stream>>>(a, ntiles);
         } else {
             ntt_pass_kernel<<<q.blocks * batch, threads, smem, ctx->stream>>>(a);
         }
