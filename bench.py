@@ -6,9 +6,11 @@
                                            # prover / best_multiexp / best_fft on this box's cores
 
 Workloads (one "step" = one pass of the hot path over one batch of synthetic input):
-  prove (default) : create_proof for the MST-shaped synthetic circuit (20 advice,
-                    8 u8 lookups, 16 permutation columns, degree 6) at k = 20 — BASELINE.json's
-                    headline "create_proof ms (MST k=20)".  SRS and proving key resident in HBM.
+  prove (default) : create_proof for the reference's Merkle Sum Tree circuit (chips.py: Poseidon
+                    width 5, LtChip, u8 lookups; inclusion path of a 2^16-leaf tree, synthetic
+                    values) padded to k = 20 — BASELINE.json's headline "create_proof ms (MST k=20)".
+                    --circuit mst_dense is the same shape with every row in use (dense witness).
+                    SRS and proving key resident in HBM.
   msm             : one best_multiexp over 2^L uniform scalars and 2^L SRS points
   ntt             : one best_fft over 2^L uniform Fr elements
 Prints ONE JSON line: value = device-timed with inputs resident in HBM; e2e = the same call through
@@ -39,6 +41,29 @@ MUL32_PER_FIELD_MUL = 136           # 8x8 product + 8x8 reduct
 def msm_work_mul32(n):
     """SURVEY.md §8(d) accounting (c = 16, W = 16): (N*16*11 + 2*65536*16*16) * 136 mul32."""
     return (n * 16 * 11 + 2 * 65536 * 16 * 16) * MUL32_PER_FIELD_MUL
+
+
+def ntt_digits(log_n):
+    """Pass structure the library plans for a transform of 2^log_n (csrc/ntt_plan.hpp)."""
+    if 10 <= log_n <= 21:
+        P = (log_n + 7) // 8
+    else:
+        P = min(3, max(1, (log_n + 9) // 10))
+    return [log_n // P + (1 if p < log_n % P else 0) for p in range(P)]
+
+
+def ntt_passes(log_n):
+    return len(ntt_digits(log_n))
+
+
+def ntt_work_mul32(log_n):
+    """Field multiplications one transform needs as executed: butterflies whose twiddle is not 1
+    (stage with half-size 2^lh: a fraction 1 - 2^-lh of N/2) plus one inter-pass twiddle per element
+    and pass boundary; 132 IMAD.WIDE-equivalents each (128 wide + 8 low IMAD at twice the rate)."""
+    n = 1 << log_n
+    d = ntt_digits(log_n)
+    muls = sum(n / 2 * (1 - 2.0 ** -lh) for m in d for lh in range(m)) + n * (len(d) - 1)
+    return muls * 132
 
 
 def measured_peaks():
@@ -147,15 +172,15 @@ def timed(be, dist, local, steps, fn):
     return max_over_ranks(dist, local, ms)
 
 
-CIRCUITS = {"mst": ("mst_shaped", "MST-shaped synthetic circuit k={k}: 20 advice, 8 u8 lookups, 16 permutation columns, degree 6, ext 8n"),
-            "v3": ("v3_shaped", "Merkle-v3-shaped synthetic circuit k={k}: 9 advice, no lookups, 12 permutation columns, degree 6, ext 8n"),
-            "mst_real": ("merkle_sum_tree_job", "the reference's MerkleSumTreeCircuit (Poseidon width 5, LtChip, 16-level path = 2^16 leaves) padded to k={k}: 20 advice, 15 fixed, 8 u8 lookups, 16 permutation columns, degree 6, ext 8n; witness rows mostly empty"),
-            "v3_real": ("merkle_v3_job", "the reference's MerkleTreeV3Circuit (Poseidon width 3, 13-level path) at k={k}: 7 advice, 10 fixed, 10 permutation columns, degree 6, ext 8n")}
+CIRCUITS = {"mst": ("merkle_sum_tree_job", "the reference's MerkleSumTreeCircuit (Poseidon width 5, LtChip, 16-level path = tree of 2^16 leaves) padded to k={k}: 20 advice, 15 fixed, 8 u8 lookups, 16 permutation columns, degree 6; synthetic leaf / sibling values"),
+            "v3": ("merkle_v3_job", "the reference's MerkleTreeV3Circuit (Poseidon width 3, 13-level path) at k={k}: 7 advice, 10 fixed, 10 permutation columns, degree 6"),
+            "mst_dense": ("mst_shaped", "MST-shaped synthetic circuit k={k} with every row in use (dense witness, worst case for the commits): 20 advice, 8 u8 lookups, 16 permutation columns, degree 6"),
+            "v3_dense": ("v3_shaped", "Merkle-v3-shaped synthetic circuit k={k} with every row in use: 9 advice, no lookups, 12 permutation columns, degree 6")}
 
 
 def build_job(zk, circuit, k, seed):
     """Dense synthetic circuits come from circuits_synth, the reference's real circuits from chips."""
-    mod = importlib.import_module(zk.__name__ + (".chips" if circuit.endswith("_real") else ".circuits_synth"))
+    mod = importlib.import_module(zk.__name__ + (".circuits_synth" if circuit.endswith("_dense") else ".chips"))
     return getattr(mod, CIRCUITS[circuit][0])(k, seed=seed)
 WORKLOAD_TEXT = {
     "prove": "create_proof (KZG/SHPLONK/Blake2b), {circuit}; SRS + pk resident in HBM",
@@ -317,25 +342,39 @@ def run_gpu(args):
                  "gpu_launches": int(launches), "clocks": clocks})
 
     # ---- roofline of the dominant kernel ------------------------------------------------
-    if args.workload in ("prove", "msm"):
-        if args.workload == "prove":
-            # dominant kernel = msm_accumulate inside the ~56 commits; time one dense commit of the
-            # same size on the same SRS with events (the random_poly commit of the proof)
-            d_dense = be.to_device(random_scalars(n, 5))
-            for _ in range(3):
-                params.commit_dev(d_dense, n, lagrange=False)
-            reps = 5
-            ms_msm = timed(be, dist, local, reps, lambda: params.commit_dev(d_dense, n, lagrange=False)) / reps
-            share = extra["phase_ms"]["msm"] / max(sum(extra["phase_ms"].values()), 1e-9)
-        else:
-            ms_msm, share = ms_per_step, 1.0
-        ach = msm_work_mul32(n) / (ms_msm / 1e3)
+    imad_note = ("no HBM/tensor bound applies: 254-bit Montgomery arithmetic is IMAD-pipe bound; peak = measured IMAD.WIDE.U32 issue "
+                 "rate on this B200 (tools/imad_bench.cu, profiles/r01_imad_microbench.jsonl)")
+    if args.workload == "prove":
+        # dominant kernel = the NTT pass kernel (per-coset size-n transforms of coeff_to_extended and
+        # the iNTTs): time one size-n transform on device data with events
+        omega = synth.mont_from_ints([pow(pow(7, (synth.R_MOD - 1) >> 28, synth.R_MOD), 1 << (28 - k), synth.R_MOD)])[0]
+        d_vec = be.to_device(random_scalars(n, 5))
+        for _ in range(3):
+            be.best_fft_dev(d_vec, omega, k)
+        reps = 20
+        ms_ntt = timed(be, dist, local, reps, lambda: be.best_fft_dev(d_vec, omega, k)) / reps
+        ph = extra["phase_ms"]
+        ach = ntt_work_mul32(k) / (ms_ntt / 1e3)
+        hbm = 64.0 * n / (ms_ntt / 1e3) / 1e9
+        line["roofline"] = {"bound": "imad", "kernel": f"ntt pass kernel, one 2^{k} transform = {ntt_passes(k)} launches", "achieved": ach / 1e12,
+                            "peak": IMAD_WIDE_PEAK / 1e12, "unit": "T IMAD.WIDE.U32/s", "frac": ach / IMAD_WIDE_PEAK, "traffic": None,
+                            "ms_per_launch_group": ms_ntt, "share_of_step": ph["ntt"] / max(sum(ph.values()), 1e-9),
+                            "hbm_view": {"achieved": hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm / peaks["hbm_gbs"],
+                                         "algorithmic_bytes": 64 * n, "peak_source": peak_src},
+                            "note": imad_note + "; work = non-trivial butterfly and inter-pass twiddle multiplications x 132 (DESIGN.md §4)"}
+        d_dense = be.to_device(random_scalars(n, 6))
+        for _ in range(3):
+            params.commit_dev(d_dense, n, lagrange=False)
+        ms_msm = timed(be, dist, local, 5, lambda: params.commit_dev(d_dense, n, lagrange=False)) / 5
+        line["roofline_msm"] = {"bound": "imad", "kernel": f"dense commit 2^{k} (msm_accumulate_task dominates)",
+                                "achieved": msm_work_mul32(n) / (ms_msm / 1e3) / 1e12, "peak": IMAD_WIDE_PEAK / 1e12, "unit": "T IMAD.WIDE.U32/s",
+                                "frac": msm_work_mul32(n) / (ms_msm / 1e3) / IMAD_WIDE_PEAK, "ms_per_launch_group": ms_msm,
+                                "share_of_step": ph["msm"] / max(sum(ph.values()), 1e-9), "note": "work per SURVEY.md 8(d)"}
+    elif args.workload == "msm":
+        ach = msm_work_mul32(n) / (ms_per_step / 1e3)
         line["roofline"] = {"bound": "imad", "kernel": f"MSM 2^{int(np.log2(n))} (msm_accumulate dominates)", "achieved": ach / 1e12,
                             "peak": IMAD_WIDE_PEAK / 1e12, "unit": "T IMAD.WIDE.U32/s", "frac": ach / IMAD_WIDE_PEAK, "traffic": None,
-                            "ms_per_launch_group": ms_msm, "share_of_step": share,
-                            "note": "no HBM/tensor bound applies: 254-bit Montgomery arithmetic is IMAD-pipe bound; peak = measured "
-                                    "IMAD.WIDE.U32 issue rate on this B200 (tools/imad_bench.cu, profiles/r01_imad_microbench.jsonl); "
-                                    "work per SURVEY.md 8(d)"}
+                            "ms_per_launch_group": ms_per_step, "share_of_step": 1.0, "note": imad_note + "; work per SURVEY.md 8(d)"}
     else:
         ach = 64.0 * n / (ms_per_step / 1e3) / 1e9
         line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
