@@ -15,12 +15,13 @@ __global__ void __launch_bounds__(NTT_THREADS, 1) ntt_pass_kernel(const NttPassA
     ntt_pass_block(a, blockIdx.x, blockDim.x, ntt_sm);
 }
 
-// one warp per 256-element tile; 8 KB of warp-private shared memory each
-__global__ void __launch_bounds__(32 * NTT_WARPS_PER_BLOCK, 4) ntt_warp_pass_kernel(const NttPassArgs a, uint32_t ntiles) {
-    __shared__ half_t sm[NTT_WARPS_PER_BLOCK][512];
+// one warp per 128-element tile; 4 KB of warp-private shared memory each
+__global__ void __launch_bounds__(32 * NTT_WARPS_PER_BLOCK, 6) ntt_warp_pass_kernel(const NttPassArgs a, uint32_t ntiles) {
+    __shared__ half_t sm[NTT_WARPS_PER_BLOCK][256];
     const uint32_t w = threadIdx.x >> 5, wid = blockIdx.x * NTT_WARPS_PER_BLOCK + w;
     if (wid < ntiles) ntt_pass_warp(a, wid, threadIdx.x & 31, sm[w]);
 }
+
 __global__ void ntt_pow_table_kernel(fe_t* out, const fe_t base, uint32_t count, uint32_t shift) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) ntt_pow_table_thread(out, base, i, shift);

@@ -47,17 +47,15 @@ inline NttShape ntt_plan_shape(uint32_t log_n, uint32_t max_log_m, uint32_t max_
     return s;
 }
 
-// Plan for the warp-level kernel (ntt_warp.cuh): every pass is a 2^5..2^8-point transform on
-// tiles of 256 elements (TW = 256 / M columns), at most three passes -> 10 <= log_n <= 24.
-// Measured on B200 (profiles/r01_ntt_warp_vs_block.txt): 0.251 vs 0.284 ms at 2^20, where data
-// and twiddles stay in L2, but 2.34 vs 2.06 ms at 2^23 and 4.74 vs 4.20 ms at 2^24, where the
-// scattered HBM reads meet 16 warps per SM instead of 32 — so the block kernel keeps the large sizes.
-inline bool ntt_warp_eligible(uint32_t log_n, uint32_t max_log = 21) { return log_n >= 10 && log_n <= 24 && log_n <= max_log; }
+// Plan for the warp-level kernel (ntt_warp.cuh): every pass is a 2^4..2^7-point transform on
+// tiles of 128 elements (TW = 128 / M columns), at most three passes -> 12 <= log_n <= 21.
+inline bool ntt_warp_eligible(uint32_t log_n, uint32_t max_log = 21) { return log_n >= 12 && log_n <= 21 && log_n <= max_log; }
 
 inline NttShape ntt_plan_shape_warp(uint32_t log_n) {
+    const uint32_t tile_log = 7;
     NttShape s{};
     s.log_n = log_n;
-    uint32_t P = (log_n + 7) / 8;
+    uint32_t P = (log_n + tile_log - 1) / tile_log;
     s.npass = P;
     uint32_t base = log_n / P, rem = log_n % P, d[3] = {0, 0, 0};
     for (uint32_t p = 0; p < P; ++p) d[p] = base + (p < rem ? 1 : 0);
@@ -70,8 +68,8 @@ inline NttShape ntt_plan_shape_warp(uint32_t log_n) {
         q.is_last = (p + 1 == P);
         q.log_m1 = P > 1 ? d[0] : 0;
         q.log_mid = P == 3 ? d[1] : 0;
-        q.log_tw = 8 - d[p];
-        q.blocks = 1u << (log_n - 8);                   // warp tiles
+        q.log_tw = tile_log - d[p];
+        q.blocks = 1u << (log_n - tile_log);            // warp tiles
     }
     s.log_roots = d[0];
     s.tw_lo_bits = (log_n + 1) / 2;

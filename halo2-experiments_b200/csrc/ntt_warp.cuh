@@ -2,50 +2,51 @@
 // ntt_pass_block in ntt.cuh — see there for the reference mapping to halo2's best_fft).
 //
 // ntt_pass_block runs one butterfly stage per __syncthreads with every operand going through
-// shared memory: the IMAD.WIDE pipe sat at ~70 % and issue slots at ~42 % while warps waited on
-// barriers (profiles/r01_ncu_ntt_summary.txt).  Here ONE WARP owns a tile of 256 elements =
-// 2^lm points x 2^(8-lm) adjacent columns (5 <= lm <= 8), every lane keeps 8 elements in
-// registers, and the <= 8 butterfly stages run in three register rounds:
-//     tile index u = point * TW + column  (8 bits);  a stage pairs the elements differing in one u bit
-//     round 1  lane holds u = e*32 + lane                          bits 7,6,5 are lane-local
-//     round 2  lane holds u = (lane>>2)*32 + e*4 + (lane&3)        bits 4,3,2 are lane-local
-//     round 3  lane holds u = lane*8 + e                           bits 1,0   are lane-local
-// Between rounds the 8 KB tile is transposed through warp-private shared memory (two 16-byte
-// planes, slot = u ^ ((u >> 3) & 7), which makes every quarter-warp access cover the eight
-// 16-byte bank groups once in all three layouts).  No block-level barrier anywhere; each lane has
-// four independent field multiplications in flight per stage.
+// shared memory.  Here ONE WARP owns a tile of 128 elements = 2^lm points x 2^(7-lm) adjacent
+// columns (4 <= lm <= 7), every lane keeps 4 elements in registers, and the <= 7 butterfly
+// stages run in register rounds; a stage pairs the elements whose tile index
+// u = point * TW + column differs in one bit:
+//     round 1  lane holds u = e*32 + lane                        bits 6,5 lane-local
+//     round 2  lane holds u = (lane>>3)*32 + e*8 + (lane&7)      bits 4,3 lane-local
+//     round 3  lane holds u = (lane>>1)*8 + e*2 + (lane&1)       bits 2,1 lane-local
+//     bit 0    partner lane = lane ^ 1: its twiddle is always 1, so the stage is a shuffle, an
+//              addition on the even lane and a subtraction on the odd one.
+// slot = u ^ ((u >> 2) & 6) keeps every quarter-warp access conflict-free in all three layouts.
+//
+// No block-level barrier anywhere; 80 registers per thread, 24 resident warps per SM.  Measured on
+// B200 (profiles/r01_ntt_warp_vs_block.txt): 2^16 0.037 vs 0.064 ms, 2^20 0.235 vs 0.284 ms,
+// 2^21 0.478 vs 0.505 ms against the block kernel.  Three passes of at most 7 bits cover 2^21;
+// beyond that the block kernel runs.  (A variant with 8 elements per lane — 128 registers, 16
+// warps per SM, 288 KB of code — was slower than both from 2^21 up and is not kept.)
 #pragma once
 #include "ntt.cuh"
 
 namespace b200zk {
 
-static constexpr uint32_t NTT_WARP_TILE_LOG = 8;
+static constexpr uint32_t NTT_WARP_TILE_LOG = 7;
 static constexpr uint32_t NTT_WARPS_PER_BLOCK = 4;
 
-__device__ __forceinline__ uint32_t ntt_warp_slot(uint32_t u) { return u ^ ((u >> 3) & 7u); }
+__device__ __forceinline__ uint32_t ntt_warp_slot(uint32_t u) { return u ^ ((u >> 2) & 6u); }
 
 template <int LAYOUT> __device__ __forceinline__ uint32_t ntt_warp_u(uint32_t lane, uint32_t e) {
     if (LAYOUT == 0) return (e << 5) | lane;
-    if (LAYOUT == 1) return ((lane >> 2) << 5) | (e << 2) | (lane & 3u);
-    return (lane << 3) | e;
+    if (LAYOUT == 1) return ((lane >> 3) << 5) | (e << 3) | (lane & 7u);
+    return ((lane >> 1) << 3) | (e << 1) | (lane & 1u);
 }
-
-template <int LAYOUT> __device__ __forceinline__ void ntt_warp_put(half_t* sm, uint32_t lane, const fe_t (&x)[8]) {
+template <int LAYOUT> __device__ __forceinline__ void ntt_warp_put(half_t* sm, uint32_t lane, const fe_t (&x)[4]) {
 #pragma unroll
-    for (uint32_t e = 0; e < 8; ++e) tile_st(sm, 256, ntt_warp_slot(ntt_warp_u<LAYOUT>(lane, e)), x[e]);
+    for (uint32_t e = 0; e < 4; ++e) tile_st(sm, 128, ntt_warp_slot(ntt_warp_u<LAYOUT>(lane, e)), x[e]);
 }
-template <int LAYOUT> __device__ __forceinline__ void ntt_warp_get(const half_t* sm, uint32_t lane, fe_t (&x)[8]) {
+template <int LAYOUT> __device__ __forceinline__ void ntt_warp_get(const half_t* sm, uint32_t lane, fe_t (&x)[4]) {
 #pragma unroll
-    for (uint32_t e = 0; e < 8; ++e) x[e] = tile_ld(sm, 256, ntt_warp_slot(ntt_warp_u<LAYOUT>(lane, e)));
+    for (uint32_t e = 0; e < 4; ++e) x[e] = tile_ld(sm, 128, ntt_warp_slot(ntt_warp_u<LAYOUT>(lane, e)));
 }
-
-// One DIF stage on tile bit B, which is bit EB of the lane-local element index in this layout.
 template <int LAYOUT, int B, int EB>
-__device__ __forceinline__ void ntt_warp_stage(const NttPassArgs& a, uint32_t lane, uint32_t log_tw, fe_t (&x)[8]) {
-    if ((uint32_t)B < log_tw) return;                          // column bit: not part of the transform
+__device__ __forceinline__ void ntt_warp_stage(const NttPassArgs& a, uint32_t lane, uint32_t log_tw, fe_t (&x)[4]) {
+    if ((uint32_t)B < log_tw) return;
     const uint32_t lh = (uint32_t)B - log_tw;
 #pragma unroll
-    for (uint32_t e0 = 0; e0 < 8; ++e0) {
+    for (uint32_t e0 = 0; e0 < 4; ++e0) {
         if (e0 & (1u << EB)) continue;
         const uint32_t e1 = e0 | (1u << EB);
         const uint32_t j = (ntt_warp_u<LAYOUT>(lane, e0) >> log_tw) & ((1u << lh) - 1u);
@@ -55,7 +56,6 @@ __device__ __forceinline__ void ntt_warp_stage(const NttPassArgs& a, uint32_t la
     }
 }
 
-// wid = global warp index = tile index (same tile numbering as ntt_pass_block with TW = 256 / M).
 __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid, uint32_t lane, half_t* sm) {
     const uint32_t log_tw = NTT_WARP_TILE_LOG - a.log_m, TW = 1u << log_tw;
     uint32_t h = 0, l0 = 0, k1_0 = 0, rho_mid = 0;
@@ -68,22 +68,9 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
         if (a.batch_tiles) { batch_base = (size_t)(wid / a.batch_tiles) << a.log_n; wl = wid % a.batch_tiles; }
         rho_mid = wl % mid; k1_0 = (wl / mid) << log_tw;
     }
-    // The inter-pass twiddles of this tile are scattered 32-byte reads from a table as large as the
-    // transform: ask L2 for them now, they are needed after the last round.
-    if (!a.is_last && a.tw_full) {
-        const bool r3 = log_tw < 2;
+    fe_t x[4];
 #pragma unroll
-        for (uint32_t e = 0; e < 8; ++e) {
-            const uint32_t u = r3 ? ntt_warp_u<2>(lane, e) : ntt_warp_u<1>(lane, e);
-            const uint32_t k = __brev(u >> log_tw) >> (32 - a.log_m);
-            const uint64_t E = ((uint64_t)(l0 + (u & (TW - 1)) + a.l_offset) * k) << a.tw_shift;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.tw_full + (uint32_t)E));
-        }
-    }
-    fe_t x[8];
-    // ---- load (layout of round 1) ----
-#pragma unroll
-    for (uint32_t e = 0; e < 8; ++e) {
+    for (uint32_t e = 0; e < 4; ++e) {
         const uint32_t u = ntt_warp_u<0>(lane, e), m = u >> log_tw, c = u & (TW - 1);
         size_t g;
         if (!a.is_last) g = ((size_t)h << (a.log_m + a.log_l)) + ((size_t)m << a.log_l) + l0 + c;
@@ -96,30 +83,32 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
             x[e] = Fr::zero();
         }
     }
-    // ---- round 1: bits 7, 6, 5 ----
-    ntt_warp_stage<0, 7, 2>(a, lane, log_tw, x);
     ntt_warp_stage<0, 6, 1>(a, lane, log_tw, x);
     ntt_warp_stage<0, 5, 0>(a, lane, log_tw, x);
     ntt_warp_put<0>(sm, lane, x);
     __syncwarp();
     ntt_warp_get<1>(sm, lane, x);
-    // ---- round 2: bits 4, 3, 2 ----
-    ntt_warp_stage<1, 4, 2>(a, lane, log_tw, x);
-    ntt_warp_stage<1, 3, 1>(a, lane, log_tw, x);
-    ntt_warp_stage<1, 2, 0>(a, lane, log_tw, x);
-    const bool round3 = log_tw < 2;                            // uniform: bits 1 / 0 carry points only for M >= 128
-    if (round3) {
-        __syncwarp();
-        ntt_warp_put<1>(sm, lane, x);
-        __syncwarp();
-        ntt_warp_get<2>(sm, lane, x);
-        ntt_warp_stage<2, 1, 1>(a, lane, log_tw, x);
-        ntt_warp_stage<2, 0, 0>(a, lane, log_tw, x);
-    }
-    // ---- store: position p holds X[bitrev(p)] ----
+    ntt_warp_stage<1, 4, 1>(a, lane, log_tw, x);
+    ntt_warp_stage<1, 3, 0>(a, lane, log_tw, x);
+    __syncwarp();
+    ntt_warp_put<1>(sm, lane, x);
+    __syncwarp();
+    ntt_warp_get<2>(sm, lane, x);
+    ntt_warp_stage<2, 2, 1>(a, lane, log_tw, x);
+    ntt_warp_stage<2, 1, 0>(a, lane, log_tw, x);
+    if (log_tw == 0) {                                         // bit 0 carries a point: twiddle-free stage across lane pairs
+        const bool odd = lane & 1u;
 #pragma unroll
-    for (uint32_t e = 0; e < 8; ++e) {
-        const uint32_t u = round3 ? ntt_warp_u<2>(lane, e) : ntt_warp_u<1>(lane, e);
+        for (uint32_t e = 0; e < 4; ++e) {
+            fe_t y;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y.l[i] = __shfl_xor_sync(0xffffffffu, x[e].l[i], 1);
+            x[e] = odd ? Fr::sub(y, x[e]) : Fr::add(x[e], y);
+        }
+    }
+#pragma unroll
+    for (uint32_t e = 0; e < 4; ++e) {
+        const uint32_t u = ntt_warp_u<2>(lane, e);
         const uint32_t p = u >> log_tw, c = u & (TW - 1);
         const uint32_t k = __brev(p) >> (32 - a.log_m);
         fe_t v = x[e];
