@@ -19,9 +19,18 @@ namespace b200zk {
 
 static constexpr uint32_t LK_THREADS = 256;
 
-__global__ void lk_canonical_kernel(const fe_t* in, fe_t* out, uint32_t n) {
+// canonical values, plus the OR of every 32-bit limb over the column (limb_or[8]): lookup columns
+// of real circuits hold bytes / small integers, and a radix pass over bits that are zero in every
+// key is the identity
+__global__ void lk_canonical_kernel(const fe_t* in, fe_t* out, uint32_t n, uint32_t* limb_or) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { fe_t v = in[i]; out[i] = Fr::from_mont(v); }
+    fe_t v = Fr::zero();
+    if (i < n) { v = Fr::from_mont(in[i]); out[i] = v; }
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+        uint32_t w = __reduce_or_sync(0xffffffffu, v.l[l]);
+        if ((threadIdx.x & 31) == 0 && w) atomicOr(&limb_or[l], w);
+    }
 }
 __global__ void lk_iota_kernel(uint32_t* idx, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,20 +93,29 @@ static unsigned nb(size_t n) { return (unsigned)((n + LK_THREADS - 1) / LK_THREA
 
 struct SortScratch {
     fe_t* canon; fe_t* canon_sorted; uint32_t *idx_a, *idx_b; unsigned long long *key_a, *key_b; void* cub_tmp; size_t cub_bytes;
+    uint32_t* limb_or;          // 8 device words
 };
 
 // sorts `in` (Montgomery, u rows) by canonical value; outputs Montgomery rows in sorted order and the
 // canonical sorted keys.
 static int32_t sort256(b200zk_ctx* ctx, const fe_t* in, uint32_t u, fe_t* out_mont, const SortScratch& s) {
     cudaStream_t st = ctx->stream;
-    lk_canonical_kernel<<<nb(u), LK_THREADS, 0, st>>>(in, s.canon, u);
+    ZK_CUDA(ctx, cudaMemsetAsync(s.limb_or, 0, 32, st));
+    lk_canonical_kernel<<<nb(u), LK_THREADS, 0, st>>>(in, s.canon, u, s.limb_or);
     lk_iota_kernel<<<nb(u), LK_THREADS, 0, st>>>(s.idx_a, u);
     ctx->launches += 2;
+    uint32_t ors[8];
+    ZK_CUDA(ctx, cudaMemcpyAsync(ors, s.limb_or, 32, cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(ctx, cudaStreamSynchronize(st));
     uint32_t *ia = s.idx_a, *ib = s.idx_b;
     for (uint32_t limb = 0; limb < 4; ++limb) {
+        const unsigned long long bits = (unsigned long long)ors[2 * limb] | ((unsigned long long)ors[2 * limb + 1] << 32);
+        if (bits == 0) continue;                                   // every key has this limb zero: stable sort = identity
+        int end_bit = 64;
+        while (end_bit > 1 && !((bits >> (end_bit - 1)) & 1)) --end_bit;
         lk_limb_kernel<<<nb(u), LK_THREADS, 0, st>>>(s.canon, ia, limb, s.key_a, u);
         size_t bytes = s.cub_bytes;
-        ZK_CUDA(ctx, cub::DeviceRadixSort::SortPairs(s.cub_tmp, bytes, s.key_a, s.key_b, ia, ib, (int)u, 0, 64, st));
+        ZK_CUDA(ctx, cub::DeviceRadixSort::SortPairs(s.cub_tmp, bytes, s.key_a, s.key_b, ia, ib, (int)u, 0, end_bit, st));
         ctx->launches += 2;
         uint32_t* t = ia; ia = ib; ib = t;
     }
@@ -124,14 +142,14 @@ int32_t lookup_permute_run(b200zk_ctx* ctx, const fe_t* d_in, const fe_t* d_tab,
     size_t o_canon = take((size_t)u * 32), o_a_canon = take((size_t)u * 32), o_t_canon = take((size_t)u * 32), o_t_mont = take((size_t)u * 32);
     size_t o_idx_a = take((size_t)u * 4), o_idx_b = take((size_t)u * 4), o_key_a = take((size_t)u * 8), o_key_b = take((size_t)u * 8);
     size_t o_rep = take((size_t)u * 4), o_rep_scan = take((size_t)u * 4), o_keep = take((size_t)u * 4), o_keep_scan = take((size_t)u * 4);
-    size_t o_left = take((size_t)u * 4), o_cub = take(cub_bytes), o_cnt = take(64);
+    size_t o_left = take((size_t)u * 4), o_cub = take(cub_bytes), o_cnt = take(64);   // o_cnt: limb_or
     ZK_TRY(ws_reserve(ctx, ctx->lookup_ws, off));
     char* base = (char*)ctx->lookup_ws.p;
     SortScratch s;
     s.canon = (fe_t*)(base + o_canon);
     s.idx_a = (uint32_t*)(base + o_idx_a); s.idx_b = (uint32_t*)(base + o_idx_b);
     s.key_a = (unsigned long long*)(base + o_key_a); s.key_b = (unsigned long long*)(base + o_key_b);
-    s.cub_tmp = base + o_cub; s.cub_bytes = cub_bytes;
+    s.cub_tmp = base + o_cub; s.cub_bytes = cub_bytes; s.limb_or = (uint32_t*)(base + o_cnt);
     fe_t* a_canon = (fe_t*)(base + o_a_canon);
     fe_t* t_canon = (fe_t*)(base + o_t_canon);
     fe_t* t_mont = (fe_t*)(base + o_t_mont);
@@ -160,7 +178,6 @@ int32_t lookup_permute_run(b200zk_ctx* ctx, const fe_t* d_in, const fe_t* d_tab,
     lk_build_table_kernel<<<nb(u), LK_THREADS, 0, st>>>(d_pin, t_mont, rep, rep_scan, leftover, m, d_ptab, u);
     ctx->launches++;
     ZK_CUDA(ctx, cudaGetLastError());
-    (void)o_cnt;
     return B200ZK_OK;
 }
 
