@@ -15,8 +15,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 1) ntt_pass_kernel(const NttPassA
     ntt_pass_block(a, blockIdx.x, blockDim.x, ntt_sm);
 }
 
-// one warp per 128-element tile; 4 KB of warp-private shared memory each
-__global__ void __launch_bounds__(32 * NTT_WARPS_PER_BLOCK, 6) ntt_warp_pass_kernel(const NttPassArgs a, uint32_t ntiles) {
+// one warp per 128-element tile, 4 KB of warp-private shared memory each.  8 warps per block and
+// 3 blocks per SM measured best (2^20: 0.217 ms vs 0.234 ms with 4 x 6 or 2 x 12; 64-register
+// variants with 32 warps per SM spill and lose) — profiles/r01_ntt_warp_vs_block.txt
+__global__ void __launch_bounds__(32 * NTT_WARPS_PER_BLOCK, 3) ntt_warp_pass_kernel(const NttPassArgs a, uint32_t ntiles) {
     __shared__ half_t sm[NTT_WARPS_PER_BLOCK][256];
     const uint32_t w = threadIdx.x >> 5, wid = blockIdx.x * NTT_WARPS_PER_BLOCK + w;
     if (wid < ntiles) ntt_pass_warp(a, wid, threadIdx.x & 31, sm[w]);

@@ -24,7 +24,7 @@
 namespace b200zk {
 
 static constexpr uint32_t NTT_WARP_TILE_LOG = 7;
-static constexpr uint32_t NTT_WARPS_PER_BLOCK = 4;
+static constexpr uint32_t NTT_WARPS_PER_BLOCK = 8;
 
 __device__ __forceinline__ uint32_t ntt_warp_slot(uint32_t u) { return u ^ ((u >> 2) & 6u); }
 
