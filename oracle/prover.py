@@ -682,8 +682,10 @@ def verify_proof(s_secret, pk, instances, proof, transcript_repr):
                    fixed_evals=fixed_evals, sigma_evals=sigma_evals)
 
 
-def verify_full(s_secret, params_g, pk, instances, proof, transcript_repr):
-    """Complete check, including the SHPLONK opening against the known secret."""
+def verify_full(s_secret, params_g, pk, instances, proof, transcript_repr, s_g2=None):
+    """Complete check, including the SHPLONK opening: against the known secret (s_secret), or — as
+    halo2's verifier does it (shplonk/verifier.rs, DualMSM::check) — by pairing against the SRS's
+    [s]_2 when `s_g2` is given and s_secret is None:  e(h2, [s]_2) = e(u h2 + L / z_0, [1]_2)."""
     cs, dom = pk.cs, pk.dom
     Q, st = verify_proof(s_secret, pk, instances, proof, transcript_repr)
     x, rd = st["x"], st["rd"]
@@ -744,6 +746,10 @@ def verify_full(s_secret, params_g, pk, instances, proof, transcript_repr):
     zt = vanish_eval(super_points, u)
     Lpt = P.g1_add(Lpt, P.g1_mul(h1, (-zt) % R) if h1 is not None else None)
     Lpt = P.g1_mul(Lpt, pow(z0, -1, R)) if Lpt is not None else None
-    lhs = P.g1_mul(h2, s_secret) if h2 is not None else None
     rhs = P.g1_add(P.g1_mul(h2, u) if h2 is not None else None, Lpt)
+    if s_secret is None:
+        from oracle import pairing as PR
+        neg_rhs = None if rhs is None else (rhs[0], (-rhs[1]) % PR.Q)
+        return PR.pairing_product_is_one([(h2, s_g2), (neg_rhs, PR.G2_GEN)])
+    lhs = P.g1_mul(h2, s_secret) if h2 is not None else None
     return lhs == rhs

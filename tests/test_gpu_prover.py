@@ -26,7 +26,7 @@ def _first_diff(a, b):
     return None
 
 
-def _run(zk, backend, orc, job, check_verify=True):
+def _run(zk, backend, orc, job, check_verify=True, pairing=False):
     s = orc.random_fr(1, 4321)[0]
     params = zk.ParamsKZG.setup(backend, job.k, s)
     g, gl = params.read()
@@ -43,6 +43,10 @@ def _run(zk, backend, orc, job, check_verify=True):
     assert got == want, f"first differing 32-byte item: {_first_diff(got, want)} of {len(want) // 32}"
     if check_verify:
         assert OP.verify_full(orc.mont_to_ints(s)[0], g, pk_cpu, job.instances, got, job.transcript_repr)
+    if pairing:                                 # as halo2's verifier: e(., [s]_2) from the SRS, no secret
+        from oracle import pairing as PR
+        s_g2 = PR.g2_mul(PR.G2_GEN, orc.mont_to_ints(s)[0])
+        assert OP.verify_full(None, g, pk_cpu, job.instances, got, job.transcript_repr, s_g2=s_g2)
     # device-resident entry point gives the same bytes
     d_adv = backend.to_device(np.concatenate([np.ascontiguousarray(a).reshape(-1, 4) for a in job.advice]))
     d_wide = backend.to_device(wide)
@@ -97,7 +101,7 @@ def test_real_merkle_sum_tree_k9(zk, backend, orc):
     root = chips.compute_merkle_sum_root(leaf, elements, indices)
     circuit = chips.MerkleSumTreeCircuit(leaf[0], leaf[1], [e[0] for e in elements], [e[1] for e in elements], indices, 500)
     job = fe.synthesize_job(circuit, 9, [[leaf[0], leaf[1], root[0], 500]])
-    _run(zk, backend, orc, job, check_verify=True)
+    _run(zk, backend, orc, job, check_verify=True, pairing=True)
 
 
 @pytest.mark.parametrize("k,levels", [(10, 5), (14, 13)])
