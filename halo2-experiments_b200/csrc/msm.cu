@@ -91,6 +91,25 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_reduce_kernel(const MsmAr
 __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_reduce_bits_kernel(const MsmArgs a) {
     msm_reduce_bits_thread(a, blockIdx.x * blockDim.x + threadIdx.x);
 }
+// reduce_bits with the first 7 levels of the fold inside the block: the 128 chunk sums of a block
+// are tree-added in shared memory and ONE partial per block is written, so the fold that follows
+// (c blocks, latency bound) adds 2^(log_t - 7) values per bit instead of 2^log_t.
+__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_reduce_bits_tree_kernel(const MsmArgs a) {
+    __shared__ xyzz_t sm[MSM_ACC_THREADS];
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;     // (bit t, chunk), exact multiple of the block
+    const uint32_t t = gid >> a.log_t, chunk = gid & ((1u << a.log_t) - 1);
+    const uint32_t m = (1u << (a.c - 1)) >> a.log_t, b0 = chunk * m;
+    xyzz_t acc = xyzz_identity();
+    for (uint32_t b = b0; b < b0 + m; ++b)
+        if (((b + 1) >> t) & 1) xyzz_add(acc, a.buckets[b]);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t s = MSM_ACC_THREADS >> 1; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { xyzz_t v = sm[threadIdx.x]; xyzz_add(v, sm[threadIdx.x + s]); sm[threadIdx.x] = v; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.partials[blockIdx.x] = sm[0];          // index = t * 2^(log_t - 7) + block within the bit
+}
 __global__ void __launch_bounds__(MSM_FOLD_THREADS) msm_fold_kernel(const MsmArgs a) {
     __shared__ xyzz_t sm[MSM_FOLD_THREADS];
     msm_fold_block(a, blockIdx.x, blockDim.x, sm);
@@ -235,9 +254,16 @@ int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bas
         ctx->launches++;
     }
     size_t nred = (size_t)nsums << s.log_t;
-    if (pre) msm_reduce_bits_kernel<<<nb(nred, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
-    else msm_reduce_kernel<<<nb(nred, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
-    msm_fold_kernel<<<nsums, MSM_FOLD_THREADS, 0, st>>>(a);
+    if (pre && s.log_t >= 7) {
+        msm_reduce_bits_tree_kernel<<<(unsigned)(nred / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
+        MsmArgs af = a;
+        af.log_t = s.log_t - 7;                                  // partials per bit after the in-block tree
+        msm_fold_kernel<<<nsums, af.log_t >= 5 ? 32 : (1u << af.log_t), 0, st>>>(af);
+    } else {
+        if (pre) msm_reduce_bits_kernel<<<nb(nred, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
+        else msm_reduce_kernel<<<nb(nred, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
+        msm_fold_kernel<<<nsums, MSM_FOLD_THREADS, 0, st>>>(a);
+    }
     ctx->launches += 2;
     ZK_CUDA(ctx, cudaGetLastError());
     ZK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, a.window_sums, nsums * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));

@@ -682,6 +682,16 @@ def verify_proof(s_secret, pk, instances, proof, transcript_repr):
                    fixed_evals=fixed_evals, sigma_evals=sigma_evals)
 
 
+def verifying_key(cs, k, fixed_commitments, sigma_commitments):
+    """What verify_proof needs of a VerifyingKey: the constraint system, the domain and the
+    commitments to the fixed and permutation polynomials (affine integer pairs, None = identity)."""
+    vk = ProvingKey()
+    vk.cs, vk.k, vk.n = cs, k, 1 << k
+    vk.dom = B.Domain(cs.degree(), k)
+    vk.fixed_commitments, vk.sigma_commitments = list(fixed_commitments), list(sigma_commitments)
+    return vk
+
+
 def verify_full(s_secret, params_g, pk, instances, proof, transcript_repr, s_g2=None):
     """Complete check, including the SHPLONK opening: against the known secret (s_secret), or — as
     halo2's verifier does it (shplonk/verifier.rs, DualMSM::check) — by pairing against the SRS's
@@ -689,10 +699,14 @@ def verify_full(s_secret, params_g, pk, instances, proof, transcript_repr, s_g2=
     cs, dom = pk.cs, pk.dom
     Q, st = verify_proof(s_secret, pk, instances, proof, transcript_repr)
     x, rd = st["x"], st["rd"]
+    have_vk = hasattr(pk, "fixed_commitments")                   # verifying_key(): commitments given, no polynomials
+    fixed_c = {}
     for (col, rot), e in zip(cs.fixed_queries, st["fixed_evals"]):
-        Q.append((("fix", col), commit(params_g, pk.fixed_polys[col]), rotate_omega(dom, x, rot), e))
+        if col not in fixed_c:
+            fixed_c[col] = pk.fixed_commitments[col] if have_vk else commit(params_g, pk.fixed_polys[col])
+        Q.append((("fix", col), fixed_c[col], rotate_omega(dom, x, rot), e))
     for j, e in enumerate(st["sigma_evals"]):
-        Q.append((("sig", j), commit(params_g, pk.perm_polys[j]), x, e))
+        Q.append((("sig", j), pk.sigma_commitments[j] if have_vk else commit(params_g, pk.perm_polys[j]), x, e))
     Q.append((("h",), st["h_commit"], x, st["expected_h"]))
     Q.append((("rand",), st["random_c"], x, st["random_eval"]))
     y = rd.squeeze()
