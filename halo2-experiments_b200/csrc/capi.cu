@@ -97,38 +97,49 @@ static int32_t build_sum_table(b200zk_params* p, int which, const affine_t* base
 // buckets.  When three probes of a full-length column agree on a non-zero c the commitment is
 // computed as  MSM(poly - c) + c * sum(basis):  the subtraction happens inside the digit pass and
 // turns the column sparse, sum(basis) is computed once per params.  Exact for any column (if the
-// probes mislead, MSM(poly - c) is simply dense again).
-int32_t params_commit_run(b200zk_params* p, const fe_t* d_poly, size_t len, bool lagrange, host::HAffine* out) {
+// probes mislead, MSM(poly - c) is simply dense again).  Several columns of the same length are
+// committed in one batched launch sequence (msm_run_multi).
+int32_t params_commit_multi(b200zk_params* p, const fe_t* const* d_polys, uint32_t ncols, size_t len, bool lagrange, host::HAffine* outs) {
     b200zk_ctx* ctx = p->ctx;
     const affine_t* bases = lagrange ? p->d_g_lagrange : p->d_g;
     if (!bases) return fail(ctx, B200ZK_EINVAL, "commit", "basis not loaded");
     const size_t n = (size_t)1 << p->k;
     if (len > n) return fail(ctx, B200ZK_EINVAL, "commit", "polynomial longer than the SRS");
+    if (ncols == 0) return B200ZK_OK;
     const affine_t* table = lagrange ? p->d_gl_pre : p->d_g_pre;
-    fe_t sub;
-    bool use_sub = false;
+    const int which = lagrange ? 1 : 0;
+    std::vector<fe_t> sub(ncols);
+    std::vector<const fe_t*> subp(ncols, nullptr);
     static const bool const_run = !(getenv("B200ZK_MSM_CONST_RUN") && getenv("B200ZK_MSM_CONST_RUN")[0] == '0');
-    if (const_run && len == n && n >= 1024) {
+    bool any = false;
+    if (const_run && len == n && n >= 1024 && (size_t)ncols * 3 * sizeof(fe_t) <= ((size_t)60 << 10)) {
         fe_t* probe = (fe_t*)ctx->pinned;
         const size_t at[3] = {n / 2, n / 2 + 1, n / 4 * 3};
-        for (int i = 0; i < 3; ++i) ZK_CUDA(ctx, cudaMemcpyAsync(probe + i, d_poly + at[i], sizeof(fe_t), cudaMemcpyDeviceToHost, ctx->stream));
+        for (uint32_t b = 0; b < ncols; ++b)
+            for (int i = 0; i < 3; ++i)
+                ZK_CUDA(ctx, cudaMemcpyAsync(probe + 3 * b + i, d_polys[b] + at[i], sizeof(fe_t), cudaMemcpyDeviceToHost, ctx->stream));
         ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         const fe_t zero{};
-        if (!memcmp(probe, probe + 1, 32) && !memcmp(probe, probe + 2, 32) && memcmp(probe, &zero, 32)) { sub = probe[0]; use_sub = true; }
+        for (uint32_t b = 0; b < ncols; ++b) {
+            const fe_t* q = probe + 3 * b;
+            if (!memcmp(q, q + 1, 32) && !memcmp(q, q + 2, 32) && memcmp(q, &zero, 32)) { sub[b] = q[0]; subp[b] = &sub[b]; any = true; }
+        }
     }
-    if (use_sub && p->sum_table[lagrange ? 1 : 0].empty()) ZK_TRY(build_sum_table(p, lagrange ? 1 : 0, bases, table));
-    host::HAffine r;
-    if (table) ZK_TRY(msm_run_ex(ctx, d_poly, table, len, &p->pre, &r, use_sub ? &sub : nullptr));
-    else ZK_TRY(msm_run_ex(ctx, d_poly, bases, len, nullptr, &r, use_sub ? &sub : nullptr));
-    if (use_sub) {
+    if (any && p->sum_table[which].empty()) ZK_TRY(build_sum_table(p, which, bases, table));
+    ZK_TRY(msm_run_multi(ctx, d_polys, ncols, table ? table : bases, len, table ? &p->pre : nullptr, outs, any ? subp.data() : nullptr));
+    for (uint32_t b = 0; b < ncols; ++b) {
+        if (!subp[b]) continue;
         host::HFr c;
-        memcpy(c.v, sub.l, 32);
-        host::HXyzz acc = sum_table_mul(p->sum_table[lagrange ? 1 : 0], c);
-        if (!(r.x.is_zero() && r.y.is_zero())) acc = host::hx_add(acc, host::hx_from_affine(r));
-        r = host::hx_to_affine(acc);
+        memcpy(c.v, sub[b].l, 32);
+        host::HXyzz acc = sum_table_mul(p->sum_table[which], c);
+        if (!(outs[b].x.is_zero() && outs[b].y.is_zero())) acc = host::hx_add(acc, host::hx_from_affine(outs[b]));
+        outs[b] = host::hx_to_affine(acc);
     }
-    *out = r;
     return B200ZK_OK;
+}
+
+int32_t params_commit_run(b200zk_params* p, const fe_t* d_poly, size_t len, bool lagrange, host::HAffine* out) {
+    return params_commit_multi(p, &d_poly, 1, len, lagrange, out);
 }
 
 }  // namespace b200zk

@@ -112,11 +112,14 @@ int32_t fr_scale_periodic(b200zk_ctx* ctx, fe_t* d_a, size_t n, const fe_t* d_m,
 // msm.cu ---------------------------------------------------------------------
 int32_t msm_run(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, host::HAffine* out);
 // fixed-base variant: d_bases is a table built by msm_precompute_run (pre != null)
+int32_t msm_run_multi(b200zk_ctx* ctx, const fe_t* const* d_cols, uint32_t ncols, const affine_t* d_bases, size_t n, const MsmPre* pre,
+                      host::HAffine* outs, const fe_t* const* subs);
 int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, const MsmPre* pre, host::HAffine* out,
                    const fe_t* sub = nullptr);
 int32_t msm_precompute_run(b200zk_ctx* ctx, const affine_t* d_bases, size_t n, uint32_t c, uint32_t nwin, affine_t* d_table);
 // commit over a params basis, through the fixed-base table when it exists
 int32_t params_commit_run(b200zk_params* p, const fe_t* d_poly, size_t len, bool lagrange, host::HAffine* out);
+int32_t params_commit_multi(b200zk_params* p, const fe_t* const* d_polys, uint32_t ncols, size_t len, bool lagrange, host::HAffine* outs);
 // builds the fixed-base tables of a params object if memory allows (capi.cu)
 int32_t params_build_tables(b200zk_params* p);
 

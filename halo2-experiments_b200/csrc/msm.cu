@@ -23,12 +23,15 @@ static constexpr uint32_t MSM_FAST_MAX = 16;
 //     unused row, sorted lookup columns are long runs of one value — one lane adds 32 to the
 //     counter / claims 32 slots instead of 32 atomics serialising on one address
 //     (1.1 ms -> count and 1.8 ms -> scatter for a z column of the Merkle Sum Tree circuit at k = 20).
-template <bool SCATTER> __device__ __forceinline__ void msm_digit_pass_warp(const MsmArgs& a, uint32_t i) {
+template <bool SCATTER> __device__ __forceinline__ void msm_digit_pass_warp(const MsmArgs& a, uint32_t col, uint32_t i) {
     const unsigned FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
-    fe_t s = i < a.n ? a.scalars[i] : Fr::zero();
-    if (a.use_sub && i < a.n) s = Fr::sub(s, a.sub);
+    const fe_t* scalars = a.batch > 1 ? a.scalars_tab[col] : a.scalars;
+    fe_t s = i < a.n ? scalars[i] : Fr::zero();
+    if (a.batch > 1) { if (a.subs_on[col] && i < a.n) s = Fr::sub(s, a.subs[col]); }
+    else if (a.use_sub && i < a.n) s = Fr::sub(s, a.sub);
     if (!__any_sync(FULL, !Fr::is_zero(s))) return;
+    const uint32_t key_base = col * a.set_buckets;
     s = Fr::from_mont(s);
     uint32_t carry = 0;
     const uint32_t half = 1u << (a.c - 1);
@@ -36,7 +39,7 @@ template <bool SCATTER> __device__ __forceinline__ void msm_digit_pass_warp(cons
         uint32_t d = msm_window_bits(s, j * a.c, a.c) + carry;
         uint32_t sign = 0;
         if (d > half) { d = (1u << a.c) - d; sign = 1; carry = 1; } else carry = 0;
-        const uint32_t key = d == 0 ? 0xffffffffu : (a.pre ? d - 1 : j * half + d - 1);
+        const uint32_t key = d == 0 ? 0xffffffffu : key_base + (a.pre ? d - 1 : j * half + d - 1);
         const uint32_t entry = ((a.pre ? j * a.pre_stride + i : i) << 1) | sign;
         const uint32_t k0 = __shfl_sync(FULL, key, 0);
         if (__all_sync(FULL, key == k0)) {
@@ -55,11 +58,12 @@ template <bool SCATTER> __device__ __forceinline__ void msm_digit_pass_warp(cons
         }
     }
 }
-__global__ void __launch_bounds__(MSM_DIGIT_THREADS) msm_count_kernel(const MsmArgs a) {
-    msm_digit_pass_warp<false>(a, blockIdx.x * blockDim.x + threadIdx.x);
+// grid = batch * blocks_per_col blocks: a block never straddles two columns
+__global__ void __launch_bounds__(MSM_DIGIT_THREADS) msm_count_kernel(const MsmArgs a, uint32_t blocks_per_col) {
+    msm_digit_pass_warp<false>(a, blockIdx.x / blocks_per_col, (blockIdx.x % blocks_per_col) * blockDim.x + threadIdx.x);
 }
-__global__ void __launch_bounds__(MSM_DIGIT_THREADS) msm_scatter_kernel(const MsmArgs a) {
-    msm_digit_pass_warp<true>(a, blockIdx.x * blockDim.x + threadIdx.x);
+__global__ void __launch_bounds__(MSM_DIGIT_THREADS) msm_scatter_kernel(const MsmArgs a, uint32_t blocks_per_col) {
+    msm_digit_pass_warp<true>(a, blockIdx.x / blocks_per_col, (blockIdx.x % blocks_per_col) * blockDim.x + threadIdx.x);
 }
 __global__ void __launch_bounds__(MSM_SCAN_THREADS) scan_blocksum_kernel(const ScanArgs s) {
     __shared__ uint32_t sm[2 * MSM_SCAN_THREADS];
@@ -96,19 +100,22 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_reduce_bits_kernel(const 
 // (c blocks, latency bound) adds 2^(log_t - 7) values per bit instead of 2^log_t.
 __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_reduce_bits_tree_kernel(const MsmArgs a) {
     __shared__ xyzz_t sm[MSM_ACC_THREADS];
-    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;     // (bit t, chunk), exact multiple of the block
+    const uint32_t blocks_per_set = (a.c << a.log_t) / MSM_ACC_THREADS;
+    const uint32_t col = blockIdx.x / blocks_per_set;
+    const uint32_t gid = (blockIdx.x % blocks_per_set) * blockDim.x + threadIdx.x;     // (bit t, chunk) inside the column
     const uint32_t t = gid >> a.log_t, chunk = gid & ((1u << a.log_t) - 1);
     const uint32_t m = (1u << (a.c - 1)) >> a.log_t, b0 = chunk * m;
+    const xyzz_t* B = a.buckets + (size_t)col * a.set_buckets;
     xyzz_t acc = xyzz_identity();
     for (uint32_t b = b0; b < b0 + m; ++b)
-        if (((b + 1) >> t) & 1) xyzz_add(acc, a.buckets[b]);
+        if (((b + 1) >> t) & 1) xyzz_add(acc, B[b]);
     sm[threadIdx.x] = acc;
     __syncthreads();
     for (uint32_t s = MSM_ACC_THREADS >> 1; s > 0; s >>= 1) {
         if (threadIdx.x < s) { xyzz_t v = sm[threadIdx.x]; xyzz_add(v, sm[threadIdx.x + s]); sm[threadIdx.x] = v; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) a.partials[blockIdx.x] = sm[0];          // index = t * 2^(log_t - 7) + block within the bit
+    if (threadIdx.x == 0) a.partials[blockIdx.x] = sm[0];          // index = (col * c + t) * 2^(log_t - 7) + block within the bit
 }
 __global__ void __launch_bounds__(MSM_FOLD_THREADS) msm_fold_kernel(const MsmArgs a) {
     __shared__ xyzz_t sm[MSM_FOLD_THREADS];
@@ -166,50 +173,81 @@ int32_t msm_precompute_run(b200zk_ctx* ctx, const affine_t* d_bases, size_t n, u
     return B200ZK_OK;
 }
 
-// d_bases: the n points (pre == null), or the fixed-base table of a params object with
-// `pre->stride` points per window (pre != null; then n <= stride).
-int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, const MsmPre* pre, host::HAffine* out,
-                   const fe_t* sub) {
-    if (n == 0) { *out = {host::HFq::zero(), host::HFq::zero()}; return B200ZK_OK; }
+// `ncols` columns of n scalars each against the same bases: d_bases = the n points (pre == null,
+// ncols = 1), or the fixed-base table of a params object with `pre->stride` points per window
+// (pre != null; then n <= stride).  One launch sequence for all columns: the latency-bound tail
+// of a commit (scans, reduce, fold: ~0.25 ms for an almost empty column) is paid once per batch,
+// and its kernels get ncols times the parallelism.  subs[b] (may be null) = constant subtracted
+// from column b's scalars (params_commit_run).
+int32_t msm_run_multi(b200zk_ctx* ctx, const fe_t* const* d_cols, uint32_t ncols, const affine_t* d_bases, size_t n, const MsmPre* pre,
+                      host::HAffine* outs, const fe_t* const* subs) {
+    if (ncols == 0) return B200ZK_OK;
+    if (n == 0) { for (uint32_t b = 0; b < ncols; ++b) outs[b] = {host::HFq::zero(), host::HFq::zero()}; return B200ZK_OK; }
     if (n >= ((size_t)1 << 31)) return fail(ctx, B200ZK_EINVAL, "msm_run", "len must be < 2^31");
     MsmShape s = pre ? pre->shape : msm_plan_shape(n, ctx->msm_force_c);
-    const uint32_t B = (uint32_t)s.nbuckets;
-    const uint32_t nsums = pre ? s.c : s.nwin;              // results handed to the host
+    const uint32_t nsums = pre ? s.c : s.nwin;              // results per column handed to the host
+    const bool tree = pre && s.log_t >= 7;
+    if (ncols > 1 && (!tree || (size_t)ncols * nsums * sizeof(xyzz_t) > ((size_t)60 << 10) || (uint64_t)ncols * n * s.nwin >= ((uint64_t)1 << 32))) {
+        for (uint32_t b = 0; b < ncols; ++b) ZK_TRY(msm_run_multi(ctx, d_cols + b, 1, d_bases, n, pre, outs + b, subs ? subs + b : nullptr));
+        return B200ZK_OK;
+    }
+    const uint32_t NB = (uint32_t)s.nbuckets, B = NB * ncols;
     // workspace layout
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     size_t o_counts = take((size_t)B * 4 + 4), o_offsets = take(((size_t)B + 1) * 4), o_cursor = take((size_t)B * 4);
-    size_t o_entries = take(n * s.nwin * 4);
+    size_t o_entries = take((size_t)ncols * n * s.nwin * 4);
     size_t o_buckets = take((size_t)B * sizeof(xyzz_t));
-    size_t o_partials = take(((size_t)nsums << s.log_t) * sizeof(xyzz_t));
-    size_t o_wsum = take(nsums * sizeof(xyzz_t));
+    size_t o_partials = take((((size_t)nsums * ncols) << s.log_t) * sizeof(xyzz_t));
+    size_t o_wsum = take((size_t)nsums * ncols * sizeof(xyzz_t));
     const uint32_t scan_items = MSM_SCAN_THREADS * MSM_SCAN_PER_THREAD;
     size_t o_bsums = take((size_t)((B + scan_items - 1) / scan_items) * 4);
     size_t o_toff1 = take(((size_t)B + 1) * 4), o_toff2 = take(((size_t)B + 1) * 4);
+    size_t o_tab = take((size_t)ncols * (sizeof(void*) + sizeof(fe_t) + 4));
     ZK_TRY(ws_reserve(ctx, ctx->msm_ws, off));
     char* base = (char*)ctx->msm_ws.p;
     MsmArgs a{};
-    a.scalars = d_scalars; a.bases = d_bases; a.n = (uint32_t)n;
+    a.scalars = d_cols[0]; a.bases = d_bases; a.n = (uint32_t)n;
     a.c = s.c; a.nwin = s.nwin; a.log_t = s.log_t;
     a.pre = pre ? 1 : 0; a.pre_stride = pre ? pre->stride : 0; a.nbuckets = B;
-    a.use_sub = sub ? 1 : 0;
-    if (sub) a.sub = *sub;
+    a.batch = ncols; a.set_buckets = NB;
+    a.use_sub = (ncols == 1 && subs && subs[0]) ? 1 : 0;
+    if (a.use_sub) a.sub = *subs[0];
     a.counts = (uint32_t*)(base + o_counts); a.offsets = (uint32_t*)(base + o_offsets); a.cursor = (uint32_t*)(base + o_cursor);
     a.entries = (uint32_t*)(base + o_entries);
     a.buckets = (xyzz_t*)(base + o_buckets); a.partials = (xyzz_t*)(base + o_partials); a.window_sums = (xyzz_t*)(base + o_wsum);
     uint32_t* d_max = a.counts + B;                         // one extra word after the histogram
     uint32_t* bsums = (uint32_t*)(base + o_bsums);
-
     cudaStream_t st = ctx->stream;
+    if (ncols > 1) {                                        // column pointers, constants and flags, staged through pinned memory
+        // layout (32-byte aligned first): constants [ncols] | column pointers [ncols] | flags [ncols]
+        char* h = (char*)ctx->pinned + ((size_t)60 << 10);      // last 4 KB of the 64 KB staging buffer
+        fe_t* hs = (fe_t*)h;
+        const fe_t** hp = (const fe_t**)(h + ncols * sizeof(fe_t));
+        uint32_t* hf = (uint32_t*)(h + ncols * (sizeof(fe_t) + sizeof(void*)));
+        for (uint32_t b = 0; b < ncols; ++b) {
+            hp[b] = d_cols[b];
+            hf[b] = (subs && subs[b]) ? 1u : 0u;
+            if (hf[b]) memcpy(&hs[b], subs[b], sizeof(fe_t)); else memset(&hs[b], 0, sizeof(fe_t));
+        }
+        ZK_CUDA(ctx, cudaMemcpyAsync(base + o_tab, h, (size_t)ncols * (sizeof(void*) + sizeof(fe_t) + 4), cudaMemcpyHostToDevice, st));
+        a.subs = (const fe_t*)(base + o_tab);
+        a.scalars_tab = (const fe_t* const*)(base + o_tab + ncols * sizeof(fe_t));
+        a.subs_on = (const uint32_t*)(base + o_tab + ncols * (sizeof(fe_t) + sizeof(void*)));
+    }
+
+    const uint32_t blocks_per_col = nb(n, MSM_DIGIT_THREADS);
     ZK_CUDA(ctx, cudaMemsetAsync(a.counts, 0, (size_t)B * 4 + 4, st));
-    msm_count_kernel<<<nb(n, MSM_DIGIT_THREADS), MSM_DIGIT_THREADS, 0, st>>>(a);
+    msm_count_kernel<<<blocks_per_col * ncols, MSM_DIGIT_THREADS, 0, st>>>(a, blocks_per_col);
     ctx->launches++;
     run_scan(ctx, ScanArgs{a.counts, a.offsets, a.cursor, bsums, d_max, B, 0, 0});
     ZK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, d_max, 4, cudaMemcpyDeviceToHost, st));
-    msm_scatter_kernel<<<nb(n, MSM_DIGIT_THREADS), MSM_DIGIT_THREADS, 0, st>>>(a);
+    ZK_CUDA(ctx, cudaMemcpyAsync((char*)ctx->pinned + 4, a.offsets + B, 4, cudaMemcpyDeviceToHost, st));
+    msm_scatter_kernel<<<blocks_per_col * ncols, MSM_DIGIT_THREADS, 0, st>>>(a, blocks_per_col);
     ctx->launches++;
     ZK_CUDA(ctx, cudaStreamSynchronize(st));
-    const uint32_t maxcnt = *(const uint32_t*)ctx->pinned;
+    const uint32_t maxcnt = ((const uint32_t*)ctx->pinned)[0];
+    const size_t total_entries = ((const uint32_t*)ctx->pinned)[1];
 
     uint32_t fast_max = MSM_FAST_MAX;
     if (const char* e = getenv("B200ZK_MSM_FAST_MAX")) fast_max = (uint32_t)strtoul(e, nullptr, 10);
@@ -226,8 +264,8 @@ int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bas
         // with >= maxcnt / L^level independent tasks (a cube-root split left 10^4 threads with
         // 100-long serial chains: 2.85 ms for one such bucket).
         uint32_t L = seg_min < 2 ? 2 : seg_min;
-        // level k has at most n*W / L^k + B * (1 + 1/L + ...) tasks: both ping-pong buffers hold n*W/L + 2B
-        const size_t t1_bound = n * (size_t)s.nwin / L + B;
+        // level k has at most entries / L^k + B * (1 + 1/L + ...) tasks: both ping-pong buffers hold entries/L + 2B
+        const size_t t1_bound = total_entries / L + B;
         const size_t pcap = t1_bound + B;
         ZK_TRY(ws_reserve(ctx, ctx->msm_ws2, 2 * pcap * sizeof(xyzz_t) + (size_t)(B + 1) * 4 + 1024));
         xyzz_t* pbuf[2] = {(xyzz_t*)ctx->msm_ws2.p, (xyzz_t*)ctx->msm_ws2.p + pcap};
@@ -253,12 +291,12 @@ int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bas
         msm_combine_bucket_kernel<<<nb(B, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(t3);
         ctx->launches++;
     }
-    size_t nred = (size_t)nsums << s.log_t;
-    if (pre && s.log_t >= 7) {
+    size_t nred = ((size_t)nsums << s.log_t) * ncols;
+    if (tree) {
         msm_reduce_bits_tree_kernel<<<(unsigned)(nred / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
         MsmArgs af = a;
         af.log_t = s.log_t - 7;                                  // partials per bit after the in-block tree
-        msm_fold_kernel<<<nsums, af.log_t >= 5 ? 32 : (1u << af.log_t), 0, st>>>(af);
+        msm_fold_kernel<<<nsums * ncols, af.log_t >= 5 ? 32 : (1u << af.log_t), 0, st>>>(af);
     } else {
         if (pre) msm_reduce_bits_kernel<<<nb(nred, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
         else msm_reduce_kernel<<<nb(nred, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);
@@ -266,10 +304,18 @@ int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bas
     }
     ctx->launches += 2;
     ZK_CUDA(ctx, cudaGetLastError());
-    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, a.window_sums, nsums * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, a.window_sums, (size_t)nsums * ncols * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
     ZK_CUDA(ctx, cudaStreamSynchronize(st));
-    *out = pre ? msm_finish_bits(ctx->pinned, s.c) : msm_finish(ctx->pinned, s.nwin, s.c);
+    for (uint32_t b = 0; b < ncols; ++b) {
+        const char* ws = (const char*)ctx->pinned + (size_t)b * nsums * sizeof(xyzz_t);
+        outs[b] = pre ? msm_finish_bits(ws, s.c) : msm_finish(ws, s.nwin, s.c);
+    }
     return B200ZK_OK;
+}
+
+int32_t msm_run_ex(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, const MsmPre* pre, host::HAffine* out,
+                   const fe_t* sub) {
+    return msm_run_multi(ctx, &d_scalars, 1, d_bases, n, pre, out, sub ? &sub : nullptr);
 }
 
 int32_t msm_run(b200zk_ctx* ctx, const fe_t* d_scalars, const affine_t* d_bases, size_t n, host::HAffine* out) {

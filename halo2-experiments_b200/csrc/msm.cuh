@@ -43,6 +43,12 @@ struct MsmArgs {
     uint32_t nbuckets;          // W << (c-1), or 1 << (c-1) in fixed-base mode
     uint32_t use_sub;           // scalars are taken as scalars[i] - sub (see params_commit_run: constant-run columns)
     fe_t sub;
+    // Batched commits (fixed-base mode): `batch` columns of n scalars over the same table, column b
+    // owning buckets [b * set_buckets, (b + 1) * set_buckets); nbuckets = batch * set_buckets.
+    uint32_t batch, set_buckets;
+    const fe_t* const* scalars_tab;     // device array of `batch` column pointers (batch > 1)
+    const fe_t* subs;                   // device, per column; subs_on[b] != 0 selects it
+    const uint32_t* subs_on;
     uint32_t* counts;           // [W << (c-1)]
     uint32_t* offsets;          // [(W << (c-1)) + 1]
     uint32_t* cursor;           // [W << (c-1)]

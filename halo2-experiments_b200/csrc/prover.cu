@@ -323,6 +323,16 @@ static int32_t commit_dev(b200zk_pk* pk, const fe_t* d_poly, size_t len, bool la
     PhaseTimer t(pk, PH_MSM);
     return params_commit_run(pk->params, d_poly, len, lagrange, out);
 }
+// several full-length columns in one batched launch sequence (msm_run_multi), <= 24 at a time
+static int32_t commit_multi_dev(b200zk_pk* pk, const std::vector<const fe_t*>& cols, size_t len, bool lagrange, std::vector<HAffine>& outs) {
+    PhaseTimer t(pk, PH_MSM);
+    outs.resize(cols.size());
+    for (size_t b = 0; b < cols.size(); b += 24) {
+        uint32_t m = (uint32_t)std::min<size_t>(24, cols.size() - b);
+        ZK_TRY(params_commit_multi(pk->params, cols.data() + b, m, len, lagrange, outs.data() + b));
+    }
+    return B200ZK_OK;
+}
 static int32_t lagrange_to_coeff(b200zk_pk* pk, fe_t* d_a) {
     PhaseTimer t(pk, PH_NTT);
     HFr post[3] = {pk->dom->ifft_divisor, pk->dom->ifft_divisor, pk->dom->ifft_divisor};
@@ -521,10 +531,12 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         ZK_CUDA(ctx, cudaMemcpyAsync(advice_values + (size_t)c * n, advice_host[c], n * sizeof(fe_t), cudaMemcpyHostToDevice, st));
     for (uint32_t c = 0; c < A; ++c) ZK_CUDA(ctx, copy_rows(advice_values + (size_t)c * n + usable, rng_take(bf + 1), bf + 1));
     rng_take(A);                                                  // Blind per column (unused by KZG)
-    for (uint32_t c = 0; c < A; ++c) {
-        HAffine pt;
-        ZK_TRY(commit_dev(pk, advice_values + (size_t)c * n, n, true, &pt));
-        tr.write_point(pt);
+    {
+        std::vector<const fe_t*> cols;
+        std::vector<HAffine> pts;
+        for (uint32_t c = 0; c < A; ++c) cols.push_back(advice_values + (size_t)c * n);
+        ZK_TRY(commit_multi_dev(pk, cols, n, true, pts));
+        for (uint32_t c = 0; c < A; ++c) tr.write_point(pts[c]);
     }
     HFr ch[4];                                                    // theta, beta, gamma, y
     ch[EXF_THETA] = tr.squeeze_challenge();
@@ -542,16 +554,19 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         }
         ZK_CUDA(ctx, copy_rows(pin + usable, rng_take(bf + 1), bf + 1));
         ZK_CUDA(ctx, copy_rows(ptab + usable, rng_take(bf + 1), bf + 1));
-        HAffine c_in, c_tab;
         ZK_CUDA(ctx, copy_rows(pin_poly, pin, n));
         ZK_TRY(lagrange_to_coeff(pk, pin_poly));
         rng_take(1);
-        ZK_TRY(commit_dev(pk, pin, n, true, &c_in));
         ZK_CUDA(ctx, copy_rows(ptab_poly, ptab, n));
         ZK_TRY(lagrange_to_coeff(pk, ptab_poly));
         rng_take(1);
-        ZK_TRY(commit_dev(pk, ptab, n, true, &c_tab));
-        tr.write_point(c_in); tr.write_point(c_tab);
+    }
+    if (L) {                                                      // permuted input / table commitments of all lookups, one batch
+        std::vector<const fe_t*> cols;
+        std::vector<HAffine> pts;
+        for (uint32_t l = 0; l < L; ++l) { cols.push_back(LK(l, 2)); cols.push_back(LK(l, 3)); }
+        ZK_TRY(commit_multi_dev(pk, cols, n, true, pts));
+        for (auto& pt : pts) tr.write_point(pt);
     }
     {
         uint32_t err = 0;
@@ -598,9 +613,16 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
             ZK_CUDA(ctx, cudaStreamSynchronize(st));
             last_z = HFr::from_limbs(ctx->pinned);
             rng_take(1);
-            HAffine pt;
-            ZK_TRY(commit_dev(pk, z, n, true, &pt));
-            tr.write_point(pt);
+        }
+        if (S) {                                                  // the S grand products: one batch of commitments, then coefficients and cosets
+            std::vector<const fe_t*> cols;
+            std::vector<HAffine> pts;
+            for (uint32_t s = 0; s < S; ++s) cols.push_back(perm_polys + (size_t)s * n);
+            ZK_TRY(commit_multi_dev(pk, cols, n, true, pts));
+            for (auto& pt : pts) tr.write_point(pt);
+        }
+        for (uint32_t s = 0; s < S; ++s) {
+            fe_t* z = perm_polys + (size_t)s * n;
             ZK_TRY(lagrange_to_coeff(pk, z));
             ZK_TRY(coeff_to_extended(pk, z, perm_cosets + (size_t)s * ext));
         }
@@ -621,10 +643,14 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         }
         ZK_CUDA(ctx, copy_rows(z + (n - bf), rng_take(bf), bf));
         rng_take(1);
-        HAffine pt;
-        ZK_TRY(commit_dev(pk, z, n, true, &pt));
-        tr.write_point(pt);
-        ZK_TRY(lagrange_to_coeff(pk, z));
+    }
+    if (L) {
+        std::vector<const fe_t*> cols;
+        std::vector<HAffine> pts;
+        for (uint32_t l = 0; l < L; ++l) cols.push_back(LK(l, 6));
+        ZK_TRY(commit_multi_dev(pk, cols, n, true, pts));
+        for (auto& pt : pts) tr.write_point(pt);
+        for (uint32_t l = 0; l < L; ++l) ZK_TRY(lagrange_to_coeff(pk, LK(l, 6)));
     }
 
     // ---- step 8: vanishing argument, random polynomial
@@ -710,10 +736,12 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     }
     const uint32_t q = pk->q;
     rng_take(q);                                                  // h_blinds
-    for (uint32_t i = 0; i < q; ++i) {
-        HAffine pt;
-        ZK_TRY(commit_dev(pk, h + (size_t)i * n, n, false, &pt));
-        tr.write_point(pt);
+    {
+        std::vector<const fe_t*> cols;
+        std::vector<HAffine> pts;
+        for (uint32_t i = 0; i < q; ++i) cols.push_back(h + (size_t)i * n);
+        ZK_TRY(commit_multi_dev(pk, cols, n, false, pts));
+        for (auto& pt : pts) tr.write_point(pt);
     }
     if (rpos != draws) return fail(ctx, B200ZK_EINVAL, "create_proof", "internal: rng draw count mismatch");
     const HFr x = tr.squeeze_challenge();
