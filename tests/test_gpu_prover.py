@@ -104,6 +104,16 @@ def test_real_merkle_sum_tree_k9(zk, backend, orc):
     _run(zk, backend, orc, job, check_verify=True, pairing=True)
 
 
+def test_real_merkle_sum_tree_k11(zk, backend, orc):
+    """Same circuit with a 9-level path at k = 11: large enough for the batched commits, the
+    constant-run columns (grand products equal to one value on every unused row) and the warp-level
+    NTT to be the code that runs; proof bytes identical to the oracle."""
+    fe, chips = _frontend(zk)
+    job = chips.merkle_sum_tree_job(11, levels=9, seed=5)
+    assert fe.mock_verify(job, rows=range(job.rows_used + 2)) == []
+    _run(zk, backend, orc, job, check_verify=False)
+
+
 @pytest.mark.parametrize("k,levels", [(10, 5), (14, 13)])
 def test_real_merkle_v3(zk, backend, orc, k, levels):
     """BASELINE config 2: Poseidon Merkle tree v3 full prove (k = 14), bytes identical to the CPU path."""
