@@ -5,18 +5,23 @@
 // The group element returned is independent of the bucket method, so parity with
 // the CPU path is bit-exact after affine normalisation.
 //
-// Device pipeline (all state in HBM, one launch each):
-//   1. digits+count : scalar -> canonical (one Montgomery mul by 1), W signed
-//                     c-bit digits, histogram of (window, |digit|) keys
+// Device pipeline (all state in HBM; launch side in msm.cu):
+//   1. digits+count : scalar -> canonical (one Montgomery mul by 1), W signed c-bit digits,
+//                     histogram of the bucket keys.  One warp walks 32 scalars in lockstep: all-zero
+//                     warps leave at once, a window in which all lanes hit one bucket costs one atomic
 //   2. scan         : exclusive prefix sum of the histogram
 //   3. scatter      : counting sort of (point index, sign) entries by key
-//   4. accumulate   : one thread per bucket, XYZZ mixed additions (the IMAD-bound
-//                     kernel; N*W additions of 8M+2S)
-//   5. reduce       : per window, chunked running sums  sum_v v*B_v
-//   6. fold         : per window tree sum of the chunk results
-// The W window sums (W*128 B) go back to the host, which does the last W*c
-// doublings — a strictly serial chain that a CPU core finishes ~10x sooner than
-// one GPU thread — and the affine normalisation for the transcript.
+//   4. accumulate   : XYZZ mixed additions (the IMAD-bound kernel; N*W additions of 8M+2S), one
+//                     thread per bucket when no bucket is long, else balanced levels of <= 16 items
+//                     per task (entries -> partials -> ... -> bucket)
+//   5. reduce       : sum_v v*B_v — per window by chunked running sums, or, with the fixed-base
+//                     tables of an SRS (all windows share one bucket set), by bit decomposition with
+//                     the first seven fold levels inside the block
+//   6. fold         : tree sum of the remaining partials
+// Several columns over the same SRS run as ONE such sequence (msm_run_multi: column b owns bucket
+// set b), so the latency-bound tail is paid once per batch.  The per-window / per-bit sums go back to
+// the host, which does the last doublings — a strictly serial chain that a CPU core finishes ~10x
+// sooner than one GPU thread — and the affine normalisation for the transcript.
 #pragma once
 #include "curve.cuh"
 #include "blockexec.cuh"
