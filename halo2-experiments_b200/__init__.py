@@ -403,6 +403,14 @@ class ParamsKZG:
         self.backend._check(lib().b200zk_commit_lagrange(self._h, _p(poly), ctypes.c_size_t(poly.shape[0]), _p(out)))
         return out
 
+    def commit_many_dev(self, d_polys, n, lagrange):
+        """Commitments to several device-resident polynomials of length n (one batched launch sequence)."""
+        ptrs = (ctypes.c_void_p * max(len(d_polys), 1))(*[d.ptr for d in d_polys])
+        out = np.zeros((len(d_polys), 12), dtype=np.uint64)
+        self.backend._check(lib().b200zk_commit_many_dev(self._h, ptrs, ctypes.c_uint32(len(d_polys)), ctypes.c_size_t(n),
+                                                         ctypes.c_int32(1 if lagrange else 0), _p(out)))
+        return out
+
     def commit_dev(self, d_poly, n, lagrange):
         out = np.zeros(12, dtype=np.uint64)
         self.backend._check(lib().b200zk_commit_dev(self._h, d_poly.ptr, ctypes.c_size_t(n), ctypes.c_int32(1 if lagrange else 0), _p(out)))

@@ -533,6 +533,20 @@ int32_t b200zk_commit_dev(b200zk_params* p, const void* d_poly, size_t len, int3
     return B200ZK_OK;
 }
 
+int32_t b200zk_commit_many_dev(b200zk_params* p, const void* const* d_polys, uint32_t count, size_t len, int32_t lagrange,
+                               void* out_g1_host) {
+    if (!p || (count && (!d_polys || !out_g1_host)) || len > ((size_t)1 << p->k)) return B200ZK_EINVAL;
+    for (uint32_t i = 0; i < count; ++i) if (len && !d_polys[i]) return B200ZK_EINVAL;
+    ZK_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    std::vector<host::HAffine> r(count);
+    for (uint32_t b = 0; b < count; b += 24) {
+        uint32_t m = std::min<uint32_t>(24, count - b);
+        ZK_TRY(params_commit_multi(p, (const fe_t* const*)d_polys + b, m, len, lagrange != 0, r.data() + b));
+    }
+    for (uint32_t i = 0; i < count; ++i) write_g1(r[i], (char*)out_g1_host + (size_t)i * 96);
+    return B200ZK_OK;
+}
+
 static int32_t commit_host(b200zk_params* p, const void* poly, size_t len, int32_t lagrange, void* out_g1) {
     if (!p || !out_g1 || (len && !poly) || len > ((size_t)1 << p->k)) return B200ZK_EINVAL;
     b200zk_ctx* ctx = p->ctx;

@@ -127,6 +127,11 @@ int32_t b200zk_params_read(b200zk_params* p, void* g_out, void* g_lagrange_out);
 int32_t b200zk_commit(b200zk_params* p, const void* poly, size_t len, void* out_g1);
 int32_t b200zk_commit_lagrange(b200zk_params* p, const void* poly, size_t len, void* out_g1);
 int32_t b200zk_commit_dev(b200zk_params* p, const void* d_poly, size_t len, int32_t lagrange, void* out_g1_host);
+/* `count` polynomials of the same length in one batched launch sequence — what create_proof's
+ * column loops (`advice.iter().map(|poly| params.commit_lagrange(poly, blind))`, plonk/prover.rs)
+ * amount to; d_polys: host array of `count` device pointers, out: count * 96 bytes on the host. */
+int32_t b200zk_commit_many_dev(b200zk_params* p, const void* const* d_polys, uint32_t count, size_t len, int32_t lagrange,
+                               void* out_g1_host);
 
 /* ---- arithmetic::eval_polynomial / kate_division, ff::BatchInvert -----------------
  * eval_polynomial(poly, x) -> Fr (Horner);  kate_division(a, b): quotient of a(X) by

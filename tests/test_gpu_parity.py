@@ -253,6 +253,40 @@ def test_best_multiexp_skewed_columns(backend, orc, kind):
         params.close()
 
 
+@pytest.mark.parametrize("lagrange", [False, True])
+def test_commit_many_matches_single_commits(zk, backend, orc, lagrange):
+    """Batched commits (one bucket set per column): seven columns of different character — dense,
+    zero, constant-run (grand-product like), sorted bytes, sparse, all-equal, bits — against the oracle."""
+    k = 14
+    n = 1 << k
+    g, gl = _setup(orc, k)
+    params = zk.ParamsKZG.load(backend, k, g, gl)
+    rng = np.random.Generator(np.random.PCG64(21))
+    small = lambda v: orc.ints_to_mont([int(x) for x in np.unique(v)])[np.unique(v, return_inverse=True)[1]]
+    cols = [orc.random_fr(n, 31)]
+    cols.append(np.zeros((n, 4), dtype=np.uint64))
+    z = np.repeat(orc.random_fr(1, 32), n, axis=0); z[:500] = orc.random_fr(500, 33); z[n - 6:] = orc.random_fr(6, 34)
+    cols.append(z)
+    cols.append(small(np.sort(rng.integers(0, 256, size=n))))
+    sp = np.zeros((n, 4), dtype=np.uint64); sp[::997] = orc.random_fr(len(sp[::997]), 35)
+    cols.append(sp)
+    cols.append(small(np.full(n, 7)))
+    cols.append(small(rng.integers(0, 2, size=n)))
+    d = [backend.to_device(c) for c in cols]
+    got = params.commit_many_dev(d, n, lagrange)
+    bases = gl if lagrange else g
+    for i, c in enumerate(cols):
+        want = orc.g1_batch_normalize(orc.best_multiexp(c, bases))[0]
+        if not want.any():                                   # identity: G1 (0, 1, 0)
+            assert not got[i][:4].any() and not got[i][8:].any(), f"column {i}"
+        else:
+            assert np.array_equal(_affine(got[i]), want), f"column {i}"
+        assert np.array_equal(got[i], params.commit_dev(d[i], n, lagrange)), f"column {i} vs single commit"
+    for b in d:
+        b.free()
+    params.close()
+
+
 @pytest.mark.parametrize("log_n,log_r,world", [(10, 4, 2), (12, 6, 4), (16, 8, 8), (20, 10, 8)])
 def test_four_step_sharded_ntt_kernels(zk, backend, orc, log_n, log_r, world):
     """Column step / row step kernels of the sharded four-step NTT, with the `world` ranks emulated
