@@ -10,7 +10,12 @@
   * `MerkleSumTreeChip`    /root/reference/src/chips/merkle_sum_tree.rs:32-366;
   * `MerkleSumTreeCircuit` /root/reference/src/circuits/merkle_sum_tree.rs:16-110;
   * `MerkleTreeV3Chip`     /root/reference/src/chips/merkle_v3.rs:27-172;
-  * `MerkleTreeV3Circuit`  /root/reference/src/circuits/merkle_v3.rs:11-62.
+  * `MerkleTreeV3Circuit`  /root/reference/src/circuits/merkle_v3.rs:11-62;
+  * `LessThanChip/Circuit` /root/reference/src/chips/less_than.rs:33-88, circuits/less_than.rs:8-41
+                           (dynamic lookup into an advice table filled from the instance column);
+  * `IsZeroChip`           /root/reference/src/chips/is_zero.rs;
+  * `SafeAccumulatorChip/Circuit`  /root/reference/src/chips/safe_accumulator.rs:33-271,
+                           circuits/safe_accumulator.rs:7-91 (degree-17 range-check gates).
 
 Column allocation order, query order, gate order, region order and copy-constraint order follow
 the Rust sources statement by statement: they determine the query lists, the selector compression,
@@ -537,3 +542,204 @@ def merkle_v3_job(k, levels=13, seed=2):
     indices = [int(b) for b in rng.integers(0, 2, size=levels)]
     root = compute_merkle_root(leaf, elements, indices)
     return synthesize_job(MerkleTreeV3Circuit(leaf, elements, indices), k, [[leaf, root]])
+
+
+# ---------------------------------------------------------------- LessThan (dynamic lookup)
+
+
+class LessThanConfig:
+    pass
+
+
+class LessThanChip:
+    """/root/reference/src/chips/less_than.rs: `input` must appear in `advice_table`, an advice column
+    filled from the instance column (a dynamic lookup, no gates)."""
+
+    def __init__(self, config):
+        self.config = config
+
+    @staticmethod
+    def configure(meta, input_col, table):
+        cfg = LessThanConfig()
+        cfg.input, cfg.table = input_col, table
+        cfg.advice_table = meta.advice_column()
+        meta.enable_equality(table)
+        meta.enable_equality(cfg.advice_table)
+        meta.lookup_any("dynamic lookup check", [(meta.query(input_col, 0), meta.query(cfg.advice_table, 0))])
+        return cfg
+
+    def assign(self, layouter, value):
+        cfg = self.config
+
+        def assign(region):
+            for i in range(1000):
+                region.assign_advice_from_instance(cfg.table, i, cfg.advice_table, i)
+            region.assign_advice(cfg.input, 0, value)
+
+        layouter.assign_region("less than assignment", assign)
+
+
+class LessThanCircuit:
+    """/root/reference/src/circuits/less_than.rs:8-41; instance column = 0 .. target-1."""
+
+    def __init__(self, value):
+        self.value = value
+
+    @staticmethod
+    def configure(meta):
+        input_col = meta.advice_column()
+        table = meta.instance_column()
+        return LessThanChip.configure(meta, input_col, table)
+
+    def synthesize(self, config, layouter):
+        LessThanChip(config).assign(layouter, self.value)
+
+
+# ---------------------------------------------------------------- SafeAccumulator
+
+
+def range_check(value, rng):
+    """chips/utils.rs::range_check: value * (1 - value) * ... * (range-1 - value), degree `range`."""
+    acc = value
+    for i in range(1, rng):
+        acc = acc * (_const(i) - value)
+    return acc
+
+
+class IsZeroConfig:
+    def expr(self):
+        return self.is_zero_expr
+
+
+class IsZeroChip:
+    """/root/reference/src/chips/is_zero.rs."""
+
+    def __init__(self, config):
+        self.config = config
+
+    @staticmethod
+    def configure(meta, q_enable, value, value_inv):
+        cfg = IsZeroConfig()
+        cfg.value_inv = value_inv
+        v = value(meta)
+        q = q_enable(meta)
+        inv = meta.query(value_inv, 0)
+        cfg.is_zero_expr = _const(1) - v * inv
+        meta.create_gate("is_zero", [q * v * cfg.is_zero_expr])
+        return cfg
+
+    def assign(self, region, offset, value):
+        value %= R_MOD
+        region.assign_advice(self.config.value_inv, offset, pow(value, -1, R_MOD) if value else 0)
+
+
+class SafeAccumulatorConfig:
+    pass
+
+
+class SafeAccumulatorChip:
+    """/root/reference/src/chips/safe_accumulator.rs (MAX_BITS-bit limbs in ACC_COLS columns)."""
+
+    def __init__(self, config):
+        self.config = config
+
+    @staticmethod
+    def configure(meta, max_bits, update_value, left_most_inv, add_carries, accumulate, selector, instance):
+        acc_cols = len(accumulate)
+        bool_selector, add_carry_selector, overflow_check_selector = selector
+        cfg = SafeAccumulatorConfig()
+        cfg.is_zero = IsZeroChip.configure(meta, lambda m: m.query_selector(overflow_check_selector),
+                                           lambda m: m.query(accumulate[0], 0), left_most_inv)
+        for col in accumulate:
+            meta.enable_equality(col)
+        for col in add_carries:
+            meta.enable_equality(col)
+        meta.enable_equality(instance)
+
+        s = meta.query_selector(bool_selector)
+        polys = []
+        for carries in add_carries:
+            a = meta.query(carries, 0)
+            polys.append(s * a * (_const(1) - a))
+        meta.create_gate("bool constraint", polys)
+
+        s_add = meta.query_selector(add_carry_selector)
+        s_over = meta.query_selector(overflow_check_selector)
+        value = meta.query(update_value, 0)
+        previous_acc = [meta.query(accumulate[i], -1) for i in range(acc_cols)]
+        carries_acc = [meta.query(add_carries[i], 0) for i in range(acc_cols)]
+        updated_acc = [meta.query(accumulate[i], 0) for i in range(acc_cols)]
+        shift = _const(1 << max_bits)
+        rng = 1 << max_bits
+        polys = [s_add * ((value + previous_acc[-1]) - ((carries_acc[-1] * shift) + updated_acc[-1]))]
+        polys.append(s_add * range_check(value, rng))
+        polys += [s_add * ((updated_acc[i] + (carries_acc[i] * shift)) - (previous_acc[i] + carries_acc[i + 1]))
+                  for i in range(acc_cols - 1)]
+        polys.append(s_over * (_const(1) - cfg.is_zero.expr()))
+        polys += [s_over * range_check(w, rng) for w in previous_acc]
+        polys += [s_over * range_check(w, rng) for w in updated_acc]
+        meta.create_gate("accumulation constraint", polys)
+
+        cfg.max_bits, cfg.update_value, cfg.left_most_inv = max_bits, update_value, left_most_inv
+        cfg.add_carries, cfg.accumulate, cfg.instance = list(add_carries), list(accumulate), instance
+        cfg.selector = [add_carry_selector, overflow_check_selector]
+        return cfg
+
+    def assign(self, layouter, offset, update_value, accumulated_values):
+        cfg = self.config
+        acc_cols, max_bits = len(cfg.accumulate), cfg.max_bits
+        is_zero_chip = IsZeroChip(cfg.is_zero)
+
+        def assign(region):
+            region.enable_selector(cfg.selector[0], offset + 1)
+            region.enable_selector(cfg.selector[1], offset + 1)
+            total = update_value % R_MOD
+            region.assign_advice(cfg.update_value, 1, update_value)
+            for idx, val in enumerate(accumulated_values):
+                region.assign_advice(cfg.accumulate[idx], 0, val)
+            for idx in reversed(range(acc_cols)):
+                shift_bits = max_bits * ((acc_cols - 1) - idx)
+                total += (accumulated_values[idx] % R_MOD) << shift_bits
+                carry = 1 if (total >= (1 << (max_bits + shift_bits)) and idx > 0) else 0
+                region.assign_advice(cfg.add_carries[idx], offset + 1, carry)
+            limbs = [(total >> (max_bits * i)) & ((1 << max_bits) - 1) for i in range(acc_cols)]   # decompose_bigInt_to_ubits
+            cells, updated = [], [0] * acc_cols
+            left_most_idx = acc_cols - 1
+            for i, v in enumerate(limbs):
+                if i == left_most_idx:
+                    is_zero_chip.assign(region, 1, v)
+                cells.append(region.assign_advice(cfg.accumulate[left_most_idx - i], offset + 1, v))
+                updated[left_most_idx - i] = v
+            return cells, updated
+
+        return layouter.assign_region("calculate accumulates", assign)
+
+    def expose_public(self, layouter, cell, row):
+        layouter.constrain_instance(cell, self.config.instance, row)
+
+
+class SafeAccumulatorCircuit:
+    """/root/reference/src/circuits/safe_accumulator.rs:7-91: 4-bit limbs in 4 columns; public
+    inputs = the updated accumulator limbs."""
+
+    def __init__(self, values, accumulated_value):
+        self.values, self.accumulated_value = list(values), list(accumulated_value)
+
+    @staticmethod
+    def configure(meta):
+        new_value = meta.advice_column()
+        left_most_acc_inv = meta.advice_column()
+        carry_cols = [meta.advice_column() for _ in range(4)]
+        acc_cols = [meta.advice_column() for _ in range(4)]
+        add_selector, overflow_selector, boolean_selector = meta.selector(), meta.selector(), meta.selector()
+        instance = meta.instance_column()
+        return SafeAccumulatorChip.configure(meta, 4, new_value, left_most_acc_inv, carry_cols, acc_cols,
+                                             [boolean_selector, add_selector, overflow_selector], instance)
+
+    def synthesize(self, config, layouter):
+        chip = SafeAccumulatorChip(config)
+        cells, previous = chip.assign(layouter, 0, self.values[0], self.accumulated_value)
+        for i, v in enumerate(self.values[1:]):
+            cells, previous = chip.assign(layouter, i, v, previous)
+        for i, cell in enumerate(reversed(cells)):
+            chip.expose_public(layouter, cell, i)

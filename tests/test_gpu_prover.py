@@ -156,3 +156,11 @@ def test_real_merkle_sum_tree_k20_verifies(zk, backend, orc):
     wrong = [list(job.instances[0])]
     wrong[0][3] += 1                                  # assets_sum
     assert not OP.verify_full(s_int, None, vk, wrong, proof, job.transcript_repr)
+
+
+def test_real_less_than_and_safe_accumulator(zk, backend, orc):
+    """The other circuits the backend must prove unchanged: LessThan (dynamic lookup into an advice
+    table, 800 public inputs, k = 10) and SafeAccumulator (degree-17 range-check gates, k = 8)."""
+    fe, chips = _frontend(zk)
+    _run(zk, backend, orc, fe.synthesize_job(chips.LessThanCircuit(755), 10, [list(range(800))]), check_verify=True)
+    _run(zk, backend, orc, fe.synthesize_job(chips.SafeAccumulatorCircuit([1, 3], [0, 0, 14, 13]), 8, [[0, 0, 15, 1]]), check_verify=True)
