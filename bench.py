@@ -314,6 +314,7 @@ def run_gpu(args):
     launches = (be.launch_count() - l0) // args.steps
     if args.workload == "prove":
         extra["phase_ms"] = pk.last_phase_ms()
+        extra["phase_note"] = "device time per phase; the advice-coset NTTs run on a side stream concurrently with the lookup / permutation phases, so the phases overlap and sum to more than the step"
     # ---- end-to-end region: host buffers through the C ABI ---------------------------
     for _ in range(2):
         step_e2e()

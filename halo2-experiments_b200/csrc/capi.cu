@@ -169,7 +169,14 @@ int32_t b200zk_ctx_create(int32_t device, b200zk_ctx** out) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return B200ZK_ENODEV; }
     ctx->sm_count = prop.multiProcessorCount;
     if (prop.major < 10) { delete ctx; return B200ZK_ENODEV; }     // sm_100a code only
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200ZK_ECUDA; }
+    // the main stream outranks the side stream: its (often small, latency-bound) kernels take the
+    // block slots that free up before the side stream's big NTT grids refill them
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete ctx; return B200ZK_ECUDA; }
+    if (cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return B200ZK_ECUDA; }
     for (auto& e : ctx->events) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return B200ZK_ECUDA; }
     if (cudaHostAlloc(&ctx->pinned, 1 << 16, cudaHostAllocDefault) != cudaSuccess) { delete ctx; return B200ZK_ECUDA; }
     *out = ctx;
@@ -181,10 +188,13 @@ void b200zk_ctx_destroy(b200zk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->ntt_plans) { cudaFree(kv.second.roots); cudaFree(kv.second.tw_lo); cudaFree(kv.second.tw_hi); cudaFree(kv.second.tw_full); }
-    for (Workspace* w : {&ctx->ntt_scratch, &ctx->msm_ws, &ctx->msm_ws2, &ctx->lookup_ws, &ctx->io_a, &ctx->io_b, &ctx->poly_ws, &ctx->poly_heads, &ctx->poly_batch, &ctx->setup_ws}) if (w->p) cudaFree(w->p);
+    for (Workspace* w : {&ctx->ntt_scratch, &ctx->ntt_scratch2, &ctx->msm_ws, &ctx->msm_ws2, &ctx->lookup_ws, &ctx->io_a, &ctx->io_b, &ctx->poly_ws, &ctx->poly_heads, &ctx->poly_batch, &ctx->setup_ws}) if (w->p) cudaFree(w->p);
     if (ctx->d_gen_table) cudaFree(ctx->d_gen_table);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto& e : ctx->events) if (e) cudaEventDestroy(e);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

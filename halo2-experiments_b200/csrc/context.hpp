@@ -35,13 +35,15 @@ struct Workspace {
 struct b200zk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;                                    // side stream: work independent of the transcript (advice cosets)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     uint64_t launches = 0;
     cudaEvent_t events[64] = {};
     int sm_count = 148;
     int msm_force_c = 0;
     std::map<std::array<uint64_t, 5>, b200zk::NttPlan> ntt_plans;     // key: log_n + omega limbs
-    b200zk::Workspace ntt_scratch, msm_ws, msm_ws2, io_a, io_b, poly_ws, poly_heads, poly_batch, setup_ws, lookup_ws;
+    b200zk::Workspace ntt_scratch, ntt_scratch2, msm_ws, msm_ws2, io_a, io_b, poly_ws, poly_heads, poly_batch, setup_ws, lookup_ws;
     b200zk::affine_t* d_gen_table = nullptr;                          // fixed-base table of the G1 generator (setup.cu)
     void* pinned = nullptr;                                            // small pinned staging (results)
 };

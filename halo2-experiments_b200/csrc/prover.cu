@@ -452,6 +452,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     const CsDesc& cs = pk->cs;
     const b200zk_domain* dom = pk->dom;
     cudaStream_t st = ctx->stream;
+    cudaStreamSynchronize(ctx->stream2);                          // nothing of an earlier (failed) proof may still be writing the arena
     const size_t n = pk->n, ext = pk->ext_n;
     const uint32_t A = cs.A, I = cs.I, F = cs.F, L = pk->L, S = pk->S, bf = cs.bf;
     const size_t usable = n - (bf + 1);
@@ -537,6 +538,26 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         for (uint32_t c = 0; c < A; ++c) cols.push_back(advice_values + (size_t)c * n);
         ZK_TRY(commit_multi_dev(pk, cols, n, true, pts));
         for (uint32_t c = 0; c < A; ++c) tr.write_point(pts[c]);
+    }
+    // ---- step 10 (moved up): advice polynomials and cosets depend on nothing the transcript still has
+    // to produce, so they run on the side stream while the lookup / permutation arguments — sorts,
+    // scans, batch inversions, the latency-bound tails of their commits — occupy the main one.
+    // evaluate_h (step 11) waits for them.
+    {
+        ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        std::swap(ctx->stream, ctx->stream2);
+        std::swap(ctx->ntt_scratch, ctx->ntt_scratch2);
+        int32_t rc2 = B200ZK_OK;
+        cudaError_t e2 = cudaMemcpyAsync(advice_polys, advice_values, A * n * sizeof(fe_t), cudaMemcpyDeviceToDevice, ctx->stream);
+        for (uint32_t c = 0; c < A && rc2 == B200ZK_OK; ++c) rc2 = lagrange_to_coeff(pk, advice_polys + (size_t)c * n);
+        for (uint32_t c = 0; c < A && rc2 == B200ZK_OK; ++c) rc2 = coeff_to_extended(pk, advice_polys + (size_t)c * n, advice_cosets + (size_t)c * ext);
+        for (uint32_t c = 0; c < I && rc2 == B200ZK_OK; ++c) rc2 = coeff_to_extended(pk, inst_polys + (size_t)c * n, inst_cosets + (size_t)c * ext);
+        if (e2 == cudaSuccess) e2 = cudaEventRecord(ctx->ev_join, ctx->stream);
+        std::swap(ctx->stream, ctx->stream2);
+        std::swap(ctx->ntt_scratch, ctx->ntt_scratch2);
+        if (rc2 != B200ZK_OK) return rc2;
+        ZK_CUDA(ctx, e2);
     }
     HFr ch[4];                                                    // theta, beta, gamma, y
     ch[EXF_THETA] = tr.squeeze_challenge();
@@ -664,11 +685,8 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     ch[EXF_Y] = tr.squeeze_challenge();
     const HFr y = ch[EXF_Y];
 
-    // ---- step 10: advice polynomials and all cosets
-    ZK_CUDA(ctx, copy_rows(advice_polys, advice_values, A * n));
-    for (uint32_t c = 0; c < A; ++c) ZK_TRY(lagrange_to_coeff(pk, advice_polys + (size_t)c * n));
-    for (uint32_t c = 0; c < A; ++c) ZK_TRY(coeff_to_extended(pk, advice_polys + (size_t)c * n, advice_cosets + (size_t)c * ext));
-    for (uint32_t c = 0; c < I; ++c) ZK_TRY(coeff_to_extended(pk, inst_polys + (size_t)c * n, inst_cosets + (size_t)c * ext));
+    // ---- step 10: advice / instance cosets were started on the side stream after the advice commitments
+    ZK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
 
     // ---- step 11: evaluate_h
     {
