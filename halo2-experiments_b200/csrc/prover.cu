@@ -323,6 +323,26 @@ static int32_t commit_dev(b200zk_pk* pk, const fe_t* d_poly, size_t len, bool la
     PhaseTimer t(pk, PH_MSM);
     return params_commit_run(pk->params, d_poly, len, lagrange, out);
 }
+// Side-stream section: between construction and destruction every launch that goes through
+// ctx->stream (NTTs, phase timers) lands on the low-priority side stream, ordered after everything
+// the main stream has enqueued so far; the main stream consumes the results after waiting for
+// ctx->ev_join (re-recorded at the end of every section; the side stream is in-order, so the last
+// record covers all earlier sections).
+struct SideStream {
+    b200zk_ctx* ctx;
+    explicit SideStream(b200zk_ctx* c) : ctx(c) {
+        cudaEventRecord(ctx->ev_fork, ctx->stream);
+        cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0);
+        std::swap(ctx->stream, ctx->stream2);
+        std::swap(ctx->ntt_scratch, ctx->ntt_scratch2);
+    }
+    ~SideStream() {
+        cudaEventRecord(ctx->ev_join, ctx->stream);
+        std::swap(ctx->stream, ctx->stream2);
+        std::swap(ctx->ntt_scratch, ctx->ntt_scratch2);
+    }
+};
+
 // several full-length columns in one batched launch sequence (msm_run_multi), <= 24 at a time
 static int32_t commit_multi_dev(b200zk_pk* pk, const std::vector<const fe_t*>& cols, size_t len, bool lagrange, std::vector<HAffine>& outs) {
     PhaseTimer t(pk, PH_MSM);
@@ -544,20 +564,11 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     // scans, batch inversions, the latency-bound tails of their commits — occupy the main one.
     // evaluate_h (step 11) waits for them.
     {
-        ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-        ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-        std::swap(ctx->stream, ctx->stream2);
-        std::swap(ctx->ntt_scratch, ctx->ntt_scratch2);
-        int32_t rc2 = B200ZK_OK;
-        cudaError_t e2 = cudaMemcpyAsync(advice_polys, advice_values, A * n * sizeof(fe_t), cudaMemcpyDeviceToDevice, ctx->stream);
-        for (uint32_t c = 0; c < A && rc2 == B200ZK_OK; ++c) rc2 = lagrange_to_coeff(pk, advice_polys + (size_t)c * n);
-        for (uint32_t c = 0; c < A && rc2 == B200ZK_OK; ++c) rc2 = coeff_to_extended(pk, advice_polys + (size_t)c * n, advice_cosets + (size_t)c * ext);
-        for (uint32_t c = 0; c < I && rc2 == B200ZK_OK; ++c) rc2 = coeff_to_extended(pk, inst_polys + (size_t)c * n, inst_cosets + (size_t)c * ext);
-        if (e2 == cudaSuccess) e2 = cudaEventRecord(ctx->ev_join, ctx->stream);
-        std::swap(ctx->stream, ctx->stream2);
-        std::swap(ctx->ntt_scratch, ctx->ntt_scratch2);
-        if (rc2 != B200ZK_OK) return rc2;
-        ZK_CUDA(ctx, e2);
+        SideStream side(ctx);
+        ZK_CUDA(ctx, cudaMemcpyAsync(advice_polys, advice_values, A * n * sizeof(fe_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        for (uint32_t c = 0; c < A; ++c) ZK_TRY(lagrange_to_coeff(pk, advice_polys + (size_t)c * n));
+        for (uint32_t c = 0; c < A; ++c) ZK_TRY(coeff_to_extended(pk, advice_polys + (size_t)c * n, advice_cosets + (size_t)c * ext));
+        for (uint32_t c = 0; c < I; ++c) ZK_TRY(coeff_to_extended(pk, inst_polys + (size_t)c * n, inst_cosets + (size_t)c * ext));
     }
     HFr ch[4];                                                    // theta, beta, gamma, y
     ch[EXF_THETA] = tr.squeeze_challenge();
