@@ -742,7 +742,8 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         PhaseTimer t(pk, PH_QUOT);
         ExprArgs ea = expr_args(pk, pk->lookup_prog[l].first, pk->lookup_prog[l].second, true, EXM_LOOKUP_PROD, ch, tv, nullptr);
         expr_kernel<<<nb(ext), PK_THREADS, 0, st>>>(ea);
-        QuotLookupArgs ql{h, to_dev(y), to_dev(beta), to_dev(gamma), pk->l0, pk->l_last, pk->l_active, zc, ac, sc, tv, dom->k, rot_scale, (uint32_t)ext};
+        QuotLookupArgs ql{h, to_dev(y), to_dev(beta), to_dev(gamma), pk->l0, pk->l_last, pk->l_active, zc, ac, sc, tv, dom->k, rot_scale, (uint32_t)ext, {}};
+        { HFr yp = y * y; for (int i = 0; i < 4; ++i) { ql.ypow[i] = to_dev(yp); yp = yp * y; } }
         quot_lookup_kernel<<<nb(ext), PK_THREADS, 0, st>>>(ql);
         ctx->launches += 2;
     }

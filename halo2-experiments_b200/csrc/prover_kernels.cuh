@@ -139,18 +139,27 @@ struct QuotLookupArgs {
     const fe_t *z, *a, *s;              // product / permuted input / permuted table cosets
     const fe_t* table_value;            // (compressed input + beta)(compressed table + gamma)
     uint32_t log_ext, rot_scale, rows;
+    fe_t ypow[4];                       // y^2, y^3, y^4, y^5
 };
+// The five terms upstream folds one by one (h <- h*y + term):
+//   l_0 (1 - z);  l_last (z^2 - z);  l_active (z(wX)(a' + beta)(s' + gamma) - z * table_value);
+//   l_0 (a' - s');  l_active (a' - s')(a' - a'(w^-1 X))
+// are accumulated grouped by their Lagrange factor — the same polynomial value with 13 instead of
+// 15 multiplications per row:
+//   h y^5 + l_0 [(1 - z) y^4 + (a' - s') y] + l_last (z^2 - z) y^3 + l_active [(lhs - z tv) y^2 + (a' - s')(a' - a'_prev)]
 ZK_D void quot_lookup_row(const QuotLookupArgs& q, uint32_t idx) {
     fe_t h = q.h[idx], l0 = q.l0[idx], ll = q.l_last[idx], la = q.l_active[idx];
     fe_t z = q.z[idx], zn = q.z[rot_idx(idx, 1, q.rot_scale, q.log_ext)];
     fe_t a = q.a[idx], ap = q.a[rot_idx(idx, -1, q.rot_scale, q.log_ext)], s = q.s[idx], tv = q.table_value[idx];
     fe_t a_minus_s = Fr::sub(a, s);
-    h = Fr::add(Fr::mul(h, q.y), Fr::mul(Fr::sub(Fr::one(), z), l0));
-    h = Fr::add(Fr::mul(h, q.y), Fr::mul(Fr::sub(Fr::sqr(z), z), ll));
+    fe_t t0 = Fr::add(Fr::mul(Fr::sub(Fr::one(), z), q.ypow[2]), Fr::mul(a_minus_s, q.y));
+    fe_t t1 = Fr::mul(Fr::sub(Fr::sqr(z), z), q.ypow[1]);
     fe_t lhs = Fr::mul(Fr::mul(zn, Fr::add(a, q.beta)), Fr::add(s, q.gamma));
-    h = Fr::add(Fr::mul(h, q.y), Fr::mul(Fr::sub(lhs, Fr::mul(z, tv)), la));
-    h = Fr::add(Fr::mul(h, q.y), Fr::mul(a_minus_s, l0));
-    h = Fr::add(Fr::mul(h, q.y), Fr::mul(Fr::mul(a_minus_s, Fr::sub(a, ap)), la));
+    fe_t t2 = Fr::add(Fr::mul(Fr::sub(lhs, Fr::mul(z, tv)), q.ypow[0]), Fr::mul(a_minus_s, Fr::sub(a, ap)));
+    h = Fr::mul(h, q.ypow[3]);
+    h = Fr::add(h, Fr::mul(l0, t0));
+    h = Fr::add(h, Fr::mul(ll, t1));
+    h = Fr::add(h, Fr::mul(la, t2));
     q.h[idx] = h;
 }
 
