@@ -15,6 +15,10 @@
 // TMP(slot).  In the Merkle Sum Tree circuit the five (state + rc)^5 terms of Pow5Chip's
 // "full round" gate appear in five polynomials each, and the compressed-selector products
 // q(1-q)(2-q).. in every polynomial they gate: 281 -> ~150 multiplications per row.
+// Consecutive gate polynomials with a common factor (every constraint of a gate is
+// selector * poly) are folded as  acc0 <- acc0 * y^m + s * (p_0 y^(m-1) + ... + p_(m-1)):  the inner
+// Horner sum runs in acc1 (SET1 / FOLD), GROUP(m) multiplies it by the factor once — m - 1
+// multiplications less than folding s * p_i one by one.
 // Upstream orders the same arithmetic differently; the value per row is the same field element,
 // hence bit-exact.
 #pragma once
@@ -22,7 +26,7 @@
 
 namespace b200zk {
 
-enum : uint32_t { EX_CONST = 0, EX_FIXED = 1, EX_ADVICE = 2, EX_INSTANCE = 3, EX_NEG = 4, EX_ADD = 5, EX_MUL = 6, EX_SCALE = 7, EX_FOLD = 8, EX_TEE = 9, EX_TMP = 10 };
+enum : uint32_t { EX_CONST = 0, EX_FIXED = 1, EX_ADVICE = 2, EX_INSTANCE = 3, EX_NEG = 4, EX_ADD = 5, EX_MUL = 6, EX_SCALE = 7, EX_FOLD = 8, EX_TEE = 9, EX_TMP = 10, EX_SET1 = 11, EX_GROUP = 12 };
 enum : uint32_t { EXF_THETA = 0, EXF_BETA = 1, EXF_GAMMA = 2, EXF_Y = 3 };
 // output modes
 enum : uint32_t {
@@ -48,6 +52,7 @@ struct ExprArgs {
     uint32_t rows;                      // rows evaluated: n, or C * n on the quotient cosets
     uint32_t rot_scale;                 // 1
     fe_t factors[4];                    // theta, beta, gamma, y
+    fe_t ypow[9];                       // y^m for GROUP(m), m <= 8 (gate programs only)
     uint32_t mode;
     fe_t* out0;
     fe_t* out1;
@@ -81,6 +86,12 @@ ZK_D void expr_eval_row(const ExprArgs& a, uint32_t idx) {
                 const fe_t f = a.factors[arg & 0xf];
                 if ((arg >> 4) == 0) acc0 = Fr::add(Fr::mul(acc0, f), v);
                 else acc1 = Fr::add(Fr::mul(acc1, f), v);
+                break;
+            }
+            case EX_SET1: acc1 = stk[--sp]; break;
+            case EX_GROUP: {
+                fe_t v = stk[--sp];
+                acc0 = Fr::add(Fr::mul(acc0, a.ypow[arg]), Fr::mul(v, acc1));
                 break;
             }
             case EX_TEE: tmp[arg] = stk[sp - 1]; break;

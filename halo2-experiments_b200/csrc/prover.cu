@@ -380,6 +380,7 @@ static ExprArgs expr_args(const b200zk_pk* pk, uint32_t prog_off, uint32_t prog_
     a.rows = extended ? pk->ext_n : pk->n;
     a.rot_scale = 1u;
     for (int i = 0; i < 4; ++i) a.factors[i] = to_dev(ch[i]);
+    { HFr yp = HFr::one(); for (int i = 0; i < 9; ++i) { a.ypow[i] = to_dev(yp); yp = yp * ch[EXF_Y]; } }
     a.mode = mode; a.out0 = out0; a.out1 = out1;
     return a;
 }
@@ -392,7 +393,8 @@ static ExprArgs expr_args(const b200zk_pk* pk, uint32_t prog_off, uint32_t prog_
 // multiplications win.
 struct ExFold { uint32_t off, len, fold_word; };
 
-static bool ex_share_common(const std::vector<uint32_t>& src, const std::vector<ExFold>& items, std::vector<uint32_t>& out) {
+static bool ex_share_common(const std::vector<uint32_t>& src, const std::vector<ExFold>& items, std::vector<uint32_t>& out,
+                            bool group_common_factor = false) {
     struct Node { uint32_t op, arg; int l, r; uint32_t muls; };
     std::vector<Node> nodes;
     std::map<std::array<int64_t, 4>, int> intern;
@@ -444,8 +446,8 @@ static bool ex_share_common(const std::vector<uint32_t>& src, const std::vector<
     for (size_t i = 0; i < cand.size(); ++i) slot[cand[i]] = (int)i;
     std::vector<char> done(nodes.size(), 0);
     // iterative postfix emission: (node, phase)
-    for (size_t k = 0; k < roots.size(); ++k) {
-        std::vector<std::pair<int, int>> stk{{roots[k], 0}};
+    auto emit = [&](int root) {
+        std::vector<std::pair<int, int>> stk{{root, 0}};
         while (!stk.empty()) {
             auto [id, phase] = stk.back(); stk.pop_back();
             const Node& nd = nodes[id];
@@ -459,7 +461,38 @@ static bool ex_share_common(const std::vector<uint32_t>& src, const std::vector<
                 if (slot[id] >= 0) { out.push_back(EX_TEE | ((uint32_t)slot[id] << 8)); done[id] = 1; }
             }
         }
-        out.push_back(items[k].fold_word);
+    };
+    // common factor of two product roots (-1 if none)
+    auto common = [&](int a, int b) {
+        if (nodes[a].op != EX_MUL || nodes[b].op != EX_MUL) return -1;
+        for (int x : {nodes[a].l, nodes[a].r}) if (x == nodes[b].l || x == nodes[b].r) return x;
+        return -1;
+    };
+    for (size_t k = 0; k < roots.size();) {
+        size_t m = 1;
+        int f = -1;
+        if (group_common_factor && k + 1 < roots.size()) {
+            f = common(roots[k], roots[k + 1]);
+            if (f >= 0) {
+                m = 2;
+                while (k + m < roots.size() && m < 8 && nodes[roots[k + m]].op == EX_MUL &&
+                       (nodes[roots[k + m]].l == f || nodes[roots[k + m]].r == f)) ++m;
+            }
+        }
+        if (f < 0) {
+            emit(roots[k]);
+            out.push_back(items[k].fold_word);
+            ++k;
+            continue;
+        }
+        for (size_t j = 0; j < m; ++j) {                        // cofactors into acc1 by Horner in y
+            const Node& nd = nodes[roots[k + j]];
+            emit(nd.l == f ? nd.r : nd.l);
+            out.push_back(j == 0 ? (uint32_t)EX_SET1 : (EX_FOLD | ((1u << 4 | EXF_Y) << 8)));
+        }
+        emit(f);
+        out.push_back(EX_GROUP | ((uint32_t)m << 8));
+        k += m;
     }
     return true;
 }
@@ -1139,7 +1172,7 @@ int32_t b200zk_pk_create(b200zk_params* params, const uint32_t* cs_blob, size_t 
         {
             std::vector<ExFold> items;
             for (auto& g : cs.gates) items.push_back({g.first, g.second, EX_FOLD | ((0u << 4 | EXF_Y) << 8)});
-            if (!ex_share_common(cs.prog, items, prog)) return bail(fail(ctx, B200ZK_EINVAL, "pk_create", "malformed expression program"));
+            if (!ex_share_common(cs.prog, items, prog, true)) return bail(fail(ctx, B200ZK_EINVAL, "pk_create", "malformed expression program"));
         }
         pk->gates_len = (uint32_t)prog.size();
         for (auto& lk : cs.lookups) {
@@ -1154,7 +1187,7 @@ int32_t b200zk_pk_create(b200zk_params* params, const uint32_t* cs_blob, size_t 
         int depth = 0, maxd = 0;
         for (uint32_t w : prog) {
             uint32_t op = w & 0xff;
-            if (op <= EX_INSTANCE || op == EX_TMP) ++depth; else if (op == EX_ADD || op == EX_MUL || op == EX_FOLD) --depth;
+            if (op <= EX_INSTANCE || op == EX_TMP) ++depth; else if (op == EX_ADD || op == EX_MUL || op == EX_FOLD || op == EX_SET1 || op == EX_GROUP) --depth;
             maxd = std::max(maxd, depth);
             if (depth < 0) return bail(fail(ctx, B200ZK_EINVAL, "pk_create", "malformed expression program"));
         }
