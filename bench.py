@@ -358,7 +358,12 @@ def run_gpu(args):
         ach = ntt_work_mul32(k) / (ms_ntt / 1e3)
         hbm = 64.0 * n / (ms_ntt / 1e3) / 1e9
         line["roofline"] = {"bound": "imad", "kernel": f"ntt pass kernel, one 2^{k} transform = {ntt_passes(k)} launches", "achieved": ach / 1e12,
-                            "peak": IMAD_WIDE_PEAK / 1e12, "unit": "T IMAD.WIDE.U32/s", "frac": ach / IMAD_WIDE_PEAK, "traffic": None,
+                            "peak": IMAD_WIDE_PEAK / 1e12, "unit": "T IMAD.WIDE.U32/s", "frac": ach / IMAD_WIDE_PEAK,
+                            # dram__bytes_read + write per pass launch of a 2^20 transform, ncu --set full
+                            # (profiles/r01_ncu_ntt_warp_summary.txt): the 32 MB transform and its 32 MB twiddle
+                            # table stay in L2, so traffic is below the 67 MB algorithmic bytes of a pass
+                            "traffic": ({"dram_bytes_per_launch": [67.7e6, 34.1e6, 35.0e6], "algorithmic_bytes_per_launch": 64 * n,
+                                         "source": "profiles/r01_ncu_ntt_warp_summary.txt"} if k == 20 else None),
                             "ms_per_launch_group": ms_ntt, "share_of_step": ph["ntt"] / max(sum(ph.values()), 1e-9),
                             "hbm_view": {"achieved": hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm / peaks["hbm_gbs"],
                                          "algorithmic_bytes": 64 * n, "peak_source": peak_src},
