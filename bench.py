@@ -418,6 +418,8 @@ def cpu_sample(args):
         scale = float(1 << (args.k - ks))
         if args.circuit == "mst" and args.k == 20 and ks == 14:
             scale = 42.2
+        if args.circuit == "mst_dense" and args.k == 20 and ks == 14:
+            scale = 47.0                                         # 112.8 s at k = 20 (r01_parity_mst_dense_k20_gpu_vs_oracle.json) / 2.4 s
         return fn, None, f"oracle create_proof (restatement of halo2 v2023_02_02 CPU prover) on the same circuit at k={ks}", scale
     Ls = min(args.log_n, args.cpu_log_n)
     ns = 1 << Ls
