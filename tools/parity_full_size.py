@@ -3,7 +3,7 @@
 to k (default 20) is proved by the GPU backend and by the CPU oracle (restatement of halo2's
 prover, minutes at this size) from the same SRS, witness and RNG stream; the proof bytes are
 compared.  Prints one JSON line (sha256 of both proofs, timings).  Test infrastructure, not the
-product:  python tools/parity_full_size.py [k] [mst|mst_dense]"""
+product:  python tools/parity_full_size.py [k] [mst|mst_dense] [seed]"""
 import hashlib
 import importlib
 import json
@@ -22,11 +22,12 @@ from oracle import prover as OP  # noqa: E402
 def main():
     k = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     circuit = sys.argv[2] if len(sys.argv) > 2 else "mst"          # mst | mst_dense (every row in use)
+    seed = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     zk = load_package()
     chips = importlib.import_module(zk.__name__ + ".chips")
     synth = importlib.import_module(zk.__name__ + ".circuits_synth")
     orc.build()
-    job = chips.merkle_sum_tree_job(k) if circuit == "mst" else synth.mst_shaped(k)
+    job = chips.merkle_sum_tree_job(k, seed=seed) if circuit == "mst" else synth.mst_shaped(k, seed=seed)
     be = zk.Backend(0)
     s = orc.random_fr(1, 20251018)[0]
     t0 = time.perf_counter()
@@ -44,7 +45,7 @@ def main():
     want, _ = OP.create_proof(g, gl, opk, job.advice, job.instances, wide, job.transcript_repr)
     t4 = time.perf_counter()
     first = next((i // 32 for i in range(0, len(want), 32) if got[i:i + 32] != want[i:i + 32]), None)
-    print(json.dumps({"circuit": "MerkleSumTreeCircuit, 16-level path" if circuit == "mst" else "MST-shaped synthetic circuit, dense witness", "k": k, "proof_bytes": len(got),
+    print(json.dumps({"circuit": "MerkleSumTreeCircuit, 16-level path" if circuit == "mst" else "MST-shaped synthetic circuit, dense witness", "k": k, "seed": seed, "proof_bytes": len(got),
                       "gpu_sha256": hashlib.sha256(got).hexdigest(), "oracle_sha256": hashlib.sha256(want).hexdigest(),
                       "identical": got == want, "first_differing_item": first,
                       "gpu_setup_keygen_s": round(t1 - t0, 2), "gpu_create_proof_e2e_s": round(t2 - t1, 3),
