@@ -280,11 +280,16 @@ def run_gpu(args):
             sharded = importlib.import_module(zk.__name__ + ".sharded")
             dev = torch.device("cuda", local)
             log_r = min(10, L // 2)
-            fs = sharded.FourStepNTTDevice(zk, be, L, log_r, rank, world, dev)
+            # default: the exchange fused into the column-step kernel (NVLink peer stores, CUDA IPC);
+            # B200ZK_NTT_NCCL=1 selects the NCCL all-to-all path
+            fused = os.environ.get("B200ZK_NTT_NCCL", "0") != "1"
+            fs = (sharded.FourStepNTTFused if fused else sharded.FourStepNTTDevice)(zk, be, L, log_r, rank, world, dev)
+            extra["exchange"] = "fused into the column-step kernel (NVLink peer stores)" if fused else "NCCL all_to_all_single"
             blk_host = random_scalars((1 << L) // world, 300 + rank).reshape(1 << log_r, -1, 4)
             block = torch.from_numpy(blk_host.view(np.int64)).to(dev)
             omega_c = zk.EvaluationDomain(be, 2, L - log_r).omega
             pinned = torch.from_numpy(blk_host.view(np.int64)).pin_memory()
+            pinned_np = pinned.numpy()
 
             def step_dev():
                 fs.forward(block, omega, omega_c)
@@ -292,7 +297,10 @@ def run_gpu(args):
             def step_e2e():
                 block.copy_(pinned, non_blocking=False)
                 rows = fs.forward(block, omega, omega_c)
-                pinned.view(rows.shape).copy_(rows)
+                if fused:
+                    be._check(zk.lib().b200zk_download(be._ctx, pinned_np.ctypes.data_as(ctypes.c_void_p), rows.ptr, ctypes.c_size_t(pinned_np.nbytes)))
+                else:
+                    pinned.view(rows.shape).copy_(rows)
 
             n = (1 << L) // world                                   # per-rank elements; value multiplies by world
             line["scaling"] = "strong"

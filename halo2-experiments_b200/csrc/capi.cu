@@ -329,6 +329,37 @@ int32_t b200zk_fft_colstep_dev(b200zk_ctx* ctx, void* d_block, uint32_t log_r, u
     return ntt_colstep_run(ctx, (fe_t*)d_block, log_r, log_cg, col0, HFr::from_limbs(omega_n), log_n);
 }
 
+int32_t b200zk_fft_colstep_scatter_dev(b200zk_ctx* ctx, void* d_block, uint32_t log_r, uint32_t log_cg, uint32_t col0,
+                                       const void* omega_n, uint32_t log_n, void* const* peer_rows, uint32_t world) {
+    if (!ctx || !d_block || !omega_n || !peer_rows || log_n > 30 || log_r + log_cg > log_n) return B200ZK_EINVAL;
+    for (uint32_t j = 0; j < world && j < 8; ++j) if (!peer_rows[j]) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ntt_colstep_run(ctx, (fe_t*)d_block, log_r, log_cg, col0, HFr::from_limbs(omega_n), log_n, (fe_t* const*)peer_rows, world);
+}
+
+// CUDA IPC: let another process on the node (one process per GPU) address a b200zk_malloc'ed buffer
+int32_t b200zk_ipc_get_handle(b200zk_ctx* ctx, const void* d_ptr, void* handle64) {
+    if (!ctx || !d_ptr || !handle64) return B200ZK_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZK_CUDA(ctx, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, const_cast<void*>(d_ptr)));
+    return B200ZK_OK;
+}
+int32_t b200zk_ipc_open(b200zk_ctx* ctx, const void* handle64, void** d_ptr) {
+    if (!ctx || !handle64 || !d_ptr) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    ZK_CUDA(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200ZK_OK;
+}
+int32_t b200zk_ipc_close(b200zk_ctx* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return B200ZK_EINVAL;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZK_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return B200ZK_OK;
+}
+
 int32_t b200zk_fft_rows_dev(b200zk_ctx* ctx, void* d_rows, uint32_t nrows, const void* omega_c, uint32_t log_c) {
     if (!ctx || !d_rows || !omega_c || log_c > 30) return B200ZK_EINVAL;
     ZK_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -175,7 +175,7 @@ int32_t ntt_run_cosets(b200zk_ctx* ctx, const fe_t* d_in, fe_t* d_out, uint32_t 
 // d_block is this rank's [R][Cg] block (row-major, Cg = 2^log_cg columns starting at global column
 // col0).  In place: R-point transform down every column, then the twiddle omega_n^((col0 + c) * k_r).
 int32_t ntt_colstep_run(b200zk_ctx* ctx, fe_t* d_block, uint32_t log_r, uint32_t log_cg, uint32_t col0,
-                        const host::HFr& omega_n, uint32_t log_n) {
+                        const host::HFr& omega_n, uint32_t log_n, fe_t* const* peer_rows, uint32_t world) {
     if (log_r == 0 || log_r > NTT_MAX_LOG_M || log_r > log_n) return fail(ctx, B200ZK_EINVAL, "ntt_colstep", "row count must be 2^1..2^10");
     // dedicated plan: roots of order R, two-level table of omega_n
     std::array<uint64_t, 5> key = {((uint64_t)log_r << 32) | ((uint64_t)1 << 62) | log_n, omega_n.v[0], omega_n.v[1], omega_n.v[2], omega_n.v[3]};
@@ -212,6 +212,12 @@ int32_t ntt_colstep_run(b200zk_ctx* ctx, fe_t* d_block, uint32_t log_r, uint32_t
     a.roots = plan.roots; a.log_roots = log_r;
     a.tw_lo = plan.tw_lo; a.tw_hi = plan.tw_hi; a.tw_lo_bits = plan.shape.tw_lo_bits;
     a.tw_shift = 0; a.l_offset = col0;              // exponent (col0 + c) * k_r < C * R = N
+    if (peer_rows) {                                // fused all-to-all: row k -> rank k / (R / world), see NttPassArgs
+        if (world == 0 || world > 8 || (world & (world - 1)) || ((1u << log_r) % world)) return fail(ctx, B200ZK_EINVAL, "ntt_colstep", "world must be a power of two <= 8 dividing R");
+        uint32_t lw = 0; while ((1u << lw) < world) ++lw;
+        a.scatter = 1; a.log_rows_per_rank = log_r - lw; a.log_c_total = log_n - log_r;
+        for (uint32_t j = 0; j < world; ++j) a.peers[j] = peer_rows[j];
+    }
     uint32_t tile = 1u << (a.log_m + a.log_tw);
     uint32_t threads = tile / 2 < NTT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : NTT_THREADS;
     ntt_pass_kernel<<<1u << (log_cg - a.log_tw), threads, sizeof(fe_t) << (a.log_m + a.log_tw), ctx->stream>>>(a);

@@ -50,6 +50,11 @@ struct NttPassArgs {
     uint32_t tw_shift;      // inter-pass twiddle exponent = ((l + l_offset) * k) << tw_shift
     uint32_t l_offset;      // global column index of local column 0 (sharded four-step column step)
     uint32_t batch_tiles;   // last pass of a batch of independent transforms: tiles per transform (0 = single)
+    // Sharded four-step column step fused with its all-to-all: output row k goes straight into the
+    // memory of the rank that owns it (peer pointers over NVLink / NVSwitch, CUDA IPC), at
+    // [k mod rows_per_rank][global column]; no staging buffer, no separate exchange.
+    uint32_t scatter, log_rows_per_rank, log_c_total;
+    fe_t* peers[8];
 };
 
 ZK_D uint32_t bitrev32(uint32_t v, uint32_t bits) {
@@ -156,6 +161,11 @@ ZK_D void ntt_pass_block(const NttPassArgs& a, uint32_t bid, uint32_t nthreads, 
             // w_{ML}^{l k} = omega^{l k N/(ML)}
             uint64_t E = ((uint64_t)(l + a.l_offset) * k) << a.tw_shift;
             if (E) v = Fr::mul(v, ntt_twiddle(a, (uint32_t)E));
+            if (a.scatter) {
+                const uint32_t dest = k >> a.log_rows_per_rank, row = k & ((1u << a.log_rows_per_rank) - 1);
+                a.peers[dest][((size_t)row << a.log_c_total) + l + a.l_offset] = v;
+                continue;
+            }
         } else {
             // out index = k_1 + M_1 * rev(rho') + (M_1 * mid) * k ; mid digit order is preserved
             // because P <= 3 passes use a single middle digit (asserted on the host).

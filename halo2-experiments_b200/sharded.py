@@ -168,6 +168,62 @@ class FourStepNTTDevice:
         return rows
 
 
+class FourStepNTTFused(FourStepNTTDevice):
+    """Same transform with the exchange fused into the column-step kernel: every rank exports its
+    (R/G, C) row buffer over CUDA IPC, the column step writes each transformed row straight into the
+    owner's buffer with NVLink / NVSwitch peer stores (b200zk_fft_colstep_scatter_dev), and after a
+    barrier every rank runs the row step on what it received.  No NCCL all-to-all, no staging copy,
+    no transpose pass."""
+
+    def __init__(self, zk, backend, log_n, log_r, rank, world, device):
+        super().__init__(zk, backend, log_n, log_r, rank, world, device)
+        torch, dist = _torch()
+        ct, lib = self.ct, zk.lib()
+        rg = self.R // world
+        self.rows_buf = backend.alloc(rg * self.C * 32)
+        handle = (ct.c_uint8 * 64)()
+        backend._check(lib.b200zk_ipc_get_handle(backend._ctx, self.rows_buf.ptr, handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle))
+        self.peers = (ct.c_void_p * world)()
+        self._opened = []
+        for j in range(world):
+            if j == rank:
+                self.peers[j] = self.rows_buf.ptr.value
+            else:
+                p = ct.c_void_p()
+                backend._check(lib.b200zk_ipc_open(backend._ctx, (ct.c_uint8 * 64).from_buffer_copy(handles[j]), ct.byref(p)))
+                self.peers[j] = p.value
+                self._opened.append(p)
+        dist.barrier()
+
+    def forward(self, block, omega_n, omega_c):
+        """block: torch int64 CUDA tensor (R, C/G, 4), read only.  Returns this rank's DeviceBuffer with
+        the (R/G, C, 4) output rows."""
+        torch, dist = _torch()
+        ct, lib = self.ct, self.zk.lib()
+        cg, rg = self.C // self.world, self.R // self.world
+        torch.cuda.synchronize(self.device)
+        self.be._check(lib.b200zk_fft_colstep_scatter_dev(self.be._ctx, ct.c_void_p(block.data_ptr()), ct.c_uint32(self.log_r),
+                                                         ct.c_uint32(int(np.log2(cg))), ct.c_uint32(self.rank * cg),
+                                                         np.ascontiguousarray(omega_n).ctypes.data_as(ct.c_void_p), ct.c_uint32(self.log_n),
+                                                         self.peers, ct.c_uint32(self.world)))
+        self.be.sync()
+        dist.barrier()                                          # every rank's rows have arrived
+        self.be._check(lib.b200zk_fft_rows_dev(self.be._ctx, self.rows_buf.ptr, ct.c_uint32(rg),
+                                              np.ascontiguousarray(omega_c).ctypes.data_as(ct.c_void_p), ct.c_uint32(self.log_c)))
+        self.be.sync()
+        dist.barrier()                                          # nobody may overwrite a peer's rows before it has transformed them
+        return self.rows_buf
+
+    def close(self):
+        lib = self.zk.lib()
+        for p in self._opened:
+            lib.b200zk_ipc_close(self.be._ctx, p)
+        self._opened = []
+        self.rows_buf.free()
+
+
 class FourStepNTT:
     """Row/column sharded four-step NTT of size N = R*C over `world` ranks (R, C powers of two,
     world divides both).

@@ -89,6 +89,18 @@ int32_t b200zk_fft_dev(b200zk_ctx* ctx, void* d_a, const void* omega_host, uint3
 int32_t b200zk_fft_colstep_dev(b200zk_ctx* ctx, void* d_block, uint32_t log_r, uint32_t log_cg, uint32_t col0,
                                const void* omega_n, uint32_t log_n);
 int32_t b200zk_fft_rows_dev(b200zk_ctx* ctx, void* d_rows, uint32_t nrows, const void* omega_c, uint32_t log_c);
+/* Column step fused with the all-to-all that follows it: transformed row k is written straight into
+ * peer_rows[k / (R / world)] (that rank's (R / world) x C row buffer, opened with b200zk_ipc_open) at
+ * [k mod (R / world)][col0 + c] — NVLink / NVSwitch peer stores from inside the kernel, no staging
+ * buffer and no separate exchange.  d_block is read only.  The caller synchronises the ranks
+ * (every rank's stream, then a barrier) before the row step.  world: power of two <= 8. */
+int32_t b200zk_fft_colstep_scatter_dev(b200zk_ctx* ctx, void* d_block, uint32_t log_r, uint32_t log_cg, uint32_t col0,
+                                       const void* omega_n, uint32_t log_n, void* const* peer_rows, uint32_t world);
+/* CUDA IPC for one-process-per-GPU hosts: export a b200zk_malloc'ed buffer (64-byte handle), open /
+ * close a peer's handle in this process. */
+int32_t b200zk_ipc_get_handle(b200zk_ctx* ctx, const void* d_ptr, void* handle64);
+int32_t b200zk_ipc_open(b200zk_ctx* ctx, const void* handle64, void** d_ptr);
+int32_t b200zk_ipc_close(b200zk_ctx* ctx, void* d_ptr);
 
 /* ---- poly::EvaluationDomain<Fr> (src/poly/domain.rs) ------------------------
  * b200zk_domain_create(j, k) = EvaluationDomain::new(j, k). */
