@@ -311,3 +311,39 @@ def test_four_step_sharded_ntt_kernels(zk, backend, orc, log_n, log_r, world):
     got = np.ascontiguousarray(np.transpose(Z, (1, 0, 2))).reshape(N, 4)          # X[k_r + R k_c] = Z[k_r][k_c]
     want = orc.best_fft(a, omega_n, log_n) if log_n <= 16 else backend.best_fft(a, omega_n, log_n)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("log_n,log_r,world", [(10, 4, 2), (14, 6, 4), (18, 10, 8)])
+def test_four_step_fused_scatter_kernel(zk, backend, orc, log_n, log_r, world):
+    """b200zk_fft_colstep_scatter_dev: the column step that writes every transformed row into the
+    owner's row buffer (NVLink peer stores between processes; here the `world` ranks are emulated
+    one after another on one GPU and the "peer" buffers are local allocations).  Result = best_fft."""
+    import ctypes
+    from oracle import pyref
+    N, R, C = 1 << log_n, 1 << log_r, 1 << (log_n - log_r)
+    cg, rg = C // world, R // world
+    a = orc.random_fr(N, 400 + log_n)
+    w = pyref.omega_for_k(log_n)
+    omega_n = orc.ints_to_mont([w])[0]
+    omega_c = orc.ints_to_mont([pow(w, R, pyref.R_MOD)])[0]
+    L = zk.lib()
+    rows = [backend.alloc(rg * C * 32) for _ in range(world)]
+    peers = (ctypes.c_void_p * world)(*[r.ptr.value for r in rows])
+    for g in range(world):
+        block = np.ascontiguousarray(a.reshape(R, C, 4)[:, g * cg:(g + 1) * cg])
+        d = backend.to_device(block)
+        backend._check(L.b200zk_fft_colstep_scatter_dev(backend._ctx, d.ptr, ctypes.c_uint32(log_r), ctypes.c_uint32(int(np.log2(cg))),
+                                                        ctypes.c_uint32(g * cg), omega_n.ctypes.data_as(ctypes.c_void_p),
+                                                        ctypes.c_uint32(log_n), peers, ctypes.c_uint32(world)))
+        backend.sync()
+        assert np.array_equal(d.download(block.shape), block)                      # the input block is read only
+        d.free()
+    Z = np.zeros((R, C, 4), dtype=np.uint64)
+    for g in range(world):
+        backend._check(L.b200zk_fft_rows_dev(backend._ctx, rows[g].ptr, ctypes.c_uint32(rg), omega_c.ctypes.data_as(ctypes.c_void_p),
+                                             ctypes.c_uint32(log_n - log_r)))
+        Z[g * rg:(g + 1) * rg] = rows[g].download((rg, C, 4))
+        rows[g].free()
+    got = np.ascontiguousarray(np.transpose(Z, (1, 0, 2))).reshape(N, 4)
+    want = orc.best_fft(a, omega_n, log_n) if log_n <= 16 else backend.best_fft(a, omega_n, log_n)
+    assert np.array_equal(got, want)
