@@ -23,7 +23,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200zk.so")
 
-OK, EINVAL, ENODEV, ECUDA, ENOMEM = 0, -1, -2, -3, -4
+OK, EINVAL, ENODEV, ECUDA, ENOMEM, ESYNTH, EVERIFY = 0, -1, -2, -3, -4, -5, -6
 
 
 class B200zkError(RuntimeError):
@@ -353,6 +353,13 @@ class ProvingKey:
                                                            _p(out), ctypes.c_size_t(out.shape[0]), ctypes.byref(ln)))
         return bytes(out[: ln.value])
 
+    def vk_commitments(self):
+        """keygen_vk's commitments: (fixed (F, 8), sigma (P, 8)) G1Affine Montgomery limbs, computed on the device."""
+        fixed = np.zeros((max(self.cs.num_fixed, 1), 8), dtype=np.uint64)
+        sigma = np.zeros((max(len(self.cs.permutation), 1), 8), dtype=np.uint64)
+        self.backend._check(lib().b200zk_pk_vk_commitments(self._h, _p(fixed), _p(sigma)))
+        return fixed[: self.cs.num_fixed], sigma[: len(self.cs.permutation)]
+
     def last_phase_ms(self):
         out = (ctypes.c_float * 7)()
         self.backend._check(lib().b200zk_pk_last_phase_ms(self._h, out))
@@ -415,3 +422,61 @@ class ParamsKZG:
         out = np.zeros(12, dtype=np.uint64)
         self.backend._check(lib().b200zk_commit_dev(self._h, d_poly.ptr, ctypes.c_size_t(n), ctypes.c_int32(1 if lagrange else 0), _p(out)))
         return out
+
+
+# ---- verifier side (host only: no Backend, no device) -------------------------------------------
+def g2_mul(s, base=None):
+    """[s]_2 (ParamsKZG.s_g2 for the setup secret s), or s * base: G2Affine as (16,) Montgomery limbs."""
+    out = np.zeros(16, dtype=np.uint64)
+    b = None if base is None else np.ascontiguousarray(base, dtype=np.uint64).reshape(16)
+    rc = lib().b200zk_g2_mul(_p(b), _p(_fr(s, 1)), _p(out))
+    if rc != OK:
+        raise B200zkError(f"b200zk_g2_mul: error {rc}")
+    return out
+
+
+def pairing_check(g1_points, g2_points):
+    """prod e(P_i, Q_i) == 1 for G1Affine (m, 8) and G2Affine (m, 16) Montgomery limbs."""
+    a = np.ascontiguousarray(g1_points, dtype=np.uint64).reshape(-1, 8)
+    b = np.ascontiguousarray(g2_points, dtype=np.uint64).reshape(-1, 16)
+    if a.shape[0] != b.shape[0]:
+        raise B200zkError("pairing_check: length mismatch")
+    rc = lib().b200zk_pairing_check(_p(a), _p(b), ctypes.c_size_t(a.shape[0]))
+    if rc not in (OK, EVERIFY):
+        raise B200zkError(f"b200zk_pairing_check: error {rc}")
+    return rc == OK
+
+
+class VerifyingKey:
+    """What plonk::verify_proof reads of a VerifyingKey: the constraint system, k, and the commitments to
+    the fixed and permutation polynomials (ProvingKey.vk_commitments()); plus the verifier params
+    (g1 = params.get_g()[0], g2, s_g2)."""
+
+    def __init__(self, cs, k, fixed_commitments, sigma_commitments, g1, s_g2, g2=None):
+        self.cs, self.k = cs, k
+        self.blob = np.ascontiguousarray(cs.to_blob(k), dtype=np.uint32)
+        self.fixed = np.ascontiguousarray(fixed_commitments, dtype=np.uint64).reshape(-1, 8)
+        self.sigma = np.ascontiguousarray(sigma_commitments, dtype=np.uint64).reshape(-1, 8)
+        self.g1 = np.ascontiguousarray(g1, dtype=np.uint64).reshape(8)
+        self.s_g2 = np.ascontiguousarray(s_g2, dtype=np.uint64).reshape(16)
+        self.g2 = g2_mul(np.array(_FR_ONE, dtype=np.uint64)) if g2 is None else np.ascontiguousarray(g2, dtype=np.uint64).reshape(16)
+        if self.fixed.shape[0] != cs.num_fixed or self.sigma.shape[0] != len(cs.permutation):
+            raise B200zkError("commitment counts do not match the constraint system")
+
+    def verify_proof(self, instances, proof, transcript_repr):
+        """plonk::verify_proof(..).is_ok() with VerifierSHPLONK / SingleStrategy / Blake2bRead."""
+        cols = [np.ascontiguousarray(c, dtype=np.uint64).reshape(-1, 4) for c in instances]
+        lens = np.array([c.shape[0] for c in cols] + [0], dtype=np.uint32)
+        keep = [c if c.shape[0] else np.zeros((1, 4), dtype=np.uint64) for c in cols]
+        buf = np.frombuffer(bytes(proof), dtype=np.uint8)
+        fixed = self.fixed if self.fixed.shape[0] else np.zeros((1, 8), dtype=np.uint64)
+        sigma = self.sigma if self.sigma.shape[0] else np.zeros((1, 8), dtype=np.uint64)
+        rc = lib().b200zk_verify_proof(_p(self.blob), ctypes.c_size_t(self.blob.shape[0]), _p(fixed), _p(sigma), _p(self.g1), _p(self.g2),
+                                       _p(self.s_g2), _ptr_array(keep), _p(lens), _p(_fr(transcript_repr, 1)),
+                                       _p(buf) if buf.shape[0] else None, ctypes.c_size_t(buf.shape[0]))
+        if rc not in (OK, EVERIFY):
+            raise B200zkError(f"b200zk_verify_proof: error {rc}")
+        return rc == OK
+
+
+_FR_ONE = [0xac96341c4ffffffb, 0x36fc76959f60cd29, 0x666ea36f7879462e, 0x0e0a77c19a07df2f]      # R mod r

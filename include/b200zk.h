@@ -199,6 +199,33 @@ int32_t b200zk_pk_debug_buffer(b200zk_pk* pk, const char* name, void* host_out, 
 /* per-phase device times (ms) of the last create_proof: msm, ntt, quotient, lookup, permutation, evals+shplonk, other */
 int32_t b200zk_pk_last_phase_ms(const b200zk_pk* pk, float* out7);
 
+/* ---- plonk::keygen_vk / plonk::verify_proof (src/plonk/keygen.rs, src/plonk/verifier.rs,
+ *      src/poly/kzg/multiopen/shplonk/verifier.rs, src/poly/kzg/strategy.rs) ----------------------
+ * The call `full_prover` makes at /root/reference/src/circuits/utils.rs:52-63 with VerifierSHPLONK,
+ * SingleStrategy, Challenge255 and Blake2bRead, for one circuit instance.
+ *
+ * pk_vk_commitments: the commitments a VerifyingKey holds (keygen_vk's O(n) work, on the device):
+ * F fixed-column commitments and P permutation (sigma) commitments, 64-byte G1Affine each.
+ *
+ * verify_proof runs on the caller's thread without a ctx or a device (O(#queries) field work, ~100
+ * G1 scalar multiplications, two Miller loops) — like upstream's verifier it needs nothing of size n.
+ * cs_blob as in pk_create; g1_generator = params.get_g()[0]; g2 / s_g2 = ParamsKZG's [1]_2 and
+ * [s]_2 as G2Affine (x.c0, x.c1, y.c0, y.c1: 4 x 32-byte Montgomery Fq, halo2curves' layout).
+ * Returns 0 for Ok(()), B200ZK_EVERIFY for every Err upstream returns (malformed or non-canonical
+ * proof elements, instance too large, the final pairing check failing), B200ZK_EINVAL for a bad
+ * argument.  Bytes after the last proof element are ignored, as upstream's reader ignores them. */
+#define B200ZK_EVERIFY (-6)
+int32_t b200zk_pk_vk_commitments(b200zk_pk* pk, void* fixed_out, void* sigma_out);
+int32_t b200zk_verify_proof(const uint32_t* cs_blob, size_t blob_words, const void* fixed_commitments,
+                            const void* sigma_commitments, const void* g1_generator, const void* g2, const void* s_g2,
+                            const void* const* instance_columns, const uint32_t* instance_lens,
+                            const void* transcript_repr, const uint8_t* proof, size_t proof_len);
+/* ParamsKZG::setup's G2 side: out = s * base (base NULL = the G2 generator, i.e. out = [s]_2). */
+int32_t b200zk_g2_mul(const void* g2_or_null, const void* s_fr, void* out_g2);
+/* prod e(g1_points[i], g2_points[i]) == 1 ?  0 = yes, B200ZK_EVERIFY = no (Engine::pairing product;
+ * G1Affine 64 B, G2Affine 128 B each). */
+int32_t b200zk_pairing_check(const void* g1_points, const void* g2_points, size_t count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,12 @@ def _run(zk, backend, orc, job, check_verify=True, pairing=False):
         from oracle import pairing as PR
         s_g2 = PR.g2_mul(PR.G2_GEN, orc.mont_to_ints(s)[0])
         assert OP.verify_full(None, g, pk_cpu, job.instances, got, job.transcript_repr, s_g2=s_g2)
+    # the product's own verifier (b200zk_verify_proof; verifying-key commitments computed on the device)
+    fixed_c, sigma_c = pk_gpu.vk_commitments()
+    vk = zk.VerifyingKey(job.cs, job.k, fixed_c, sigma_c, g[0], zk.g2_mul(s))
+    assert vk.verify_proof(inst, got, tr_repr)
+    bad = bytearray(got); bad[len(got) // 2] ^= 1
+    assert not vk.verify_proof(inst, bytes(bad), tr_repr)
     # device-resident entry point gives the same bytes
     d_adv = backend.to_device(np.concatenate([np.ascontiguousarray(a).reshape(-1, 4) for a in job.advice]))
     d_wide = backend.to_device(wide)
@@ -141,7 +147,14 @@ def test_real_merkle_sum_tree_k20_verifies(zk, backend, orc):
     inst = [_mont_ints(orc, c) for c in job.instances]
     proof = pk.create_proof(job.advice, inst, wide, orc.ints_to_mont([job.transcript_repr])[0])
     assert len(proof) == pk.proof_size
+    vk_fixed, vk_sigma = pk.vk_commitments()
     pk.close()
+    # full-size `verify_proof(..).is_ok()` by pairing, through the C ABI (/root/reference/src/circuits/utils.rs:56-63)
+    pvk = zk.VerifyingKey(job.cs, k, vk_fixed, vk_sigma, orc.g1_generator()[:8], zk.g2_mul(s))
+    assert pvk.verify_proof(inst, proof, orc.ints_to_mont([job.transcript_repr])[0])
+    inst_wrong = [c.copy() for c in inst]
+    inst_wrong[0][3] = inst[0][0]
+    assert not pvk.verify_proof(inst_wrong, proof, orc.ints_to_mont([job.transcript_repr])[0])
 
     def aff(out12):
         return orc.affine_to_ints(np.asarray(out12[:8]).reshape(1, 8))[0]
@@ -150,6 +163,8 @@ def test_real_merkle_sum_tree_k20_verifies(zk, backend, orc):
     dom = orc.Domain(job.cs.degree(), k)
     sigma_c = [aff(params.commit_lagrange(sg)) for sg in OP.sigma_from_mapping(dom, job.map_col, job.map_row)]
     params.close()
+    assert fixed_c == [orc.affine_to_ints(c.reshape(1, 8))[0] for c in vk_fixed]
+    assert sigma_c == [orc.affine_to_ints(c.reshape(1, 8))[0] for c in vk_sigma]
     vk = OP.verifying_key(job.cs, k, fixed_c, sigma_c)
     s_int = orc.mont_to_ints(s)[0]
     assert OP.verify_full(s_int, None, vk, job.instances, proof, job.transcript_repr)
@@ -164,3 +179,26 @@ def test_real_less_than_and_safe_accumulator(zk, backend, orc):
     fe, chips = _frontend(zk)
     _run(zk, backend, orc, fe.synthesize_job(chips.LessThanCircuit(755), 10, [list(range(800))]), check_verify=True)
     _run(zk, backend, orc, fe.synthesize_job(chips.SafeAccumulatorCircuit([1, 3], [0, 0, 14, 13]), 8, [[0, 0, 15, 1]]), check_verify=True)
+
+
+@pytest.mark.parametrize("name", ["small_k5", "mst_k9"])
+def test_golden_vectors(zk, backend, orc, name):
+    """The committed golden vectors (tests/golden/, made by make_golden.py from the oracle): the GPU's
+    verifying-key commitments and proof bytes for the same job, SRS secret and rng stream are the committed ones."""
+    import hashlib
+    gold = importlib.import_module("tests.golden.make_golden")
+    tv = importlib.import_module("tests.test_verifier")
+    z, vk, inst, want = tv.load_golden(zk, name)
+    job = _synth(zk).small(5) if name == "small_k5" else gold.mst_k9_job(zk)
+    assert np.array_equal(np.asarray(job.cs.to_blob(job.k), dtype=np.uint32), z["blob"])
+    s = orc.random_fr(1, int(z["seed_s"]))[0]
+    params = zk.ParamsKZG.setup(backend, job.k, s)
+    pk = zk.ProvingKey(params, job.cs, job.k, job.fixed, job.map_col, job.map_row)
+    fixed_c, sigma_c = pk.vk_commitments()
+    assert np.array_equal(fixed_c, z["fixed_commitments"]) and np.array_equal(sigma_c, z["sigma_commitments"])
+    assert np.array_equal(zk.g2_mul(s), z["s_g2"])
+    wide = orc.XorShiftWide().draw(pk.rng_draws)
+    got = pk.create_proof(job.advice, inst, wide, z["transcript_repr"])
+    assert got == want and hashlib.sha256(got).hexdigest() == tv.SHA[name]
+    assert vk.verify_proof(inst, got, z["transcript_repr"])
+    pk.close(); params.close()
