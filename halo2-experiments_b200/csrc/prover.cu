@@ -126,6 +126,11 @@ struct b200zk_pk {
     std::vector<TimerEv> timer_events;                // pool, grown on demand
     size_t timer_used = 0;
     std::vector<void*> owned;
+    // upload pipeline of create_proof: the advice columns arrive on copy_stream one by one (H2D from the caller's
+    // buffers, or D2D), col_events[c] marks column c complete (blinding rows included)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_rnd = nullptr;
+    std::vector<cudaEvent_t> col_events;
     std::map<std::string, std::pair<const void*, size_t>> dbg;     // buffers of the last proof, for b200zk_pk_debug_buffer
 };
 
@@ -416,6 +421,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     const b200zk_domain* dom = pk->dom;
     cudaStream_t st = ctx->stream;
     cudaStreamSynchronize(ctx->stream2);                          // nothing of an earlier (failed) proof may still be writing the arena
+    if (pk->copy_stream) cudaStreamSynchronize(pk->copy_stream);
     const size_t n = pk->n, ext = pk->ext_n;
     const uint32_t A = cs.A, I = cs.I, F = cs.F, L = pk->L, S = pk->S, bf = cs.bf;
     const size_t usable = n - (bf + 1);
@@ -489,29 +495,56 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         return cudaMemcpyAsync(dst, src, count * sizeof(fe_t), cudaMemcpyDeviceToDevice, st);
     };
 
-    // ---- step 2: advice columns: blinding rows, blinds, commitments
-    if (advice_on_device) ZK_CUDA(ctx, copy_rows(advice_values, d_advice_in, A * n));
-    else for (uint32_t c = 0; c < A; ++c)
-        ZK_CUDA(ctx, cudaMemcpyAsync(advice_values + (size_t)c * n, advice_host[c], n * sizeof(fe_t), cudaMemcpyHostToDevice, st));
-    for (uint32_t c = 0; c < A; ++c) ZK_CUDA(ctx, copy_rows(advice_values + (size_t)c * n + usable, rng_take(bf + 1), bf + 1));
+    // ---- step 2: advice columns: blinding rows, blinds, commitments.
+    // The columns arrive on the pk's copy stream one at a time (H2D from the caller's buffers, 32 MiB each at
+    // k = 20, or D2D), each followed by its blinding rows; col_events[c] marks column c complete.  Everything that
+    // does not need the transcript starts under that transfer: on the side stream the coefficient form and the
+    // quotient cosets of column c as soon as it has landed (step 10, moved up), and — when the columns come from
+    // the host — on the main stream the commitment to the vanishing argument's random polynomial (step 8), which
+    // depends on the rng stream only.  The main stream then waits for the last column and commits all of them.
+    if (!pk->copy_stream) {
+        ZK_CUDA(ctx, cudaStreamCreateWithFlags(&pk->copy_stream, cudaStreamNonBlocking));
+        ZK_CUDA(ctx, cudaEventCreateWithFlags(&pk->ev_rnd, cudaEventDisableTiming));
+    }
+    while (pk->col_events.size() < A) {
+        cudaEvent_t e;
+        ZK_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        pk->col_events.push_back(e);
+    }
+    const size_t rpos_advice = rpos;
+    rng_take((size_t)A * (bf + 1));
     rng_take(A);                                                  // Blind per column (unused by KZG)
+    ZK_CUDA(ctx, cudaEventRecord(pk->ev_rnd, st));
+    ZK_CUDA(ctx, cudaStreamWaitEvent(pk->copy_stream, pk->ev_rnd, 0));      // rnd (and the arena's previous users on st) first
+    for (uint32_t c = 0; c < A; ++c) {
+        fe_t* col = advice_values + (size_t)c * n;
+        if (advice_on_device) ZK_CUDA(ctx, cudaMemcpyAsync(col, d_advice_in + (size_t)c * n, n * sizeof(fe_t), cudaMemcpyDeviceToDevice, pk->copy_stream));
+        else ZK_CUDA(ctx, cudaMemcpyAsync(col, advice_host[c], n * sizeof(fe_t), cudaMemcpyHostToDevice, pk->copy_stream));
+        ZK_CUDA(ctx, cudaMemcpyAsync(col + usable, rnd + rpos_advice + (size_t)c * (bf + 1), (bf + 1) * sizeof(fe_t), cudaMemcpyDeviceToDevice, pk->copy_stream));
+        ZK_CUDA(ctx, cudaEventRecord(pk->col_events[c], pk->copy_stream));
+    }
+    {
+        SideStream side(ctx);
+        for (uint32_t c = 0; c < A; ++c) {
+            ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pk->col_events[c], 0));
+            ZK_CUDA(ctx, cudaMemcpyAsync(advice_polys + (size_t)c * n, advice_values + (size_t)c * n, n * sizeof(fe_t), cudaMemcpyDeviceToDevice, ctx->stream));
+            ZK_TRY(lagrange_to_coeff(pk, advice_polys + (size_t)c * n));
+            ZK_TRY(coeff_to_extended(pk, advice_polys + (size_t)c * n, advice_cosets + (size_t)c * ext));
+        }
+        for (uint32_t c = 0; c < I; ++c) ZK_TRY(coeff_to_extended(pk, inst_polys + (size_t)c * n, inst_cosets + (size_t)c * ext));
+    }
+    // position of the random polynomial in the rng stream (draw order: SURVEY.md 8(a7))
+    const size_t rpos_random = rpos + (size_t)L * (2 * (bf + 1) + 2) + (size_t)S * (bf + 1) + (size_t)L * (bf + 1);
+    HAffine random_pt = {host::HFq::zero(), host::HFq::zero()};
+    const bool random_early = !advice_on_device;
+    if (random_early) ZK_TRY(commit_dev(pk, rnd + rpos_random, n, false, &random_pt));
+    if (A) ZK_CUDA(ctx, cudaStreamWaitEvent(st, pk->col_events[A - 1], 0));
     {
         std::vector<const fe_t*> cols;
         std::vector<HAffine> pts;
         for (uint32_t c = 0; c < A; ++c) cols.push_back(advice_values + (size_t)c * n);
         ZK_TRY(commit_multi_dev(pk, cols, n, true, pts));
         for (uint32_t c = 0; c < A; ++c) tr.write_point(pts[c]);
-    }
-    // ---- step 10 (moved up): advice polynomials and cosets depend on nothing the transcript still has
-    // to produce, so they run on the side stream while the lookup / permutation arguments — sorts,
-    // scans, batch inversions, the latency-bound tails of their commits — occupy the main one.
-    // evaluate_h (step 11) waits for them.
-    {
-        SideStream side(ctx);
-        ZK_CUDA(ctx, cudaMemcpyAsync(advice_polys, advice_values, A * n * sizeof(fe_t), cudaMemcpyDeviceToDevice, ctx->stream));
-        for (uint32_t c = 0; c < A; ++c) ZK_TRY(lagrange_to_coeff(pk, advice_polys + (size_t)c * n));
-        for (uint32_t c = 0; c < A; ++c) ZK_TRY(coeff_to_extended(pk, advice_polys + (size_t)c * n, advice_cosets + (size_t)c * ext));
-        for (uint32_t c = 0; c < I; ++c) ZK_TRY(coeff_to_extended(pk, inst_polys + (size_t)c * n, inst_cosets + (size_t)c * ext));
     }
     HFr ch[4];                                                    // theta, beta, gamma, y
     ch[EXF_THETA] = tr.squeeze_challenge();
@@ -629,13 +662,11 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     }
 
     // ---- step 8: vanishing argument, random polynomial
+    if (rpos != rpos_random) return fail(ctx, B200ZK_EINVAL, "create_proof", "rng draw order");
     const fe_t* random_poly = rng_take(n);
     rng_take(1);
-    {
-        HAffine pt;
-        ZK_TRY(commit_dev(pk, random_poly, n, false, &pt));
-        tr.write_point(pt);
-    }
+    if (!random_early) ZK_TRY(commit_dev(pk, random_poly, n, false, &random_pt));
+    tr.write_point(random_pt);
     ch[EXF_Y] = tr.squeeze_challenge();
     const HFr y = ch[EXF_Y];
 
@@ -972,6 +1003,9 @@ int32_t b200zk_pk_vk_commitments(b200zk_pk* pk, void* fixed_out, void* sigma_out
 void b200zk_pk_destroy(b200zk_pk* pk) {
     if (!pk) return;
     cudaSetDevice(pk->ctx->device);
+    if (pk->copy_stream) { cudaStreamSynchronize(pk->copy_stream); cudaStreamDestroy(pk->copy_stream); }
+    if (pk->ev_rnd) cudaEventDestroy(pk->ev_rnd);
+    for (cudaEvent_t e : pk->col_events) cudaEventDestroy(e);
     cudaStreamSynchronize(pk->ctx->stream);
     for (void* p : pk->owned) cudaFree(p);
     for (auto& t : pk->timer_events) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
