@@ -266,6 +266,25 @@ class EvaluationDomain:
         self.backend._check(lib().b200zk_divide_by_vanishing_poly(self._h, _p(a)))
         return a
 
+    def rotate_omega(self, value, rotation):
+        out = np.zeros(4, dtype=np.uint64)
+        self.backend._check(lib().b200zk_domain_rotate_omega(self._h, _p(_fr(value, 1)), ctypes.c_int32(rotation), _p(out)))
+        return out
+
+    def l_i_range(self, x, rot_lo, rot_hi):
+        """l_i(x) for i in rot_lo..=rot_hi (upstream's l_i_range(x, x^n, rot_lo..=rot_hi))."""
+        out = np.zeros((rot_hi - rot_lo + 1, 4), dtype=np.uint64)
+        self.backend._check(lib().b200zk_domain_l_i_range(self._h, _p(_fr(x, 1)), ctypes.c_int32(rot_lo), ctypes.c_int32(rot_hi), _p(out)))
+        return out
+
+    def rotate_extended(self, a, rotation):
+        a = _fr(a, self.extended_len())
+        d_in, d_out = self.backend.to_device(a), self.backend.alloc(a.nbytes)
+        self.backend._check(lib().b200zk_rotate_extended_dev(self._h, d_in.ptr, ctypes.c_int32(rotation), d_out.ptr))
+        out = d_out.download(a.shape)
+        d_in.free(); d_out.free()
+        return out
+
     # device-resident variants (DeviceBuffer in, DeviceBuffer out)
     def lagrange_to_coeff_dev(self, d_a):
         self.backend._check(lib().b200zk_lagrange_to_coeff_dev(self._h, d_a.ptr))

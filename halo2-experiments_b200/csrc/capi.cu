@@ -1,5 +1,6 @@
 // C ABI of libb200zk.so (declarations and reference mapping: include/b200zk.h).
 #include "context.hpp"
+#include <vector>
 #include <new>
 #include <cuda_profiler_api.h>
 
@@ -431,6 +432,56 @@ int32_t b200zk_domain_constant(const b200zk_domain* d, uint32_t which, void* out
     const HFr* f[] = {&d->omega, &d->omega_inv, &d->extended_omega, &d->extended_omega_inv, &d->g_coset, &d->g_coset_inv,
                       &d->ifft_divisor, &d->extended_ifft_divisor, &d->barycentric_weight};
     f[which]->store(out_fr);
+    return B200ZK_OK;
+}
+
+// EvaluationDomain::rotate_omega(value, rotation) = value * omega^rotation
+int32_t b200zk_domain_rotate_omega(const b200zk_domain* d, const void* value_fr, int32_t rotation, void* out_fr) {
+    if (!d || !value_fr || !out_fr) return B200ZK_EINVAL;
+    HFr v = HFr::from_limbs(value_fr);
+    HFr r = rotation >= 0 ? v * d->omega.pow_u64((uint64_t)rotation) : v * d->omega_inv.pow_u64((uint64_t)(-(int64_t)rotation));
+    r.store(out_fr);
+    return B200ZK_OK;
+}
+
+// EvaluationDomain::l_i_range(x, x^n, rot_lo..=rot_hi): l_i(x) = (x^n - 1) / n * omega^i / (x - omega^i) for every
+// rotation i of the range (the verifier's l_0, l_last, l_blind and instance evaluations).  Like upstream, an x
+// inside the domain has no defined value here (upstream divides by zero silently): EINVAL.
+int32_t b200zk_domain_l_i_range(const b200zk_domain* d, const void* x_fr, int32_t rot_lo, int32_t rot_hi, void* out_fr) {
+    if (!d || !x_fr || !out_fr || rot_hi < rot_lo) return B200ZK_EINVAL;
+    HFr x = HFr::from_limbs(x_fr), xn = x;
+    for (uint32_t i = 0; i < d->k; ++i) xn = xn.sqr();
+    HFr common = (xn - HFr::one()) * d->barycentric_weight;
+    size_t count = (size_t)((int64_t)rot_hi - rot_lo + 1);
+    std::vector<HFr> root(count), den(count), pref(count);
+    HFr w = rot_lo >= 0 ? d->omega.pow_u64((uint64_t)rot_lo) : d->omega_inv.pow_u64((uint64_t)(-(int64_t)rot_lo));
+    HFr acc = HFr::one();
+    for (size_t i = 0; i < count; ++i) {
+        root[i] = w; den[i] = x - w;
+        if (den[i].is_zero()) return B200ZK_EINVAL;
+        pref[i] = acc; acc = acc * den[i];
+        w = w * d->omega;
+    }
+    HFr inv = acc.inv();                                       // one inversion for the range (BatchInvert)
+    for (size_t i = count; i-- > 0;) {
+        HFr di = inv * pref[i];
+        inv = inv * den[i];
+        (di * root[i] * common).store((uint8_t*)out_fr + 32 * i);
+    }
+    return B200ZK_OK;
+}
+
+// EvaluationDomain::rotate_extended(poly, rotation): out[i] = in[(i + rotation * 2^(extended_k - k)) mod 2^extended_k]
+int32_t b200zk_rotate_extended_dev(b200zk_domain* d, const void* d_in, int32_t rotation, void* d_out) {
+    if (!d || !d_in || !d_out || d_in == d_out) return B200ZK_EINVAL;
+    ZK_CUDA(d->ctx, cudaSetDevice(d->ctx->device));
+    const size_t ext = (size_t)1 << d->extended_k;
+    const int64_t step = (int64_t)rotation * (int64_t)(1u << (d->extended_k - d->k));
+    const size_t sh = (size_t)(((step % (int64_t)ext) + (int64_t)ext) % (int64_t)ext);
+    const fe_t* in = (const fe_t*)d_in;
+    fe_t* out = (fe_t*)d_out;
+    ZK_CUDA(d->ctx, cudaMemcpyAsync(out, in + sh, (ext - sh) * sizeof(fe_t), cudaMemcpyDeviceToDevice, d->ctx->stream));
+    if (sh) ZK_CUDA(d->ctx, cudaMemcpyAsync(out + (ext - sh), in, sh * sizeof(fe_t), cudaMemcpyDeviceToDevice, d->ctx->stream));
     return B200ZK_OK;
 }
 

@@ -112,6 +112,12 @@ uint32_t b200zk_domain_quotient_poly_degree(const b200zk_domain* dom);
 /* which: 0 omega, 1 omega_inv, 2 extended_omega, 3 extended_omega_inv, 4 g_coset,
  *        5 g_coset_inv, 6 ifft_divisor, 7 extended_ifft_divisor, 8 barycentric_weight */
 int32_t b200zk_domain_constant(const b200zk_domain* dom, uint32_t which, void* out_fr);
+/* rotate_omega(value, rotation) = value * omega^rotation;  l_i_range(x, x^n, rot_lo..=rot_hi): the Lagrange
+ * basis polynomials l_i(x), i = rot_lo .. rot_hi (negative i counts from the end of the domain), rot_hi - rot_lo + 1
+ * elements out;  rotate_extended: out[i] = in[(i + rotation * 2^(extended_k - k)) mod 2^extended_k] (out != in). */
+int32_t b200zk_domain_rotate_omega(const b200zk_domain* dom, const void* value_fr, int32_t rotation, void* out_fr);
+int32_t b200zk_domain_l_i_range(const b200zk_domain* dom, const void* x_fr, int32_t rot_lo, int32_t rot_hi, void* out_fr);
+int32_t b200zk_rotate_extended_dev(b200zk_domain* dom, const void* d_in, int32_t rotation, void* d_out);
 /* lagrange_to_coeff: n elements in place */
 int32_t b200zk_lagrange_to_coeff(b200zk_domain* dom, void* a);
 int32_t b200zk_lagrange_to_coeff_dev(b200zk_domain* dom, void* d_a);

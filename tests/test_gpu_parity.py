@@ -66,6 +66,21 @@ def test_domain_matches_oracle(zk, backend, orc, j, k):
     # round trip: extended_to_coeff(coeff_to_extended(p)) = p || 0
     back = d.extended_to_coeff(ext)
     assert np.array_equal(back[: 1 << k], coeff) and not back[1 << k:].any()
+    # rotate_omega, l_i_range, rotate_extended
+    x = orc.random_fr(1, 70 + k)[0]
+    for rot in (0, 1, -1, 5, -6):
+        assert np.array_equal(d.rotate_omega(x, rot), od.rotate_omega(x, rot))
+    n, R = 1 << k, 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+    xi, wi = orc.mont_to_ints(x)[0], orc.mont_to_ints(od.omega)[0]
+    lo, hi = -min(6, n - 1), min(3, n - 1)
+    want = [(pow(xi, n, R) - 1) * pow(n, -1, R) * pow(wi, i % n, R) * pow(xi - pow(wi, i % n, R), -1, R) % R for i in range(lo, hi + 1)]
+    assert orc.mont_to_ints(d.l_i_range(x, lo, hi)) == want
+    full = orc.mont_to_ints(d.l_i_range(x, 0, n - 1)) if k <= 7 else None
+    if full is not None:
+        assert sum(full) % R == 1                                      # the Lagrange basis sums to one
+    scale = 1 << (od.extended_k - k)
+    for rot in (1, -1, 3):
+        assert np.array_equal(d.rotate_extended(ext, rot), np.roll(ext, -rot * scale, axis=0))
     d.close()
 
 
