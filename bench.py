@@ -259,7 +259,6 @@ def run_gpu(args):
         dtype = "u32x8 Montgomery (bn256 Fq/Fr, IMAD pipe)"
         workload = WORKLOAD_TEXT["msm"].format(L=L)
     else:
-        import ctypes
         L = args.log_n
         n = 1 << L
         dom = zk.EvaluationDomain(be, 2, L)
