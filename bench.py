@@ -409,7 +409,7 @@ def run_gpu(args):
     line.update(extra)
     if rank == 0:
         line["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(line), flush=True)
+        emit(line)
     barrier(dist, be)
     be.close()
     if dist is not None:
@@ -489,15 +489,31 @@ def run_reference(args):
         unit, metric, hib = ("Mpts/s", "msm_mpts_per_s", True) if args.workload == "msm" else ("GB/s", "ntt_gb_per_s", True)
         workload = WORKLOAD_TEXT[args.workload].format(L=args.log_n)
         sample = f"{desc} per step"
-    print(json.dumps({"impl": "reference", "metric": metric, "unit": unit, "value": v, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+    emit({"impl": "reference", "metric": metric, "unit": unit, "value": v, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": hib,
                       "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 Montgomery (CPU)", "data": "synthetic",
                       "config": {"workload": workload},
                       "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
-                      "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+                      "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's real stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL prints its version banner there
+    # under torchrun) are sent to stderr, the line itself goes to a duplicate of the original descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
