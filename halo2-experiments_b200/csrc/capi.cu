@@ -489,7 +489,10 @@ int32_t b200zk_lagrange_to_coeff_dev(b200zk_domain* d, void* d_a) {
     if (!d || !d_a) return B200ZK_EINVAL;
     ZK_CUDA(d->ctx, cudaSetDevice(d->ctx->device));
     HFr post[3] = {d->ifft_divisor, d->ifft_divisor, d->ifft_divisor};
-    return ntt_run(d->ctx, (const fe_t*)d_a, 1u << d->k, (fe_t*)d_a, d->k, d->omega_inv, nullptr, post);
+    d->ctx->ntt_sparse_hint = true;
+    int32_t rc = ntt_run(d->ctx, (const fe_t*)d_a, 1u << d->k, (fe_t*)d_a, d->k, d->omega_inv, nullptr, post);
+    d->ctx->ntt_sparse_hint = false;
+    return rc;
 }
 
 int32_t b200zk_coeff_to_extended_dev(b200zk_domain* d, const void* d_coeffs, void* d_out_ext) {

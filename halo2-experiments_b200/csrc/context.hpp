@@ -42,6 +42,7 @@ struct b200zk_ctx {
     cudaEvent_t events[64] = {};
     int sm_count = 148;
     int msm_force_c = 0;
+    bool ntt_sparse_hint = false;                                      // next ntt_run: input is a Lagrange column (often zero outside the used rows)
     std::map<std::array<uint64_t, 5>, b200zk::NttPlan> ntt_plans;     // key: log_n + omega limbs
     b200zk::Workspace ntt_scratch, ntt_scratch2, msm_ws, msm_ws2, io_a, io_b, poly_ws, poly_heads, poly_batch, setup_ws, lookup_ws;
     b200zk::affine_t* d_gen_table = nullptr;                          // fixed-base table of the G1 generator (setup.cu)

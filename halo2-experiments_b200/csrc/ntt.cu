@@ -21,7 +21,15 @@ __global__ void __launch_bounds__(NTT_THREADS, 1) ntt_pass_kernel(const NttPassA
 __global__ void __launch_bounds__(32 * NTT_WARPS_PER_BLOCK, 3) ntt_warp_pass_kernel(const NttPassArgs a, uint32_t ntiles) {
     __shared__ half_t sm[NTT_WARPS_PER_BLOCK][256];
     const uint32_t w = threadIdx.x >> 5, wid = blockIdx.x * NTT_WARPS_PER_BLOCK + w;
-    if (wid < ntiles) ntt_pass_warp(a, wid, threadIdx.x & 31, sm[w]);
+    if (wid < ntiles) ntt_pass_warp<false>(a, wid, threadIdx.x & 31, sm[w]);
+}
+// first pass of lagrange_to_coeff (ctx->ntt_sparse_hint): all-zero tiles skip the arithmetic.  The witness columns
+// of a padded circuit are zero outside the used rows and the blinding rows, and a first-pass tile gathers rows at
+// stride n / 128: 262 of 8192 tiles are live for the Merkle Sum Tree circuit at k = 20.
+__global__ void __launch_bounds__(32 * NTT_WARPS_PER_BLOCK, 3) ntt_warp_pass_sparse_kernel(const NttPassArgs a, uint32_t ntiles) {
+    __shared__ half_t sm[NTT_WARPS_PER_BLOCK][256];
+    const uint32_t w = threadIdx.x >> 5, wid = blockIdx.x * NTT_WARPS_PER_BLOCK + w;
+    if (wid < ntiles) ntt_pass_warp<true>(a, wid, threadIdx.x & 31, sm[w]);
 }
 
 __global__ void ntt_pow_table_kernel(fe_t* out, const fe_t base, uint32_t count, uint32_t shift) {
@@ -151,7 +159,9 @@ static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, f
         uint32_t threads = tile / 2 < NTT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : NTT_THREADS;
         if (plan.warp) {
             const uint32_t ntiles = q.blocks * batch;
-            ntt_warp_pass_kernel<<<(ntiles + NTT_WARPS_PER_BLOCK - 1) / NTT_WARPS_PER_BLOCK, 32 * NTT_WARPS_PER_BLOCK, 0, ctx->stream>>>(a, ntiles);
+            const uint32_t grid = (ntiles + NTT_WARPS_PER_BLOCK - 1) / NTT_WARPS_PER_BLOCK;
+            if (ctx->ntt_sparse_hint && p == 0) ntt_warp_pass_sparse_kernel<<<grid, 32 * NTT_WARPS_PER_BLOCK, 0, ctx->stream>>>(a, ntiles);
+            else ntt_warp_pass_kernel<<<grid, 32 * NTT_WARPS_PER_BLOCK, 0, ctx->stream>>>(a, ntiles);
         } else {
             ntt_pass_kernel<<<q.blocks * batch, threads, smem, ctx->stream>>>(a);
         }

@@ -56,6 +56,9 @@ __device__ __forceinline__ void ntt_warp_stage(const NttPassArgs& a, uint32_t la
     }
 }
 
+// SKIP: test the tile for all-zero inputs (first pass of an iNTT of Lagrange columns, see below); the dense
+// instantiation carries none of it.
+template <bool SKIP>
 __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid, uint32_t lane, half_t* sm) {
     const uint32_t log_tw = NTT_WARP_TILE_LOG - a.log_m, TW = 1u << log_tw;
     uint32_t h = 0, l0 = 0, k1_0 = 0, rho_mid = 0;
@@ -69,6 +72,7 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
         rho_mid = wl % mid; k1_0 = (wl / mid) << log_tw;
     }
     fe_t x[4];
+    bool nz = false;
 #pragma unroll
     for (uint32_t e = 0; e < 4; ++e) {
         const uint32_t u = ntt_warp_u<0>(lane, e), m = u >> log_tw, c = u & (TW - 1);
@@ -77,10 +81,25 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
         else g = batch_base + ((((size_t)(k1_0 + c) << a.log_mid) | rho_mid) << a.log_m) + m;
         if (g < a.n_in) {
             x[e] = a.in[a.in_mask ? (g & a.in_mask) : g];
-            if (a.use_pre) { uint32_t r3 = (uint32_t)(g % 3); if (r3) x[e] = Fr::mul(x[e], a.pre[r3]); }
-            if (a.pre_tab) x[e] = Fr::mul(x[e], a.pre_tab[g]);
+            if (SKIP) nz |= !Fr::is_zero(x[e]);
         } else {
             x[e] = Fr::zero();
+        }
+    }
+    // A tile whose 128 inputs are all zero transforms to zero: the warp skips the arithmetic and only writes its
+    // outputs.  Witness columns of a padded circuit are zero outside the used rows and the blinding rows, so the
+    // first pass of their iNTT (column tiles at stride n / 128) is almost entirely such tiles.
+    const bool live = SKIP ? __any_sync(0xffffffffu, nz) : true;
+    if (live) {
+#pragma unroll
+    for (uint32_t e = 0; e < 4; ++e) {
+        const uint32_t u = ntt_warp_u<0>(lane, e), m = u >> log_tw, c = u & (TW - 1);
+        size_t g;
+        if (!a.is_last) g = ((size_t)h << (a.log_m + a.log_l)) + ((size_t)m << a.log_l) + l0 + c;
+        else g = batch_base + ((((size_t)(k1_0 + c) << a.log_mid) | rho_mid) << a.log_m) + m;
+        if (g < a.n_in) {
+            if (a.use_pre) { uint32_t r3 = (uint32_t)(g % 3); if (r3) x[e] = Fr::mul(x[e], a.pre[r3]); }
+            if (a.pre_tab) x[e] = Fr::mul(x[e], a.pre_tab[g]);
         }
     }
     ntt_warp_stage<0, 6, 1>(a, lane, log_tw, x);
@@ -106,6 +125,7 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
             x[e] = odd ? Fr::sub(y, x[e]) : Fr::add(x[e], y);
         }
     }
+    }   // live
 #pragma unroll
     for (uint32_t e = 0; e < 4; ++e) {
         const uint32_t u = ntt_warp_u<2>(lane, e);
@@ -117,10 +137,10 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
             uint32_t l = l0 + c;
             g = ((size_t)h << (a.log_m + a.log_l)) + ((size_t)k << a.log_l) + l;
             uint64_t E = ((uint64_t)(l + a.l_offset) * k) << a.tw_shift;
-            if (E) v = Fr::mul(v, ntt_twiddle(a, (uint32_t)E));
+            if (E && live) v = Fr::mul(v, ntt_twiddle(a, (uint32_t)E));
         } else {
             g = (size_t)(k1_0 + c) + ((size_t)rho_mid << a.log_m1) + ((size_t)k << (a.log_m1 + a.log_mid));
-            if (a.use_post) v = Fr::mul(v, a.post[g % 3]);
+            if (a.use_post && live) v = Fr::mul(v, a.post[g % 3]);
             g += batch_base;
         }
         a.out[g] = v;

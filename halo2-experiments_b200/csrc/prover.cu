@@ -271,7 +271,10 @@ static int32_t commit_multi_dev(b200zk_pk* pk, const std::vector<const fe_t*>& c
 static int32_t lagrange_to_coeff(b200zk_pk* pk, fe_t* d_a) {
     PhaseTimer t(pk, PH_NTT);
     HFr post[3] = {pk->dom->ifft_divisor, pk->dom->ifft_divisor, pk->dom->ifft_divisor};
-    return ntt_run(pk->ctx, d_a, pk->n, d_a, pk->dom->k, pk->dom->omega_inv, nullptr, post);
+    pk->ctx->ntt_sparse_hint = true;
+    int32_t rc = ntt_run(pk->ctx, d_a, pk->n, d_a, pk->dom->k, pk->dom->omega_inv, nullptr, post);
+    pk->ctx->ntt_sparse_hint = false;
+    return rc;
 }
 // coeff_to_extended restricted to the q cosets the quotient needs: coset j = size-n NTT of a_r * c_j^r
 static int32_t coeff_to_extended(b200zk_pk* pk, const fe_t* d_coeffs, fe_t* d_out) {
