@@ -113,3 +113,22 @@ def test_oracle_proofs_verify(zk, orc, name, k):
     assert vk.verify_proof(inst, proof, tr)
     bad = bytearray(proof); bad[len(proof) // 2] ^= 1
     assert not vk.verify_proof(inst, bytes(bad), tr)
+
+
+def test_bad_arguments_are_errors_not_verdicts(zk, orc):
+    """A malformed constraint-system blob or verifier params are caller errors (B200ZK_EINVAL), not `false`."""
+    z, vk, inst, proof = load_golden(zk, "small_k5")
+    blob = z["blob"].copy()
+    blob[0] ^= 1                                                         # magic word
+    broken = zk.VerifyingKey(_Blob(blob, vk.fixed.shape[0], vk.sigma.shape[0]), vk.k, vk.fixed, vk.sigma, vk.g1, vk.s_g2, vk.g2)
+    with pytest.raises(zk.B200zkError):
+        broken.verify_proof(inst, proof, z["transcript_repr"])
+    truncated = zk.VerifyingKey(_Blob(z["blob"][:-3], vk.fixed.shape[0], vk.sigma.shape[0]), vk.k, vk.fixed, vk.sigma, vk.g1, vk.s_g2, vk.g2)
+    with pytest.raises(zk.B200zkError):
+        truncated.verify_proof(inst, proof, z["transcript_repr"])
+    off_curve = vk.s_g2.copy(); off_curve[0] ^= np.uint64(1)
+    with pytest.raises(zk.B200zkError):
+        zk.VerifyingKey(vk.cs, vk.k, vk.fixed, vk.sigma, vk.g1, off_curve, vk.g2).verify_proof(inst, proof, z["transcript_repr"])
+    with pytest.raises(zk.B200zkError):
+        zk.g2_mul(z["transcript_repr"], base=off_curve)
+    assert zk.VerifyingKey(vk.cs, vk.k, vk.fixed, vk.sigma, vk.g1, vk.s_g2, vk.g2).verify_proof(inst, b"", z["transcript_repr"]) is False
