@@ -1183,7 +1183,11 @@ int32_t b200zk_pk_create(b200zk_params* params, const uint32_t* cs_blob, size_t 
 }
 
 static int32_t finish_proof(b200zk_pk* pk, int32_t rc, const std::vector<uint8_t>& proof, uint8_t* proof_out, size_t cap, size_t* proof_len) {
-    if (rc != B200ZK_OK) return rc;
+    if (rc != B200ZK_OK) {
+        // a failed proof may have left column uploads in flight: the caller's buffers are borrowed for the call only
+        if (pk->copy_stream) cudaStreamSynchronize(pk->copy_stream);
+        return rc;
+    }
     if (proof_len) *proof_len = proof.size();
     if (proof.size() > cap) return fail(pk->ctx, B200ZK_EINVAL, "create_proof", "proof buffer too small");
     memcpy(proof_out, proof.data(), proof.size());
