@@ -114,7 +114,23 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
     __syncwarp();
     ntt_warp_get<2>(sm, lane, x);
     ntt_warp_stage<2, 2, 1>(a, lane, log_tw, x);
-    ntt_warp_stage<2, 1, 0>(a, lane, log_tw, x);
+    if (log_tw == 0) {
+        // Stage 1 of a 128-point tile: the twiddle index is the lane's parity, so even lanes have two trivial
+        // butterflies and odd lanes two multiplications by w_4 — executed as written, the warp would spend two
+        // multiplications with half its lanes idle.  The odd lane hands one of its differences to its even
+        // neighbour instead: every lane multiplies exactly once.
+        const bool odd = lane & 1u;
+        fe_t s0 = Fr::add(x[0], x[1]), d0 = Fr::sub(x[0], x[1]), s1 = Fr::add(x[2], x[3]), d1 = Fr::sub(x[2], x[3]);
+        fe_t y;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y.l[i] = __shfl_xor_sync(0xffffffffu, d1.l[i], 1);
+        fe_t prod = Fr::mul(odd ? d0 : y, a.roots[(size_t)1 << (a.log_roots - 2)]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y.l[i] = __shfl_xor_sync(0xffffffffu, prod.l[i], 1);
+        x[0] = s0; x[1] = odd ? prod : d0; x[2] = s1; x[3] = odd ? y : d1;
+    } else {
+        ntt_warp_stage<2, 1, 0>(a, lane, log_tw, x);
+    }
     if (log_tw == 0) {                                         // bit 0 carries a point: twiddle-free stage across lane pairs
         const bool odd = lane & 1u;
 #pragma unroll
