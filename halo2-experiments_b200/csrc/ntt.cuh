@@ -136,10 +136,17 @@ ZK_D void ntt_pass_block(const NttPassArgs& a, uint32_t bid, uint32_t nthreads, 
     for (uint32_t lh = a.log_m; lh-- > 0;) {           // half-size h = 2^lh
         ZK_PHASE_BEGIN(tid, nthreads)
         const uint32_t half = 1u << lh;
+        // Butterfly p of this stage = (group, j), twiddle w^j.  With tiles of >= 8 columns a quarter-warp is one p
+        // (8 contiguous 16-byte halves: conflict-free whatever p is), so p is decoded j-major: the threads of a warp
+        // share j, and the warps whose j is 0 — 1 / 2^lh of the stage — skip the multiplication instead of idling
+        // through it beside lanes that need it.  Narrower tiles keep the group-major order (contiguous rows).
+        const uint32_t glog = a.log_m - 1 - lh;
+        const bool jmajor = a.log_tw >= 3 && glog >= 2;
         for (uint32_t b = tid; b < tile / 2; b += nthreads) {
             uint32_t p = b >> a.log_tw, c = b & (TW - 1);
-            uint32_t j = p & (half - 1);
-            uint32_t i0 = ((p >> lh) << (lh + 1)) + j;
+            uint32_t j = jmajor ? (p >> glog) : (p & (half - 1));
+            uint32_t grp = jmajor ? (p & ((1u << glog) - 1)) : (p >> lh);
+            uint32_t i0 = (grp << (lh + 1)) + j;
             uint32_t s0 = (i0 << a.log_tw) + c, s1 = ((i0 + half) << a.log_tw) + c;
             fe_t x = tile_ld(sm, tile, s0), y = tile_ld(sm, tile, s1);
             fe_t s = Fr::add(x, y), d = Fr::sub(x, y);
