@@ -63,9 +63,13 @@ __global__ void __launch_bounds__(PK_THREADS) quot_lookup_kernel(const QuotLooku
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.rows) quot_lookup_row(a, i);
 }
-__global__ void __launch_bounds__(PK_THREADS) coset_interpolate_kernel(const fe_t* g, const fe_t* inv_pow, const fe_t* vinv, uint32_t C, size_t n, fe_t* out) {
+__global__ void __launch_bounds__(PK_THREADS) coset_interpolate_kernel(const fe_t* g, const fe_t* inv_pow, const fe_t* vinv, uint32_t C, size_t n, fe_t* out, const fe_t* extra) {
     size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n) coset_interpolate_row(g, inv_pow, vinv, C, n, out, r);
+    if (r < n) coset_interpolate_row(g, inv_pow, vinv, C, n, out, r, extra);
+}
+__global__ void __launch_bounds__(PK_THREADS) lookup_extrapolate_kernel(fe_t* g, const fe_t* inv_pow, const fe_t* lambda, const fe_t* tinv, uint32_t CL, uint32_t C, size_t n) {
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) lookup_extrapolate_row(g, inv_pow, lambda, tinv, CL, C, n, r);
 }
 __global__ void __launch_bounds__(PK_THREADS) fold_pieces_kernel(const fe_t* pieces, uint32_t npieces, size_t n, const fe_t xn, fe_t* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,6 +115,9 @@ struct b200zk_pk {
     fe_t *coset_pow = nullptr, *coset_pow_inv = nullptr;      // c_j^r and c_j^-r, [q][n]
     fe_t *coset_fac = nullptr, *vinv = nullptr;               // extended_omega^j [q]; inverse Vandermonde of c_j^n [q*q]
     std::vector<HFr> coset_t;                                  // 1 / (c_j^n - 1): the vanishing polynomial on coset j
+    // lookup terms on lk_cosets_n < q cosets (prover_kernels.cuh, lookup_extrapolate_row); == q: not split
+    uint32_t lk_cosets_n = 0;
+    fe_t *lk_lambda = nullptr, *coset_t_dev = nullptr;        // extrapolation weights [(q - CL) x CL]; coset_t on the device [q]
     // device program data
     uint32_t* d_prog = nullptr;                       // gates program | lookup programs
     uint32_t gates_len = 0;
@@ -168,7 +175,7 @@ static size_t arena_need(const b200zk_pk* pk) {
     size_t n = pk->n, ext = pk->ext_n, A = pk->cs.A, I = pk->cs.I, L = pk->L, S = pk->S;
     size_t draws = b200zk_pk_rng_draws(pk);
     size_t elems = 2 * A * n + 2 * I * n + draws + 7 * L * n + S * n + S * ext + 3 * n   // columns, lookups, perm, tmp
-                   + ext * (1 + A + I + 4)                                                // h, cosets, lookup cosets + table_value
+                   + ext * (1 + A + I + 4 + 1)                                            // h, cosets, lookup cosets + table_value, h_L
                    + n * (1 + 8 + 4);                                                     // h_poly, shplonk set sums, hx/lx/tmp
     return elems * sizeof(fe_t) + (size_t)draws * 64 + (64 << 10);
 }
@@ -277,9 +284,9 @@ static int32_t lagrange_to_coeff(b200zk_pk* pk, fe_t* d_a) {
     return rc;
 }
 // coeff_to_extended restricted to the q cosets the quotient needs: coset j = size-n NTT of a_r * c_j^r
-static int32_t coeff_to_extended(b200zk_pk* pk, const fe_t* d_coeffs, fe_t* d_out) {
+static int32_t coeff_to_extended(b200zk_pk* pk, const fe_t* d_coeffs, fe_t* d_out, uint32_t cosets = 0) {
     PhaseTimer t(pk, PH_NTT);
-    return ntt_run_cosets(pk->ctx, d_coeffs, d_out, pk->dom->k, pk->dom->omega, pk->coset_pow, pk->q);
+    return ntt_run_cosets(pk->ctx, d_coeffs, d_out, pk->dom->k, pk->dom->omega, pk->coset_pow, cosets ? cosets : pk->q);
 }
 static int32_t eval_dev(b200zk_pk* pk, const fe_t* d_poly, size_t len, const HFr& x, HFr* out) {
     return recurrence_run(pk->ctx, d_poly, nullptr, len, x, out);
@@ -452,6 +459,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     fe_t* advice_cosets = ar.take<fe_t>(A * ext);
     fe_t* inst_cosets = ar.take<fe_t>(I * ext);
     fe_t* lk_cosets = ar.take<fe_t>(4 * ext);                    // z, a', s', table_value
+    fe_t* h_lk = ar.take<fe_t>(ext);                             // lookup part of the quotient when it runs on fewer cosets
     fe_t* h_poly = ar.take<fe_t>(n);
     fe_t* set_sums = ar.take<fe_t>(8 * n);
     fe_t* sh_tmp = ar.take<fe_t>(4 * n);
@@ -711,17 +719,24 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
             }
         }
     }
+    // lookup terms: on all q cosets straight into h, or — when their degree allows — on the first CL cosets into
+    // h_lk, extended to the other cosets after the per-coset iNTT (lookup_extrapolate_row)
+    const uint32_t CL = pk->lk_cosets_n;
+    const bool lk_split = L && CL < pk->q;
+    const size_t lk_rows = lk_split ? (size_t)CL * n : ext;
+    if (lk_split) ZK_CUDA(ctx, cudaMemsetAsync(h_lk, 0, lk_rows * sizeof(fe_t), st));
     for (uint32_t l = 0; l < L; ++l) {
         fe_t *zc = lk_cosets, *ac = lk_cosets + ext, *sc = lk_cosets + 2 * ext, *tv = lk_cosets + 3 * ext;
-        ZK_TRY(coeff_to_extended(pk, LK(l, 6), zc));
-        ZK_TRY(coeff_to_extended(pk, LK(l, 4), ac));
-        ZK_TRY(coeff_to_extended(pk, LK(l, 5), sc));
+        ZK_TRY(coeff_to_extended(pk, LK(l, 6), zc, lk_split ? CL : 0));
+        ZK_TRY(coeff_to_extended(pk, LK(l, 4), ac, lk_split ? CL : 0));
+        ZK_TRY(coeff_to_extended(pk, LK(l, 5), sc, lk_split ? CL : 0));
         PhaseTimer t(pk, PH_QUOT);
         ExprArgs ea = expr_args(pk, pk->lookup_prog[l].first, pk->lookup_prog[l].second, true, EXM_LOOKUP_PROD, ch, tv, nullptr);
-        expr_kernel<<<nb(ext), PK_THREADS, 0, st>>>(ea);
-        QuotLookupArgs ql{h, to_dev(y), to_dev(beta), to_dev(gamma), pk->l0, pk->l_last, pk->l_active, zc, ac, sc, tv, dom->k, rot_scale, (uint32_t)ext, {}};
+        ea.rows = (uint32_t)lk_rows;
+        expr_kernel<<<nb(lk_rows), PK_THREADS, 0, st>>>(ea);
+        QuotLookupArgs ql{lk_split ? h_lk : h, to_dev(y), to_dev(beta), to_dev(gamma), pk->l0, pk->l_last, pk->l_active, zc, ac, sc, tv, dom->k, rot_scale, (uint32_t)lk_rows, {}};
         { HFr yp = y * y; for (int i = 0; i < 4; ++i) { ql.ypow[i] = to_dev(yp); yp = yp * y; } }
-        quot_lookup_kernel<<<nb(ext), PK_THREADS, 0, st>>>(ql);
+        quot_lookup_kernel<<<nb(lk_rows), PK_THREADS, 0, st>>>(ql);
         ctx->launches += 2;
     }
     ZK_CUDA(ctx, cudaGetLastError());
@@ -731,12 +746,22 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         // divide by the vanishing polynomial (constant c_j^n - 1 on coset j), per-coset iNTT, then
         // the q x q interpolation across cosets gives the coefficients of h piece by piece
         PhaseTimer t(pk, PH_NTT);
+        HFr y_lk = HFr::one();                                    // h = h_gates_perm * y^(5 L) + h_lk
+        if (lk_split) {
+            for (uint32_t i = 0; i < 5 * L; ++i) y_lk = y_lk * y;
+            for (uint32_t j = 0; j < CL; ++j) {
+                HFr post[3] = {dom->ifft_divisor, dom->ifft_divisor, dom->ifft_divisor};
+                ZK_TRY(ntt_run(ctx, h_lk + j * n, (uint32_t)n, h_lk + j * n, dom->k, dom->omega_inv, nullptr, post));
+            }
+            lookup_extrapolate_kernel<<<nb(n), PK_THREADS, 0, st>>>(h_lk, pk->coset_pow_inv, pk->lk_lambda, pk->coset_t_dev, CL, pk->q, n);
+            ctx->launches++;
+        }
         for (uint32_t j = 0; j < pk->q; ++j) {
-            HFr f = dom->ifft_divisor * pk->coset_t[j];
+            HFr f = dom->ifft_divisor * pk->coset_t[j] * y_lk;
             HFr post[3] = {f, f, f};
             ZK_TRY(ntt_run(ctx, h + j * n, (uint32_t)n, h + j * n, dom->k, dom->omega_inv, nullptr, post));
         }
-        coset_interpolate_kernel<<<nb(n), PK_THREADS, 0, st>>>(h, pk->coset_pow_inv, pk->vinv, pk->q, n, lk_cosets);
+        coset_interpolate_kernel<<<nb(n), PK_THREADS, 0, st>>>(h, pk->coset_pow_inv, pk->vinv, pk->q, n, lk_cosets, lk_split ? h_lk : nullptr);
         ctx->launches++;
         ZK_CUDA(ctx, cudaGetLastError());
         h = lk_cosets;                                            // q pieces of n coefficients
@@ -1089,6 +1114,31 @@ int32_t b200zk_pk_create(b200zk_params* params, const uint32_t* cs_blob, size_t 
         for (uint32_t t = 0; t < C; ++t) for (uint32_t j = 0; j < C; ++j) vin[(size_t)t * C + j] = to_dev(m[t][C + j]);
         PK_CUDA(cudaMemcpyAsync(pk->coset_fac, fac.data(), C * sizeof(fe_t), cudaMemcpyHostToDevice, st));
         PK_CUDA(cudaMemcpyAsync(pk->vinv, vin.data(), vin.size() * sizeof(fe_t), cudaMemcpyHostToDevice, st));
+        // cosets the lookup terms need: their degree is < (2 + deg input + deg table) * n  (circuit.rs, lookup
+        // Argument::required_degree without the max(4, .) floor being relevant: it is >= 4 already)
+        uint32_t CL = C;
+        if (!cs.lookups.empty()) {
+            uint32_t need = 0;
+            for (auto& lk : cs.lookups) {
+                uint32_t di = 1, dt = 1;
+                for (auto& e : lk.ins) di = std::max(di, expr_degree(cs, e.first, e.second));
+                for (auto& e : lk.tabs) dt = std::max(dt, expr_degree(cs, e.first, e.second));
+                need = std::max(need, 2 + di + dt);
+            }
+            CL = std::min(C, need);
+        }
+        pk->lk_cosets_n = CL;
+        std::vector<fe_t> lam((size_t)std::max<uint32_t>(C - CL, 1) * CL), tdev(C);
+        for (uint32_t j = 0; j < C; ++j) tdev[j] = to_dev(pk->coset_t[j]);
+        for (uint32_t jp = CL; jp < C; ++jp)
+            for (uint32_t j = 0; j < CL; ++j) {
+                HFr num = HFr::one(), den = HFr::one();
+                for (uint32_t m2 = 0; m2 < CL; ++m2) { if (m2 == j) continue; num = num * (y[jp] - y[m2]); den = den * (y[j] - y[m2]); }
+                lam[(size_t)(jp - CL) * CL + j] = to_dev(num * den.inv());
+            }
+        PK_TRY(dev_alloc(pk, &pk->lk_lambda, lam.size())); PK_TRY(dev_alloc(pk, &pk->coset_t_dev, C));
+        PK_CUDA(cudaMemcpyAsync(pk->lk_lambda, lam.data(), lam.size() * sizeof(fe_t), cudaMemcpyHostToDevice, st));
+        PK_CUDA(cudaMemcpyAsync(pk->coset_t_dev, tdev.data(), C * sizeof(fe_t), cudaMemcpyHostToDevice, st));
         PK_CUDA(cudaStreamSynchronize(st));
     }
     // fixed columns
