@@ -124,3 +124,18 @@ def msm_pre(scalars, bases, c, seg_len=3):
     lib().emu_msm_pre(_p(scalars), _p(bases), ctypes.c_uint32(scalars.shape[0]), ctypes.c_uint32(bases.shape[0]),
                       ctypes.c_uint32(c), ctypes.c_uint32(seg_len), _p(out))
     return out
+
+
+def lookup_extrapolate(g, inv_pow, lam, tinv, CL, C, n):
+    g = np.array(g, dtype=np.uint64).reshape(C * n, 4)
+    lib().emu_lookup_extrapolate(_p(g), _p(np.ascontiguousarray(inv_pow, dtype=np.uint64)), _p(np.ascontiguousarray(lam, dtype=np.uint64)),
+                                 _p(np.ascontiguousarray(tinv, dtype=np.uint64)), ctypes.c_uint32(CL), ctypes.c_uint32(C), ctypes.c_size_t(n))
+    return g
+
+
+def coset_interpolate(g, inv_pow, vinv, C, n, extra=None):
+    out = np.zeros((C * n, 4), dtype=np.uint64)
+    ex = None if extra is None else np.ascontiguousarray(extra, dtype=np.uint64)
+    lib().emu_coset_interpolate(_p(np.ascontiguousarray(g, dtype=np.uint64)), _p(np.ascontiguousarray(inv_pow, dtype=np.uint64)),
+                                _p(np.ascontiguousarray(vinv, dtype=np.uint64)), ctypes.c_uint32(C), ctypes.c_size_t(n), _p(out), _p(ex) if ex is not None else None)
+    return out

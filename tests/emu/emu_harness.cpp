@@ -250,4 +250,12 @@ void emu_prefix_product(const fe_t* p, fe_t* z, size_t n, size_t m, uint32_t T, 
     for (size_t c = 0; c < C; ++c) prodscan_write_chunk(p, z, n, m, c, prods.data());
 }
 
+// prover_kernels.cuh: the quotient's coset machinery (vanishing::construct without the extended iNTT)
+void emu_lookup_extrapolate(fe_t* g, const fe_t* inv_pow, const fe_t* lambda, const fe_t* tinv, uint32_t CL, uint32_t C, size_t n) {
+    for (size_t r = 0; r < n; ++r) lookup_extrapolate_row(g, inv_pow, lambda, tinv, CL, C, n, r);
+}
+void emu_coset_interpolate(const fe_t* g, const fe_t* inv_pow, const fe_t* vinv, uint32_t C, size_t n, fe_t* out, const fe_t* extra) {
+    for (size_t r = 0; r < n; ++r) coset_interpolate_row(g, inv_pow, vinv, C, n, out, r, extra);
+}
+
 }  // extern "C"

@@ -224,3 +224,52 @@ def test_msm_fixed_base_table_path(orc, c):
         S = orc.ints_to_mont(ss)
         got = emu.msm_pre(S, bases, c)
         assert np.array_equal(got, orc.g1_batch_normalize(orc.best_multiexp(S, bases[:m]))[0]), name
+
+
+@pytest.mark.parametrize("C,CL", [(5, 4), (16, 4), (16, 6), (3, 3)])
+def test_quotient_coset_interpolation_and_lookup_extrapolation(orc, C, CL):
+    """prover_kernels.cuh: h(X) = sum_r X^r H_r(X^n) is recovered from its per-coset iNTTs by the C x C inverse Vandermonde
+    (coset_interpolate_row), and a part of degree < CL * n that was evaluated on the first CL cosets only is carried to the
+    other cosets by Lagrange extrapolation in H-space (lookup_extrapolate_row) — checked against plain integers."""
+    rnd = random.Random(1000 + 16 * C + CL)
+    R, n = P.R_MOD, 8
+    cs = [rnd.randrange(1, R) for _ in range(C)]                    # coset generators (any distinct non-zero values)
+    ys = [pow(c, n, R) for c in cs]
+    tinv = [rnd.randrange(1, R) for _ in range(C)]                  # stands for 1 / (c_j^n - 1)
+    M = lambda v: orc.ints_to_mont([x % R for x in v])
+    inv_pow = M([pow(c, -r, R) for c in cs for r in range(n)])
+    ev = lambda coeffs, x: sum(cf * pow(x, t, R) for t, cf in enumerate(coeffs)) % R
+    # the part known on all C cosets (gates, permutation) and the low-degree part (lookups)
+    H_full = [[rnd.randrange(R) for _ in range(C)] for _ in range(n)]
+    H_low = [[rnd.randrange(R) for _ in range(CL)] for _ in range(n)]
+    g_full = M([pow(cs[j], r, R) * ev(H_full[r], ys[j]) for j in range(C) for r in range(n)])
+    g_low = [pow(cs[j], r, R) * ev(H_low[r], ys[j]) if j < CL else rnd.randrange(R) for j in range(C) for r in range(n)]
+    lam = [[1] * CL for _ in range(max(C - CL, 1))]
+    for jp in range(CL, C):
+        for j in range(CL):
+            num = den = 1
+            for m in range(CL):
+                if m != j:
+                    num = num * (ys[jp] - ys[m]) % R; den = den * (ys[j] - ys[m]) % R
+            lam[jp - CL][j] = num * pow(den, -1, R) % R
+    got = emu.lookup_extrapolate(M(g_low), inv_pow, M([x for row in lam for x in row]), M(tinv), CL, C, n)
+    want = [ev(H_low[r], ys[j]) * tinv[j] % R for j in range(C) for r in range(n)]
+    assert orc.mont_to_ints(got) == want
+    # inverse Vandermonde of the y_j by Gauss-Jordan over the integers mod R
+    A = [[pow(ys[j], t, R) for t in range(C)] + [int(i == j) for i in range(C)] for j in range(C)]
+    for c in range(C):
+        piv = next(r for r in range(c, C) if A[r][c])
+        A[c], A[piv] = A[piv], A[c]
+        inv = pow(A[c][c], -1, R)
+        A[c] = [v * inv % R for v in A[c]]
+        for r in range(C):
+            if r != c and A[r][c]:
+                f = A[r][c]
+                A[r] = [(a - f * b) % R for a, b in zip(A[r], A[c])]
+    vinv = M([A[t][C + j] for t in range(C) for j in range(C)])
+    pieces = emu.coset_interpolate(g_full, inv_pow, vinv, C, n)
+    assert orc.mont_to_ints(pieces) == [H_full[r][t] for t in range(C) for r in range(n)]
+    # both parts together: extra = the extrapolated low part (with t_j = 1 here so that it is H_low itself)
+    extra = emu.lookup_extrapolate(M(g_low), inv_pow, M([x for row in lam for x in row]), M([1] * C), CL, C, n)
+    both = emu.coset_interpolate(g_full, inv_pow, vinv, C, n, extra)
+    assert orc.mont_to_ints(both) == [(H_full[r][t] + (H_low[r][t] if t < CL else 0)) % R for t in range(C) for r in range(n)]
