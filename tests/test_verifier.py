@@ -132,3 +132,36 @@ def test_bad_arguments_are_errors_not_verdicts(zk, orc):
     with pytest.raises(zk.B200zkError):
         zk.g2_mul(z["transcript_repr"], base=off_curve)
     assert zk.VerifyingKey(vk.cs, vk.k, vk.fixed, vk.sigma, vk.g1, vk.s_g2, vk.g2).verify_proof(inst, b"", z["transcript_repr"]) is False
+
+
+@pytest.mark.parametrize("which", ["less_than", "safe_accumulator", "merkle_v3"])
+def test_reference_circuits_verify(zk, orc, which):
+    """The other circuits of the reference — LessThan (dynamic lookup, 800 public inputs; /root/reference/src/circuits/
+    less_than.rs), SafeAccumulator (degree-17 gates: 16 quotient pieces; circuits/safe_accumulator.rs) and Merkle tree v3
+    (circuits/merkle_v3.rs) — proved by the oracle and accepted by the product's verify_proof; a wrong public input is not."""
+    from oracle import pairing as PR
+    from oracle import prover as OP
+    gold = importlib.import_module("tests.golden.make_golden")
+    fe = importlib.import_module(zk.__name__ + ".frontend")
+    chips = importlib.import_module(zk.__name__ + ".chips")
+    if which == "less_than":
+        job = fe.synthesize_job(chips.LessThanCircuit(755), 10, [list(range(800))])
+    elif which == "safe_accumulator":
+        job = fe.synthesize_job(chips.SafeAccumulatorCircuit([1, 3], [0, 0, 14, 13]), 8, [[0, 0, 15, 1]])
+    else:
+        elements, indices = [3, 5, 8, 13, 21], [0, 1, 0, 1, 1]
+        job = fe.synthesize_job(chips.MerkleTreeV3Circuit(99, elements, indices), 10, [[99, chips.compute_merkle_root(99, elements, indices)]])
+    s = orc.random_fr(1, 11)[0]
+    g, gl = orc.params_setup(job.k, s)
+    pk = OP.keygen_pk(job.cs, job.k, job.fixed, job.map_col, job.map_row)
+    wide = orc.XorShiftWide().draw(OP.rng_draws_needed(job.cs, job.k))
+    proof, _ = OP.create_proof(g, gl, pk, job.advice, job.instances, wide, job.transcript_repr)
+    fixed_c = np.array([gold.g1_mont(OP.commit(g, pk.fixed_polys[c])) for c in range(job.cs.num_fixed)]).reshape(-1, 8)
+    sigma_c = np.array([gold.g1_mont(OP.commit(g, p)) for p in pk.perm_polys]).reshape(-1, 8)
+    vk = zk.VerifyingKey(job.cs, job.k, fixed_c, sigma_c, np.asarray(g[0]).reshape(8), zk.g2_mul(s))
+    inst = [np.array(orc.ints_to_mont([v % PR.R for v in col])).reshape(-1, 4) for col in job.instances]
+    tr = np.array(orc.ints_to_mont([job.transcript_repr % PR.R])).reshape(4)
+    assert vk.verify_proof(inst, proof, tr)
+    wrong = [c.copy() for c in inst]
+    wrong[0][-1] = np.array(orc.ints_to_mont([12345])).reshape(4)
+    assert not vk.verify_proof(wrong, proof, tr)
