@@ -165,3 +165,24 @@ def test_reference_circuits_verify(zk, orc, which):
     wrong = [c.copy() for c in inst]
     wrong[0][-1] = np.array(orc.ints_to_mont([12345])).reshape(4)
     assert not vk.verify_proof(wrong, proof, tr)
+
+
+def test_unsatisfied_witness_is_rejected(zk, orc):
+    """A proof made from a witness that breaks a gate is well-formed but must not verify (the expected h(x) check)."""
+    from oracle import pairing as PR
+    from oracle import prover as OP
+    gold = importlib.import_module("tests.golden.make_golden")
+    synth = importlib.import_module(zk.__name__ + ".circuits_synth")
+    job = synth.small(5)
+    adv = np.array(job.advice[2])
+    adv[3] = orc.ints_to_mont([5])[0]                                  # breaks the bool gate
+    job.advice[2] = adv
+    s = orc.random_fr(1, 77)[0]
+    g, gl = orc.params_setup(job.k, s)
+    pk = OP.keygen_pk(job.cs, job.k, job.fixed, job.map_col, job.map_row)
+    wide = orc.XorShiftWide().draw(OP.rng_draws_needed(job.cs, job.k))
+    proof, _ = OP.create_proof(g, gl, pk, job.advice, job.instances, wide, job.transcript_repr)
+    z, vk, inst, good = load_golden(zk, "small_k5")                      # same circuit, same SRS secret (seed 77)
+    assert len(proof) == len(good) and proof != good
+    assert vk.verify_proof(inst, good, z["transcript_repr"])
+    assert not vk.verify_proof(inst, proof, z["transcript_repr"])
