@@ -36,6 +36,7 @@ def test_field_limbs_match_oracle(orc, which):
     (0, 10, 2, 12), (1, 10, 2, 12), (3, 10, 2, 12), (6, 10, 2, 12),      # single pass
     (6, 3, 1, 12), (7, 4, 2, 12), (8, 4, 3, 5),                           # two passes, tile cap binding
     (6, 2, 1, 12), (9, 3, 2, 12), (8, 3, 0, 12), (10, 4, 2, 5),          # three passes
+    (10, 5, 3, 12), (11, 4, 3, 12), (12, 4, 3, 12), (8, 8, 3, 12),        # tiles of 8 columns: j-major butterfly order
 ])
 def test_ntt_pass_structure(orc, log_n, max_log_m, max_log_tw, cap):
     rnd = random.Random(100 + log_n)
