@@ -15,8 +15,13 @@ Workloads (one "step" = one pass of the hot path over one batch of synthetic inp
   ntt             : one best_fft over 2^L uniform Fr elements
 Prints ONE JSON line: value = device-timed with inputs resident in HBM; e2e = the same call through
 the host-buffer C-ABI entry point (pinned host witness / scalars -> H2D -> kernels -> D2H proof);
-roofline for the dominant kernel; cpu_baseline on rank 0.  With N > 1 every rank proves its own
-instance (weak scaling, no data-path collective); time is the max over ranks.
+roofline for the dominant kernel; cpu_baseline on rank 0.  With N > 1 the default shards ONE proof over
+the N GPUs (strong scaling: every rank holds SRS + pk and the same inputs, commits its columns, runs
+its lookups, extends / evaluates its quotient cosets and multiplies its point range of the dense
+commits; NCCL inside the library, see include/b200zk.h), checks the proof bytes against the
+single-GPU proof of the same inputs outside the timed region ("verified"), and adds a "sharded"
+block: one MSM 2^26 by point range and one NTT 2^26 four-step over the same N GPUs, each verified at
+2^24.  --mode replicas gives the round-1 behaviour (one independent proof per GPU, weak scaling).
 """
 import argparse
 import ctypes
@@ -200,11 +205,18 @@ def run_gpu(args):
     line = {"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "scaling": "weak", "vs_baseline": None,
             "data": "synthetic", "impl": "b200zk"}
     extra = {}
+    sharded_proof = False
     if args.workload == "prove":
         k = args.k
         n = 1 << k
         synth = importlib.import_module(zk.__name__ + ".circuits_synth")
-        job = build_job(zk, args.circuit, k, 1 + rank)
+        sharded_proof = world > 1 and args.mode == "sharded"
+        if sharded_proof:
+            rank_seed = 0                                         # every rank gets the same circuit, witness and rng stream
+            line["scaling"] = "strong"
+        else:
+            rank_seed = rank
+        job = build_job(zk, args.circuit, k, 1 + rank_seed)
         params = zk.ParamsKZG.setup(be, k, random_scalars(1, 4242)[0])
         pk = zk.ProvingKey(params, job.cs, k, job.fixed, job.map_col, job.map_row)
         A = job.cs.num_advice
@@ -213,10 +225,18 @@ def run_gpu(args):
             h_adv[c * n:(c + 1) * n] = job.advice[c]
         h_cols = [h_adv[c * n:(c + 1) * n] for c in range(A)]
         h_wide = be.pinned_empty((pk.rng_draws, 8))
-        h_wide[:] = np.random.Generator(np.random.PCG64(99 + rank)).integers(0, 1 << 64, size=(pk.rng_draws, 8), dtype=np.uint64)
+        h_wide[:] = np.random.Generator(np.random.PCG64(99 + rank_seed)).integers(0, 1 << 64, size=(pk.rng_draws, 8), dtype=np.uint64)
         d_adv, d_wide = be.to_device(h_adv), be.to_device(h_wide)
         lut = synth.mont_from_ints(job.instances[0] + [job.transcript_repr])
         inst, tr_repr = [lut[:-1]], lut[-1]
+        single_proof = None
+        if sharded_proof:
+            # reference bytes: the single-GPU proof of the same inputs, made on this rank before its ctx joins the
+            # communicator (outside every timed region)
+            single_proof = pk.create_proof_dev(d_adv, inst, d_wide, tr_repr)
+            uid = [zk.Backend.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            be.comm_init(world, rank, uid[0])
 
         def step_dev():
             return pk.create_proof_dev(d_adv, inst, d_wide, tr_repr)
@@ -312,8 +332,9 @@ def run_gpu(args):
         workload = WORKLOAD_TEXT["ntt"].format(L=L)
 
     # ---- device-timed region: inputs resident in HBM --------------------------------
+    last = None
     for _ in range(max(args.warmup, 3)):
-        step_dev()
+        last = step_dev()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -341,7 +362,23 @@ def run_gpu(args):
     ms_per_step = ms / args.steps
     if args.workload == "prove":
         value, e2e_value = ms_per_step, e2e_ms
-        extra["proofs_per_s_all_gpus"] = world / (ms_per_step / 1e3)
+        extra["proofs_per_s_all_gpus"] = (1 if sharded_proof else world) / (ms_per_step / 1e3)
+        if sharded_proof:
+            import hashlib
+            import torch
+            e2e_proof = step_e2e()
+            ok = int(last == single_proof and e2e_proof == single_proof)
+            t = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", local))
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            extra["verified"] = bool(t.item())
+            extra["verification"] = {"what": "sharded proof bytes (device-resident and host-buffer entry points) == the single-GPU proof of the same circuit, "
+                                             "witness, SRS and rng stream, compared on every rank (all-reduce MIN), outside the timed region",
+                                     "proof_sha256_sharded": hashlib.sha256(last).hexdigest(), "proof_sha256_single_gpu": hashlib.sha256(single_proof).hexdigest(),
+                                     "proof_bytes": len(last)}
+            extra["parallelism"] = (f"one proof over {world} GPUs: advice / lookup / grand-product commits by column, lookups by argument, quotient by coset "
+                                    f"({pk.degree - 1} cosets), dense commits (h pieces, random polynomial, SHPLONK) by point range, evaluations by query; "
+                                    "polynomial exchange = grouped ncclBroadcast, commitments / partial sums = 64-byte all-gathers")
+            h2d = h2d * world                                         # every rank uploads the witness over its own PCIe link
     else:
         value = units_per_step * world / (ms_per_step / 1e3)
         e2e_value = units_per_step * world / (e2e_ms / 1e3)
@@ -407,6 +444,14 @@ def run_gpu(args):
                             "traffic": None, "peak_source": peak_src,
                             "note": "254-bit butterflies are IMAD-bound on B200 (see DESIGN.md): 64N bytes vs ~15N field muls"}
     line.update(extra)
+    if args.workload == "prove" and not args.no_sharded_sweep:
+        # BASELINE's "MSM Mpts/s & NTT GB/s at 1/2/4/8 B200": one MSM by point range and one NTT four-step over the
+        # same N GPUs, in the same line.  The proving key is released first (2^26 points are 4 GiB per basis).
+        pk.close(); params.close(); d_adv.free(); d_wide.free()
+        try:
+            line["sharded"] = sharded_sweep(zk, be, dist, rank, world, local, args)
+        except Exception as e:                                      # the headline number stands on its own
+            line["sharded"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         line["cpu_baseline"] = cpu_baseline(args)
         emit(line)
@@ -414,6 +459,122 @@ def run_gpu(args):
     be.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def sharded_sweep(zk, be, dist, rank, world, local, args):
+    """One best_multiexp of 2^L points sharded by point range (partial sums all-gathered, 96 B per rank) and one
+    best_fft of 2^L elements sharded four-step with the exchange fused into the column-step kernel (NVLink peer
+    stores), over the `world` GPUs of this run; L = --sweep-log-n (26).  Both are verified at 2^--sweep-verify-log-n
+    (24) outside the timed regions: the sharded MSM against ONE generic-path best_multiexp over the concatenated
+    bases and scalars on rank 0, the sharded NTT rows against Horner evaluations of the full input on every rank."""
+    import torch
+    sharded = importlib.import_module(zk.__name__ + ".sharded")
+    dev = torch.device("cuda", local) if dist is not None else None
+    lw = int(np.log2(world))
+    out = {"n_gpus": world}
+
+    def msm_at(L, reps):
+        shard_log = L - lw
+        ns = 1 << shard_log
+        params = zk.ParamsKZG.setup(be, shard_log, random_scalars(1, 4242 + rank)[0])
+        h_sc = random_scalars(ns, 100 + rank)
+        d_sc = be.to_device(h_sc)
+        sc = sharded.ShardedCommit(sharded.GpuCommitEngine(zk, params), dev)
+        res = sc.commit(d_sc)
+        ms = None
+        if reps:
+            for _ in range(2):
+                sc.commit(d_sc)
+            ms = timed(be, dist, local, reps, lambda: sc.commit(d_sc)) / reps
+        return params, d_sc, res, ms
+
+    # ---- MSM: verify at Lv, time at L
+    Lv, L = args.sweep_verify_log_n, args.sweep_log_n
+    params, d_sc, res, _ = msm_at(Lv, 0)
+    ok = True
+    if rank == 0:
+        ns = 1 << (Lv - lw)
+        bases = [params.read(lagrange=False)[0]]
+        for r in range(1, world):
+            pr = zk.ParamsKZG.setup(be, Lv - lw, random_scalars(1, 4242 + r)[0])
+            bases.append(pr.read(lagrange=False)[0])
+            pr.close()
+        d_b = be.to_device(np.concatenate(bases))
+        d_s = be.to_device(np.concatenate([random_scalars(ns, 100 + r) for r in range(world)]))
+        one = be.best_multiexp_dev(d_s, d_b, ns * world)           # generic path: no fixed-base table, explicit bases
+        d_b.free(); d_s.free()
+        ok = bool(np.array_equal(one, res))
+    params.close(); d_sc.free()
+    params, d_sc, res, ms = msm_at(L, 3)
+    params.close(); d_sc.free()
+    out["msm"] = {"log_n": L, "mpts_per_s": (1 << L) / 1e6 / (ms / 1e3), "ms": ms,
+                  "path": "ParamsKZG commit over each rank's point range (fixed-base window tables when they fit in HBM, else the generic Pippenger), "
+                          "partial sums combined by a 96-byte all-gather + host additions",
+                  "verified": ok, "verified_how": f"2^{Lv} points: sharded result == one generic-path best_multiexp over the concatenation (rank 0)"}
+
+    # ---- NTT: verify at Lv, time at L
+    def ntt_at(L, reps, check):
+        log_r = min(10, L // 2)
+        R, C = 1 << log_r, 1 << (L - log_r)
+        omega = zk.EvaluationDomain(be, 2, L).omega
+        if world == 1:
+            h_a = random_scalars(1 << L, 300)
+            d_a = be.to_device(h_a)
+            good = True
+            if check:
+                d_in = be.to_device(h_a)
+                be.best_fft_dev(d_a, omega, L)
+                got = d_a.download((1 << L, 4))
+                wpow = zk.EvaluationDomain(be, 2, L)
+                for kk in (0, 1, 12345, (1 << L) - 1):
+                    x = wpow.rotate_omega(np.array(zk._FR_ONE, dtype=np.uint64), kk)
+                    good = good and bool(np.array_equal(be.eval_polynomial_dev(d_in, 1 << L, x), got[kk]))
+                d_in.free()
+            ms = None
+            if reps:
+                for _ in range(2):
+                    be.best_fft_dev(d_a, omega, L)
+                ms = timed(be, dist, local, reps, lambda: be.best_fft_dev(d_a, omega, L)) / reps
+            d_a.free()
+            return good, ms
+        cg, rg = C // world, R // world
+        fs = sharded.FourStepNTTFused(zk, be, L, log_r, rank, world, dev)
+        omega_c = zk.EvaluationDomain(be, 2, L - log_r).omega
+        good = True
+        if check:
+            full = random_scalars(1 << L, 300)                       # the same input on every rank
+            mine = np.ascontiguousarray(full.reshape(R, C, 4)[:, rank * cg:(rank + 1) * cg])
+            block = torch.from_numpy(mine.view(np.int64)).to(dev)
+            rows = fs.forward(block, omega, omega_c).download((rg, C, 4))   # [k_r local][k_c] = X[k_r + R k_c]
+            d_in = be.to_device(full)
+            dom = zk.EvaluationDomain(be, 2, L)
+            for (a, b) in ((0, 0), (rg - 1, C - 1), (rg // 2, 4321 % C), (1 % rg, C // 2)):
+                kk = (rank * rg + a) + R * b
+                x = dom.rotate_omega(np.array(zk._FR_ONE, dtype=np.uint64), kk)
+                good = good and bool(np.array_equal(be.eval_polynomial_dev(d_in, 1 << L, x), rows[a, b]))
+            d_in.free()
+        else:
+            mine = random_scalars((1 << L) // world, 300 + rank).reshape(R, cg, 4)
+            block = torch.from_numpy(mine.view(np.int64)).to(dev)
+        ms = None
+        if reps:
+            for _ in range(2):
+                fs.forward(block, omega, omega_c)
+            ms = timed(be, dist, local, reps, lambda: fs.forward(block, omega, omega_c)) / reps
+        fs.close()
+        del block
+        return good, ms
+
+    good, _ = ntt_at(Lv, 0, True)
+    _, ms = ntt_at(L, 5, False)
+    if dist is not None:
+        t = torch.tensor([int(good)], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        good = bool(t.item())
+    out["ntt"] = {"log_n": L, "gb_per_s": 64.0 * (1 << L) / 1e9 / (ms / 1e3), "ms": ms,
+                  "path": "single-GPU best_fft" if world == 1 else "four-step, column step fused with the exchange (NVLink peer stores), then row step",
+                  "verified": good, "verified_how": f"2^{Lv} elements: output rows == Horner evaluation of the full input at 4 indices per rank"}
+    return out
 
 
 # --------------------------------------------------------------------------- CPU legs
@@ -526,6 +687,10 @@ def main():
     ap.add_argument("--log-n", type=int, default=24, help="msm / ntt size")
     ap.add_argument("--cpu-log-n", type=int, default=None, help="msm / ntt: size of the bounded CPU sample")
     ap.add_argument("--profile-step", action="store_true", help="bracket one extra step with cudaProfilerStart/Stop (ncu --profile-from-start off)")
+    ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"], help="prove with N > 1: one proof over N GPUs (default) or N independent proofs")
+    ap.add_argument("--no-sharded-sweep", action="store_true", help="prove: skip the MSM / NTT 2^26 block")
+    ap.add_argument("--sweep-log-n", type=int, default=26)
+    ap.add_argument("--sweep-verify-log-n", type=int, default=24)
     args = ap.parse_args()
     if args.cpu_log_n is None:
         args.cpu_log_n = 20 if args.workload == "msm" else 22

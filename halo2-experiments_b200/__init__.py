@@ -98,7 +98,11 @@ class DeviceBuffer:
 class Backend:
     """One CUDA device + stream + scratch (b200zk_ctx)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, _ctx=None):
+        self._borrowed = _ctx is not None           # a group's ctx: the group destroys it
+        if _ctx is not None:
+            self._ctx = _ctx
+            return
         self._ctx = ctypes.c_void_p()
         rc = lib().b200zk_ctx_create(ctypes.c_int32(device), ctypes.byref(self._ctx))
         if rc != OK:
@@ -107,9 +111,29 @@ class Backend:
                               "(this backend has no CPU fallback)")
 
     def close(self):
-        if self._ctx:
+        if self._ctx and not self._borrowed:
             lib().b200zk_ctx_destroy(self._ctx)
-            self._ctx = None
+        self._ctx = None
+
+    # -- one proof over several GPUs, one process per GPU (NCCL inside the library) --
+    @staticmethod
+    def comm_unique_id():
+        """128-byte rendezvous id (rank 0 creates it and hands it to the other ranks, e.g. with
+        torch.distributed.broadcast_object_list)."""
+        buf = (ctypes.c_uint8 * 128)()
+        rc = lib().b200zk_comm_unique_id(buf)
+        if rc != OK:
+            raise B200zkError(f"b200zk_comm_unique_id failed: {rc} (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    def comm_init(self, world, rank, unique_id):
+        """Collective: after it, create_proof on this backend's proving keys is rank `rank` of one proof
+        sharded over `world` GPUs (every rank calls it with the same inputs, every rank gets the proof)."""
+        self._check(lib().b200zk_ctx_comm_init(self._ctx, ctypes.c_uint32(world), ctypes.c_uint32(rank),
+                                               (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)))
+
+    def comm_destroy(self):
+        self._check(lib().b200zk_ctx_comm_destroy(self._ctx))
 
     def _check(self, rc):
         if rc != OK:
@@ -383,6 +407,60 @@ class ProvingKey:
         out = (ctypes.c_float * 7)()
         self.backend._check(lib().b200zk_pk_last_phase_ms(self._h, out))
         return dict(zip(["msm", "ntt", "quotient", "lookup", "permutation", "open", "other"], [float(x) for x in out]))
+
+
+class Group:
+    """Several GPUs driven from this process (b200zk_group_*): `backends[r]` is rank r's Backend.  Build the
+    params and a ProvingKey on every backend, then `create_proof(pks, ...)` shards ONE proof over the ranks.
+    `devices` may repeat a device (ranks then share it: the single-GPU test configuration)."""
+
+    def __init__(self, devices):
+        L = lib()
+        L.b200zk_group_ctx.restype = ctypes.c_void_p
+        L.b200zk_group_size.restype = ctypes.c_uint32
+        L.b200zk_group_destroy.restype = None
+        self._h = ctypes.c_void_p()
+        arr = (ctypes.c_int32 * len(devices))(*devices)
+        rc = L.b200zk_group_create(arr, ctypes.c_uint32(len(devices)), ctypes.byref(self._h))
+        if rc != OK:
+            self._h = None
+            raise B200zkError(f"b200zk_group_create({list(devices)}) failed with code {rc}")
+        self.backends = [Backend(_ctx=ctypes.c_void_p(L.b200zk_group_ctx(self._h, ctypes.c_uint32(r)))) for r in range(len(devices))]
+
+    def close(self):
+        if self._h:
+            lib().b200zk_group_destroy(self._h)
+            self._h = None
+            for b in self.backends:
+                b._ctx = None
+
+    def create_proof(self, pks, advice_columns, instances, rng_wide, transcript_repr):
+        """One plonk::create_proof over all ranks from host inputs (pks[r] built on backends[r])."""
+        pk0 = pks[0]
+        adv = [np.ascontiguousarray(a, dtype=np.uint64).reshape(pk0.n, 4) for a in advice_columns]
+        keep, inst_ptrs, lens = pk0._instances(instances)
+        wide = np.ascontiguousarray(rng_wide, dtype=np.uint64).reshape(-1, 8)
+        if wide.shape[0] < pk0.rng_draws:
+            raise B200zkError(f"rng stream too short: need {pk0.rng_draws} draws")
+        out = np.zeros(pk0.proof_size, dtype=np.uint8)
+        ln = ctypes.c_size_t()
+        handles = (ctypes.c_void_p * len(pks))(*[p._h for p in pks])
+        self.backends[0]._check(lib().b200zk_group_create_proof(self._h, handles, _ptr_array(adv), inst_ptrs, _p(lens), _p(wide),
+                                                                _p(_fr(transcript_repr, 1)), _p(out), ctypes.c_size_t(out.shape[0]), ctypes.byref(ln)))
+        return bytes(out[: ln.value])
+
+    def create_proof_dev(self, pks, d_advice, instances, d_rng_wide, transcript_repr):
+        """Same with rank r's inputs resident on its device: d_advice[r], d_rng_wide[r] DeviceBuffers."""
+        pk0 = pks[0]
+        keep, inst_ptrs, lens = pk0._instances(instances)
+        out = np.zeros(pk0.proof_size, dtype=np.uint8)
+        ln = ctypes.c_size_t()
+        handles = (ctypes.c_void_p * len(pks))(*[p._h for p in pks])
+        adv = (ctypes.c_void_p * len(pks))(*[d.ptr for d in d_advice])
+        rng = (ctypes.c_void_p * len(pks))(*[d.ptr for d in d_rng_wide])
+        self.backends[0]._check(lib().b200zk_group_create_proof_dev(self._h, handles, adv, inst_ptrs, _p(lens), rng, _p(_fr(transcript_repr, 1)),
+                                                                    _p(out), ctypes.c_size_t(out.shape[0]), ctypes.byref(ln)))
+        return bytes(out[: ln.value])
 
 
 class ParamsKZG:

@@ -1,5 +1,6 @@
 // C ABI of libb200zk.so (declarations and reference mapping: include/b200zk.h).
 #include "context.hpp"
+#include "comm.hpp"
 #include <vector>
 #include <new>
 #include <cuda_profiler_api.h>
@@ -139,6 +140,20 @@ int32_t params_commit_multi(b200zk_params* p, const fe_t* const* d_polys, uint32
     return B200ZK_OK;
 }
 
+int32_t params_commit_range(b200zk_params* p, const fe_t* const* d_polys, uint32_t ncols, size_t lo, size_t hi, bool lagrange, host::HAffine* outs) {
+    b200zk_ctx* ctx = p->ctx;
+    const affine_t* bases = lagrange ? p->d_g_lagrange : p->d_g;
+    if (!bases) return fail(ctx, B200ZK_EINVAL, "commit", "basis not loaded");
+    const size_t n = (size_t)1 << p->k;
+    if (lo > hi || hi > n) return fail(ctx, B200ZK_EINVAL, "commit", "point range outside the SRS");
+    if (ncols == 0) return B200ZK_OK;
+    const affine_t* table = lagrange ? p->d_gl_pre : p->d_g_pre;
+    std::vector<const fe_t*> cols(ncols);
+    for (uint32_t b = 0; b < ncols; ++b) cols[b] = d_polys[b] + lo;
+    // table row j of point i sits at table[j * n + i]: offsetting the base pointer by lo keeps that stride
+    return msm_run_multi(ctx, cols.data(), ncols, (table ? table : bases) + lo, hi - lo, table ? &p->pre : nullptr, outs, nullptr);
+}
+
 int32_t params_commit_run(b200zk_params* p, const fe_t* d_poly, size_t len, bool lagrange, host::HAffine* out) {
     return params_commit_multi(p, &d_poly, 1, len, lagrange, out);
 }
@@ -188,6 +203,8 @@ void b200zk_ctx_destroy(b200zk_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && ctx->comm_owned) delete ctx->comm;
+    ctx->comm = nullptr;
     for (auto& kv : ctx->ntt_plans) { cudaFree(kv.second.roots); cudaFree(kv.second.tw_lo); cudaFree(kv.second.tw_hi); cudaFree(kv.second.tw_full); }
     for (Workspace* w : {&ctx->ntt_scratch, &ctx->ntt_scratch2, &ctx->msm_ws, &ctx->msm_ws2, &ctx->lookup_ws, &ctx->io_a, &ctx->io_b, &ctx->poly_ws, &ctx->poly_heads, &ctx->poly_batch, &ctx->setup_ws}) if (w->p) cudaFree(w->p);
     if (ctx->d_gen_table) cudaFree(ctx->d_gen_table);

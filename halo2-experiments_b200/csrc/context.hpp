@@ -30,6 +30,8 @@ struct Workspace {
     size_t cap = 0;
 };
 
+struct Comm;                    // comm.hpp: the exchanges of a proof sharded over several GPUs
+
 }  // namespace b200zk
 
 struct b200zk_ctx {
@@ -47,6 +49,9 @@ struct b200zk_ctx {
     b200zk::Workspace ntt_scratch, ntt_scratch2, msm_ws, msm_ws2, io_a, io_b, poly_ws, poly_heads, poly_batch, setup_ws, lookup_ws;
     b200zk::affine_t* d_gen_table = nullptr;                          // fixed-base table of the G1 generator (setup.cu)
     void* pinned = nullptr;                                            // small pinned staging (results)
+    bool ntt_attr_set = false;                                         // cudaFuncSetAttribute is per device: once per ctx
+    b200zk::Comm* comm = nullptr;                                      // set: create_proof on this ctx is one rank of a sharded proof
+    bool comm_owned = false;                                           // comm created by b200zk_ctx_comm_init (not by a group)
 };
 
 struct b200zk_domain {
@@ -123,6 +128,9 @@ int32_t msm_precompute_run(b200zk_ctx* ctx, const affine_t* d_bases, size_t n, u
 // commit over a params basis, through the fixed-base table when it exists
 int32_t params_commit_run(b200zk_params* p, const fe_t* d_poly, size_t len, bool lagrange, host::HAffine* out);
 int32_t params_commit_multi(b200zk_params* p, const fe_t* const* d_polys, uint32_t ncols, size_t len, bool lagrange, host::HAffine* outs);
+// partial commitments over the point range [lo, hi): sum_{lo <= i < hi} poly[i] * basis[i] (one rank's share of a
+// commit sharded by point range; the partial sums are added on the host)
+int32_t params_commit_range(b200zk_params* p, const fe_t* const* d_polys, uint32_t ncols, size_t lo, size_t hi, bool lagrange, host::HAffine* outs);
 // builds the fixed-base tables of a params object if memory allows (capi.cu)
 int32_t params_build_tables(b200zk_params* p);
 

@@ -50,6 +50,7 @@ struct ExprArgs {
     const int32_t* q_instance;
     uint32_t log_size;                  // rotations wrap inside blocks of 2^log_size rows (= n: one coset / the Lagrange domain)
     uint32_t rows;                      // rows evaluated: n, or C * n on the quotient cosets
+    uint32_t row0;                      // first row (a rank of a sharded proof evaluates its own cosets only)
     uint32_t rot_scale;                 // 1
     fe_t factors[4];                    // theta, beta, gamma, y
     fe_t ypow[9];                       // y^m for GROUP(m), m <= 8 (gate programs only)

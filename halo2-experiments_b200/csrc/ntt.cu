@@ -127,11 +127,10 @@ static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, f
         ZK_TRY(ws_reserve(ctx, ctx->ntt_scratch, N * batch * sizeof(fe_t)));
         scratch = (fe_t*)ctx->ntt_scratch.p;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->ntt_attr_set) {                                   // function attributes are per device (and per ctx, cheaply)
         ZK_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(sizeof(fe_t) << NTT_TILE_CAP_LOG)));
-        attr_set = true;
+        ctx->ntt_attr_set = true;
     }
     for (uint32_t p = 0; p < s.npass; ++p) {
         const NttPassShape& q = s.pass[p];
@@ -207,10 +206,9 @@ int32_t ntt_colstep_run(b200zk_ctx* ctx, fe_t* d_block, uint32_t log_r, uint32_t
         it = ctx->ntt_plans.emplace(key, plan).first;
     }
     const NttPlan& plan = it->second;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->ntt_attr_set) {
         ZK_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(fe_t) << NTT_TILE_CAP_LOG)));
-        attr_set = true;
+        ctx->ntt_attr_set = true;
     }
     NttPassArgs a{};
     a.in = d_block; a.out = d_block;

@@ -5,6 +5,7 @@
 // and does O(#queries) scalar work; every O(n) step is a kernel.  Step numbers refer to
 // SURVEY.md §3.2.
 #include "context.hpp"
+#include "comm.hpp"
 #include "cs_desc.hpp"
 #include "expr.cuh"
 #include "prover_kernels.cuh"
@@ -12,9 +13,11 @@
 #include <algorithm>
 #include <array>
 #include <map>
+#include <memory>
 #include <new>
 #include <set>
 #include <string>
+#include <thread>
 
 using namespace b200zk;
 using host::HAffine;
@@ -29,7 +32,7 @@ static fe_t to_dev(const HFr& x) { fe_t r; memcpy(r.l, x.v, 32); return r; }
 // ------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(PK_THREADS) expr_kernel(const ExprArgs a) {
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < a.rows) expr_eval_row(a, idx);
+    if (idx < a.rows) expr_eval_row(a, a.row0 + idx);
 }
 __global__ void __launch_bounds__(PK_THREADS) from_u512_kernel(const uint32_t* wide, fe_t* out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -53,15 +56,15 @@ __global__ void __launch_bounds__(PK_THREADS) lookup_num_kernel(const LookupProd
 }
 __global__ void __launch_bounds__(PK_THREADS) quot_perm_a_kernel(const QuotPermAArgs a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.rows) quot_perm_a_row(a, i);
+    if (i < a.rows) quot_perm_a_row(a, a.row0 + i);
 }
 __global__ void __launch_bounds__(PK_THREADS) quot_perm_b_kernel(const QuotPermBArgs a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.rows) quot_perm_b_row(a, i);
+    if (i < a.rows) quot_perm_b_row(a, a.row0 + i);
 }
 __global__ void __launch_bounds__(PK_THREADS) quot_lookup_kernel(const QuotLookupArgs a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.rows) quot_lookup_row(a, i);
+    if (i < a.rows) quot_lookup_row(a, a.row0 + i);
 }
 __global__ void __launch_bounds__(PK_THREADS) coset_interpolate_kernel(const fe_t* g, const fe_t* inv_pow, const fe_t* vinv, uint32_t C, size_t n, fe_t* out, const fe_t* extra) {
     size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -240,11 +243,6 @@ static HFr rotate_omega(const b200zk_domain* d, const HFr& x, int rot) {
     return rot >= 0 ? x * d->omega.pow_u64((uint64_t)rot) : x * d->omega_inv.pow_u64((uint64_t)(-(int64_t)rot));
 }
 
-// ParamsKZG::commit / commit_lagrange on a device polynomial
-static int32_t commit_dev(b200zk_pk* pk, const fe_t* d_poly, size_t len, bool lagrange, HAffine* out) {
-    PhaseTimer t(pk, PH_MSM);
-    return params_commit_run(pk->params, d_poly, len, lagrange, out);
-}
 // Side-stream section: between construction and destruction every launch that goes through
 // ctx->stream (NTTs, phase timers) lands on the low-priority side stream, ordered after everything
 // the main stream has enqueued so far; the main stream consumes the results after waiting for
@@ -422,6 +420,78 @@ static bool ex_share_common(const std::vector<uint32_t>& src, const std::vector<
     return true;
 }
 
+// ------------------------------------------------------------------ one proof over several ranks
+// Rank layout of a sharded create_proof (comm.hpp).  G = 1 degenerates to the single-GPU prover: every
+// `mine` test is true, every range is the whole, every exchange is a no-op.
+struct Shard {
+    Comm* cm; int G, R; uint32_t q;
+    explicit Shard(b200zk_pk* pk) : cm(pk->ctx->comm), G(cm ? cm->world : 1), R(cm ? cm->rank : 0), q(pk->q) {}
+    bool on() const { return G > 1; }
+    // columns / lookups / permutation sets round-robin
+    int owner(uint32_t i) const { return (int)(i % (uint32_t)G); }
+    bool mine(uint32_t i) const { return owner(i) == R; }
+    // quotient cosets in contiguous blocks: rank r evaluates cosets [coset_lo(r), coset_lo(r + 1))
+    uint32_t coset_lo(int r) const { return (uint32_t)((uint64_t)q * (uint32_t)r / (uint32_t)G); }
+    int coset_owner(uint32_t j) const { for (int r = 0; r < G; ++r) if (j >= coset_lo(r) && j < coset_lo(r + 1)) return r; return 0; }
+    // point range of a dense commit
+    size_t pt_lo(size_t len, int r) const { return len * (size_t)r / (size_t)G; }
+};
+
+// Commitments to `cols`, column i computed by rank owners[i]; every rank ends up with all of them.  `flag` (optional)
+// is OR-ed over the ranks on the way (the lookup permutation's "input not in table" bit).
+static int32_t commit_multi_split(b200zk_pk* pk, const Shard& sh, const std::vector<const fe_t*>& cols, const std::vector<int>& owners,
+                                  size_t len, bool lagrange, std::vector<HAffine>& outs, uint32_t* flag = nullptr) {
+    if (!sh.on()) return commit_multi_dev(pk, cols, len, lagrange, outs);
+    std::vector<const fe_t*> my;
+    std::vector<size_t> slot_of(cols.size());
+    std::vector<size_t> used(sh.G, 0);
+    for (size_t i = 0; i < cols.size(); ++i) { slot_of[i] = used[owners[i]]++; if (owners[i] == sh.R) my.push_back(cols[i]); }
+    size_t slots = 0;
+    for (size_t u : used) slots = std::max(slots, u);
+    std::vector<HAffine> mp;
+    ZK_TRY(commit_multi_dev(pk, my, len, lagrange, mp));
+    const size_t bytes = slots * sizeof(HAffine) + 8;
+    std::vector<uint8_t> send(bytes, 0), recv(bytes * sh.G);
+    if (!mp.empty()) memcpy(send.data(), mp.data(), mp.size() * sizeof(HAffine));
+    if (flag) memcpy(send.data() + slots * sizeof(HAffine), flag, 4);
+    {
+        PhaseTimer t(pk, PH_OTHER);
+        ZK_TRY(sh.cm->allgather_host(pk->ctx, send.data(), bytes, recv.data(), pk->ctx->stream));
+    }
+    outs.resize(cols.size());
+    for (size_t i = 0; i < cols.size(); ++i) memcpy(&outs[i], recv.data() + (size_t)owners[i] * bytes + slot_of[i] * sizeof(HAffine), sizeof(HAffine));
+    if (flag) for (int r = 0; r < sh.G; ++r) { uint32_t f; memcpy(&f, recv.data() + (size_t)r * bytes + slots * sizeof(HAffine), 4); *flag |= f; }
+    return B200ZK_OK;
+}
+
+// Dense commitments sharded by point range: every rank multiplies its slice [lo, hi) of every
+// column, the G partial sums per column are exchanged (64 bytes each) and added on the host.
+static int32_t commit_multi_range(b200zk_pk* pk, const Shard& sh, const std::vector<const fe_t*>& cols, size_t len, bool lagrange,
+                                  std::vector<HAffine>& outs) {
+    if (!sh.on()) return commit_multi_dev(pk, cols, len, lagrange, outs);
+    const uint32_t m = (uint32_t)cols.size();
+    std::vector<HAffine> part(m);
+    {
+        PhaseTimer t(pk, PH_MSM);
+        ZK_TRY(params_commit_range(pk->params, cols.data(), m, sh.pt_lo(len, sh.R), sh.pt_lo(len, sh.R + 1), lagrange, part.data()));
+    }
+    std::vector<HAffine> all((size_t)m * sh.G);
+    {
+        PhaseTimer t(pk, PH_OTHER);
+        ZK_TRY(sh.cm->allgather_host(pk->ctx, part.data(), m * sizeof(HAffine), all.data(), pk->ctx->stream));
+    }
+    outs.resize(m);
+    for (uint32_t i = 0; i < m; ++i) {
+        host::HXyzz acc = host::hx_identity();
+        for (int r = 0; r < sh.G; ++r) {
+            const HAffine& a = all[(size_t)r * m + i];
+            if (!(a.x.is_zero() && a.y.is_zero())) acc = host::hx_add(acc, host::hx_from_affine(a));
+        }
+        outs[i] = host::hx_to_affine(acc);
+    }
+    return B200ZK_OK;
+}
+
 // ------------------------------------------------------------------ create_proof
 static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_device, const void* const* advice_host,
                      const void* const* instance_columns, const uint32_t* instance_lens, const void* rng_wide, bool rng_on_device,
@@ -430,6 +500,8 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     const CsDesc& cs = pk->cs;
     const b200zk_domain* dom = pk->dom;
     cudaStream_t st = ctx->stream;
+    for (uint32_t c = 0; c < cs.I; ++c) if (instance_lens[c] && !instance_columns[c]) return fail(ctx, B200ZK_EINVAL, "create_proof", "null instance column");
+    if (!advice_on_device) for (uint32_t c = 0; c < cs.A; ++c) if (!advice_host[c]) return fail(ctx, B200ZK_EINVAL, "create_proof", "null advice column");
     cudaStreamSynchronize(ctx->stream2);                          // nothing of an earlier (failed) proof may still be writing the arena
     if (pk->copy_stream) cudaStreamSynchronize(pk->copy_stream);
     const size_t n = pk->n, ext = pk->ext_n;
@@ -439,6 +511,20 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     for (float& f : pk->phase_ms) f = 0;
     pk->timer_used = 0;
     ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const Shard sh(pk);
+    // quotient cosets this rank extends and evaluates
+    const uint32_t cj0 = sh.coset_lo(sh.R), cj1 = sh.coset_lo(sh.R + 1);
+    if (sh.on()) ZK_TRY(sh.cm->set_window(ctx, pk->arena, pk->arena_bytes));
+    auto share = [&](const std::vector<CommPiece>& pieces) -> int32_t {
+        if (!sh.on() || pieces.empty()) return B200ZK_OK;
+        PhaseTimer t(pk, PH_OTHER);
+        return sh.cm->share(ctx, pieces.data(), pieces.size(), ctx->stream);
+    };
+    auto my_cosets = [&](const fe_t* d_coeffs, fe_t* d_out, uint32_t j0, uint32_t j1) -> int32_t {     // cosets [j0, j1) of d_out
+        if (j0 >= j1) return B200ZK_OK;
+        PhaseTimer t(pk, PH_NTT);
+        return ntt_run_cosets(ctx, d_coeffs, d_out + (size_t)j0 * pk->n, pk->dom->k, pk->dom->omega, pk->coset_pow + (size_t)j0 * pk->n, j1 - j0);
+    };
     ZK_CUDA(ctx, cudaMemsetAsync(pk->d_err, 0, 4, st));
     host::Transcript tr;
     Arena ar{pk->arena, pk->arena_bytes};
@@ -540,21 +626,28 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
             ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pk->col_events[c], 0));
             ZK_CUDA(ctx, cudaMemcpyAsync(advice_polys + (size_t)c * n, advice_values + (size_t)c * n, n * sizeof(fe_t), cudaMemcpyDeviceToDevice, ctx->stream));
             ZK_TRY(lagrange_to_coeff(pk, advice_polys + (size_t)c * n));
-            ZK_TRY(coeff_to_extended(pk, advice_polys + (size_t)c * n, advice_cosets + (size_t)c * ext));
+            ZK_TRY(my_cosets(advice_polys + (size_t)c * n, advice_cosets + (size_t)c * ext, cj0, cj1));
         }
-        for (uint32_t c = 0; c < I; ++c) ZK_TRY(coeff_to_extended(pk, inst_polys + (size_t)c * n, inst_cosets + (size_t)c * ext));
+        for (uint32_t c = 0; c < I; ++c) ZK_TRY(my_cosets(inst_polys + (size_t)c * n, inst_cosets + (size_t)c * ext, cj0, cj1));
     }
     // position of the random polynomial in the rng stream (draw order: SURVEY.md 8(a7))
     const size_t rpos_random = rpos + (size_t)L * (2 * (bf + 1) + 2) + (size_t)S * (bf + 1) + (size_t)L * (bf + 1);
     HAffine random_pt = {host::HFq::zero(), host::HFq::zero()};
     const bool random_early = !advice_on_device;
-    if (random_early) ZK_TRY(commit_dev(pk, rnd + rpos_random, n, false, &random_pt));
+    auto commit_random = [&]() -> int32_t {
+        std::vector<HAffine> pts;
+        ZK_TRY(commit_multi_range(pk, sh, {rnd + rpos_random}, n, false, pts));
+        random_pt = pts[0];
+        return B200ZK_OK;
+    };
+    if (random_early) ZK_TRY(commit_random());
     if (A) ZK_CUDA(ctx, cudaStreamWaitEvent(st, pk->col_events[A - 1], 0));
     {
         std::vector<const fe_t*> cols;
+        std::vector<int> owners;
         std::vector<HAffine> pts;
-        for (uint32_t c = 0; c < A; ++c) cols.push_back(advice_values + (size_t)c * n);
-        ZK_TRY(commit_multi_dev(pk, cols, n, true, pts));
+        for (uint32_t c = 0; c < A; ++c) { cols.push_back(advice_values + (size_t)c * n); owners.push_back(sh.owner(c)); }
+        ZK_TRY(commit_multi_split(pk, sh, cols, owners, n, true, pts));
         for (uint32_t c = 0; c < A; ++c) tr.write_point(pts[c]);
     }
     HFr ch[4];                                                    // theta, beta, gamma, y
@@ -562,8 +655,10 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     ch[EXF_BETA] = ch[EXF_GAMMA] = ch[EXF_Y] = HFr::zero();
 
     // ---- step 4: lookups, commit_permuted
+    // lookup l lives on rank l mod G from here to its grand product; every rank walks the rng stream
     for (uint32_t l = 0; l < L; ++l) {
         fe_t *cin = LK(l, 0), *ctab = LK(l, 1), *pin = LK(l, 2), *ptab = LK(l, 3), *pin_poly = LK(l, 4), *ptab_poly = LK(l, 5);
+        if (!sh.mine(l)) { rng_take(2 * (bf + 1) + 2); continue; }
         {
             PhaseTimer t(pk, PH_LOOKUP);
             ExprArgs ea = expr_args(pk, pk->lookup_prog[l].first, pk->lookup_prog[l].second, false, EXM_ACC01, ch, cin, ctab);
@@ -580,18 +675,24 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         ZK_TRY(lagrange_to_coeff(pk, ptab_poly));
         rng_take(1);
     }
-    if (L) {                                                      // permuted input / table commitments of all lookups, one batch
-        std::vector<const fe_t*> cols;
-        std::vector<HAffine> pts;
-        for (uint32_t l = 0; l < L; ++l) { cols.push_back(LK(l, 2)); cols.push_back(LK(l, 3)); }
-        ZK_TRY(commit_multi_dev(pk, cols, n, true, pts));
-        for (auto& pt : pts) tr.write_point(pt);
-    }
     {
         uint32_t err = 0;
-        ZK_CUDA(ctx, cudaMemcpyAsync(&err, pk->d_err, 4, cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, pk->d_err, 4, cudaMemcpyDeviceToHost, st));
         ZK_CUDA(ctx, cudaStreamSynchronize(st));
+        err = *(const uint32_t*)ctx->pinned;
+        if (L) {                                                  // permuted input / table commitments of all lookups, one batch
+            std::vector<const fe_t*> cols;
+            std::vector<int> owners;
+            std::vector<HAffine> pts;
+            for (uint32_t l = 0; l < L; ++l) { cols.push_back(LK(l, 2)); cols.push_back(LK(l, 3)); owners.push_back(sh.owner(l)); owners.push_back(sh.owner(l)); }
+            ZK_TRY(commit_multi_split(pk, sh, cols, owners, n, true, pts, &err));
+            for (auto& pt : pts) tr.write_point(pt);
+        }
         if (err) return fail(ctx, B200ZK_ESYNTH, "create_proof", "ConstraintSystemFailure: lookup input not in table");
+        // the permuted polynomials in coefficient form: every rank opens them, the coset owners extend them
+        std::vector<CommPiece> pieces;
+        for (uint32_t l = 0; l < L; ++l) { pieces.push_back({LK(l, 4), n * sizeof(fe_t), sh.owner(l)}); pieces.push_back({LK(l, 5), n * sizeof(fe_t), sh.owner(l)}); }
+        ZK_TRY(share(pieces));
     }
     ch[EXF_BETA] = tr.squeeze_challenge();
     ch[EXF_GAMMA] = tr.squeeze_challenge();
@@ -635,21 +736,23 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         }
         if (S) {                                                  // the S grand products: one batch of commitments, then coefficients and cosets
             std::vector<const fe_t*> cols;
+            std::vector<int> owners;
             std::vector<HAffine> pts;
-            for (uint32_t s = 0; s < S; ++s) cols.push_back(perm_polys + (size_t)s * n);
-            ZK_TRY(commit_multi_dev(pk, cols, n, true, pts));
+            for (uint32_t s = 0; s < S; ++s) { cols.push_back(perm_polys + (size_t)s * n); owners.push_back(sh.owner(s)); }
+            ZK_TRY(commit_multi_split(pk, sh, cols, owners, n, true, pts));
             for (auto& pt : pts) tr.write_point(pt);
         }
         for (uint32_t s = 0; s < S; ++s) {
             fe_t* z = perm_polys + (size_t)s * n;
             ZK_TRY(lagrange_to_coeff(pk, z));
-            ZK_TRY(coeff_to_extended(pk, z, perm_cosets + (size_t)s * ext));
+            ZK_TRY(my_cosets(z, perm_cosets + (size_t)s * ext, cj0, cj1));
         }
     }
 
     // ---- step 7: lookups, commit_product
     for (uint32_t l = 0; l < L; ++l) {
         fe_t* z = LK(l, 6);
+        if (!sh.mine(l)) { rng_take(bf + 1); continue; }
         {
             PhaseTimer t(pk, PH_LOOKUP);
             LookupProdArgs la{LK(l, 2), LK(l, 3), LK(l, 0), LK(l, 1), to_dev(beta), to_dev(gamma), tmp_n, (uint32_t)n};
@@ -665,18 +768,21 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     }
     if (L) {
         std::vector<const fe_t*> cols;
+        std::vector<int> owners;
         std::vector<HAffine> pts;
-        for (uint32_t l = 0; l < L; ++l) cols.push_back(LK(l, 6));
-        ZK_TRY(commit_multi_dev(pk, cols, n, true, pts));
+        std::vector<CommPiece> pieces;
+        for (uint32_t l = 0; l < L; ++l) { cols.push_back(LK(l, 6)); owners.push_back(sh.owner(l)); pieces.push_back({LK(l, 6), n * sizeof(fe_t), sh.owner(l)}); }
+        ZK_TRY(commit_multi_split(pk, sh, cols, owners, n, true, pts));
         for (auto& pt : pts) tr.write_point(pt);
-        for (uint32_t l = 0; l < L; ++l) ZK_TRY(lagrange_to_coeff(pk, LK(l, 6)));
+        for (uint32_t l = 0; l < L; ++l) if (sh.mine(l)) ZK_TRY(lagrange_to_coeff(pk, LK(l, 6)));
+        ZK_TRY(share(pieces));
     }
 
     // ---- step 8: vanishing argument, random polynomial
     if (rpos != rpos_random) return fail(ctx, B200ZK_EINVAL, "create_proof", "rng draw order");
     const fe_t* random_poly = rng_take(n);
     rng_take(1);
-    if (!random_early) ZK_TRY(commit_dev(pk, random_poly, n, false, &random_pt));
+    if (!random_early) ZK_TRY(commit_random());
     tr.write_point(random_pt);
     ch[EXF_Y] = tr.squeeze_challenge();
     const HFr y = ch[EXF_Y];
@@ -685,28 +791,31 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     ZK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
 
     // ---- step 11: evaluate_h
-    {
+    // this rank's rows of the quotient: its cosets [cj0, cj1) (all of them on a single GPU)
+    const uint32_t my_row0 = cj0 * (uint32_t)n, my_rows = (cj1 - cj0) * (uint32_t)n;
+    if (my_rows) {
         PhaseTimer t(pk, PH_QUOT);
         if (pk->gates_len) {
             ExprArgs ea = expr_args(pk, 0, pk->gates_len, true, EXM_ACC0, ch, h, nullptr);
-            expr_kernel<<<nb(ext), PK_THREADS, 0, st>>>(ea);
+            ea.row0 = my_row0; ea.rows = my_rows;
+            expr_kernel<<<nb(my_rows), PK_THREADS, 0, st>>>(ea);
             ctx->launches++;
         } else {
-            ZK_CUDA(ctx, cudaMemsetAsync(h, 0, ext * sizeof(fe_t), st));
+            ZK_CUDA(ctx, cudaMemsetAsync(h + my_row0, 0, (size_t)my_rows * sizeof(fe_t), st));
         }
         if (S) {
             QuotPermAArgs qa{};
             qa.h = h; qa.y = to_dev(y); qa.l0 = pk->l0; qa.l_last = pk->l_last; qa.nsets = S;
-            qa.rows = (uint32_t)ext; qa.log_ext = dom->k; qa.rot_scale = rot_scale; qa.last_rot = -(int32_t)(bf + 1);
+            qa.rows = my_rows; qa.row0 = my_row0; qa.log_ext = dom->k; qa.rot_scale = rot_scale; qa.last_rot = -(int32_t)(bf + 1);
             for (uint32_t s = 0; s < S; ++s) qa.z[s] = perm_cosets + (size_t)s * ext;
-            quot_perm_a_kernel<<<nb(ext), PK_THREADS, 0, st>>>(qa);
+            quot_perm_a_kernel<<<nb(my_rows), PK_THREADS, 0, st>>>(qa);
             ctx->launches++;
             HFr cd = beta * host::fr_zeta();                      // delta_start = beta * ZETA
             for (uint32_t s = 0; s < S; ++s) {
                 uint32_t c0 = s * pk->chunk, c1 = std::min<uint32_t>(c0 + pk->chunk, pk->P);
                 QuotPermBArgs qb{};
                 qb.h = h; qb.y = to_dev(y); qb.beta = to_dev(beta); qb.gamma = to_dev(gamma); qb.l_active = pk->l_active;
-                qb.z = perm_cosets + (size_t)s * ext; qb.ncols = c1 - c0; qb.rows = (uint32_t)ext; qb.log_ext = dom->k; qb.rot_scale = rot_scale;
+                qb.z = perm_cosets + (size_t)s * ext; qb.ncols = c1 - c0; qb.rows = my_rows; qb.row0 = my_row0; qb.log_ext = dom->k; qb.rot_scale = rot_scale;
                 qb.omega_pows = pk->omega_pows; qb.coset_fac = pk->coset_fac;
                 for (uint32_t j = c0; j < c1; ++j) {
                     qb.values[j - c0] = column_cosets(cs.perm[j].first, cs.perm[j].second);
@@ -714,7 +823,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
                     qb.cdelta[j - c0] = to_dev(cd);
                     cd = cd * host::fr_delta();
                 }
-                quot_perm_b_kernel<<<nb(ext), PK_THREADS, 0, st>>>(qb);
+                quot_perm_b_kernel<<<nb(my_rows), PK_THREADS, 0, st>>>(qb);
                 ctx->launches++;
             }
         }
@@ -723,18 +832,23 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     // h_lk, extended to the other cosets after the per-coset iNTT (lookup_extrapolate_row)
     const uint32_t CL = pk->lk_cosets_n;
     const bool lk_split = L && CL < pk->q;
-    const size_t lk_rows = lk_split ? (size_t)CL * n : ext;
-    if (lk_split) ZK_CUDA(ctx, cudaMemsetAsync(h_lk, 0, lk_rows * sizeof(fe_t), st));
-    for (uint32_t l = 0; l < L; ++l) {
+    // this rank's share of the cosets the lookup terms run on
+    const uint32_t lj0 = std::min(cj0, lk_split ? CL : pk->q), lj1 = std::min(cj1, lk_split ? CL : pk->q);
+    const uint32_t lk_row0 = lj0 * (uint32_t)n, lk_rows = (lj1 - lj0) * (uint32_t)n;
+    if (lk_split && lk_rows) ZK_CUDA(ctx, cudaMemsetAsync(h_lk + lk_row0, 0, (size_t)lk_rows * sizeof(fe_t), st));
+    for (uint32_t l = 0; l < L && lk_rows; ++l) {
         fe_t *zc = lk_cosets, *ac = lk_cosets + ext, *sc = lk_cosets + 2 * ext, *tv = lk_cosets + 3 * ext;
-        ZK_TRY(coeff_to_extended(pk, LK(l, 6), zc, lk_split ? CL : 0));
-        ZK_TRY(coeff_to_extended(pk, LK(l, 4), ac, lk_split ? CL : 0));
-        ZK_TRY(coeff_to_extended(pk, LK(l, 5), sc, lk_split ? CL : 0));
+        ZK_TRY(my_cosets(LK(l, 6), zc, lj0, lj1));
+        ZK_TRY(my_cosets(LK(l, 4), ac, lj0, lj1));
+        ZK_TRY(my_cosets(LK(l, 5), sc, lj0, lj1));
         PhaseTimer t(pk, PH_QUOT);
         ExprArgs ea = expr_args(pk, pk->lookup_prog[l].first, pk->lookup_prog[l].second, true, EXM_LOOKUP_PROD, ch, tv, nullptr);
-        ea.rows = (uint32_t)lk_rows;
+        ea.row0 = lk_row0; ea.rows = lk_rows;
         expr_kernel<<<nb(lk_rows), PK_THREADS, 0, st>>>(ea);
-        QuotLookupArgs ql{lk_split ? h_lk : h, to_dev(y), to_dev(beta), to_dev(gamma), pk->l0, pk->l_last, pk->l_active, zc, ac, sc, tv, dom->k, rot_scale, (uint32_t)lk_rows, {}};
+        QuotLookupArgs ql{};
+        ql.h = lk_split ? h_lk : h; ql.y = to_dev(y); ql.beta = to_dev(beta); ql.gamma = to_dev(gamma);
+        ql.l0 = pk->l0; ql.l_last = pk->l_last; ql.l_active = pk->l_active; ql.z = zc; ql.a = ac; ql.s = sc; ql.table_value = tv;
+        ql.log_ext = dom->k; ql.rot_scale = rot_scale; ql.rows = lk_rows; ql.row0 = lk_row0;
         { HFr yp = y * y; for (int i = 0; i < 4; ++i) { ql.ypow[i] = to_dev(yp); yp = yp * y; } }
         quot_lookup_kernel<<<nb(lk_rows), PK_THREADS, 0, st>>>(ql);
         ctx->launches += 2;
@@ -749,17 +863,25 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         HFr y_lk = HFr::one();                                    // h = h_gates_perm * y^(5 L) + h_lk
         if (lk_split) {
             for (uint32_t i = 0; i < 5 * L; ++i) y_lk = y_lk * y;
-            for (uint32_t j = 0; j < CL; ++j) {
+            for (uint32_t j = lj0; j < lj1; ++j) {
                 HFr post[3] = {dom->ifft_divisor, dom->ifft_divisor, dom->ifft_divisor};
                 ZK_TRY(ntt_run(ctx, h_lk + j * n, (uint32_t)n, h_lk + j * n, dom->k, dom->omega_inv, nullptr, post));
             }
-            lookup_extrapolate_kernel<<<nb(n), PK_THREADS, 0, st>>>(h_lk, pk->coset_pow_inv, pk->lk_lambda, pk->coset_t_dev, CL, pk->q, n);
-            ctx->launches++;
         }
-        for (uint32_t j = 0; j < pk->q; ++j) {
+        for (uint32_t j = cj0; j < cj1; ++j) {
             HFr f = dom->ifft_divisor * pk->coset_t[j] * y_lk;
             HFr post[3] = {f, f, f};
             ZK_TRY(ntt_run(ctx, h + j * n, (uint32_t)n, h + j * n, dom->k, dom->omega_inv, nullptr, post));
+        }
+        if (sh.on()) {                                            // every coset's coefficients to every rank: q (+ CL) x n elements
+            std::vector<CommPiece> pieces;
+            for (uint32_t j = 0; j < pk->q; ++j) pieces.push_back({h + (size_t)j * n, n * sizeof(fe_t), sh.coset_owner(j)});
+            if (lk_split) for (uint32_t j = 0; j < CL; ++j) pieces.push_back({h_lk + (size_t)j * n, n * sizeof(fe_t), sh.coset_owner(j)});
+            ZK_TRY(sh.cm->share(ctx, pieces.data(), pieces.size(), st));
+        }
+        if (lk_split) {
+            lookup_extrapolate_kernel<<<nb(n), PK_THREADS, 0, st>>>(h_lk, pk->coset_pow_inv, pk->lk_lambda, pk->coset_t_dev, CL, pk->q, n);
+            ctx->launches++;
         }
         coset_interpolate_kernel<<<nb(n), PK_THREADS, 0, st>>>(h, pk->coset_pow_inv, pk->vinv, pk->q, n, lk_cosets, lk_split ? h_lk : nullptr);
         ctx->launches++;
@@ -772,7 +894,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         std::vector<const fe_t*> cols;
         std::vector<HAffine> pts;
         for (uint32_t i = 0; i < q; ++i) cols.push_back(h + (size_t)i * n);
-        ZK_TRY(commit_multi_dev(pk, cols, n, false, pts));
+        ZK_TRY(commit_multi_range(pk, sh, cols, n, false, pts));
         for (auto& pt : pts) tr.write_point(pt);
     }
     if (rpos != draws) return fail(ctx, B200ZK_EINVAL, "create_proof", "internal: rng draw count mismatch");
@@ -780,7 +902,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     const HFr xn = x.pow_u64(n);
 
     // ---- step 14: evaluations
-    PhaseTimer* open_timer = new PhaseTimer(pk, PH_OPEN);
+    std::unique_ptr<PhaseTimer> open_timer(new PhaseTimer(pk, PH_OPEN));
     std::map<std::pair<const fe_t*, std::array<uint64_t, 4>>, HFr> eval_cache;
     auto eval_at = [&](const fe_t* poly, const HFr& pt, HFr* out) -> int32_t {
         std::array<uint64_t, 4> key = {pt.v[0], pt.v[1], pt.v[2], pt.v[3]};
@@ -793,7 +915,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     struct Query { const fe_t* poly; HFr point; };
     std::vector<Query> queries;
     int32_t rc = B200ZK_OK;
-    auto finish = [&](int32_t r) { delete open_timer; return r; };
+    auto finish = [&](int32_t r) { open_timer.reset(); return r; };
     const HFr x_next = rotate_omega(dom, x, 1), x_prev = rotate_omega(dom, x, -1), x_last = rotate_omega(dom, x, -(int)(bf + 1));
     // vanishing::evaluate: h_poly = sum_i (x^n)^i h_piece_i
     fold_pieces_kernel<<<nb(n), PK_THREADS, 0, st>>>(h, q, n, to_dev(xn), h_poly);
@@ -819,8 +941,25 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
             if (seen.insert({qy.poly, key}).second) { bp.push_back(qy.poly); bx.push_back(qy.point); }
         }
         std::vector<HFr> vals(bp.size());
-        rc = eval_batch_run(ctx, bp.data(), bx.data(), bp.size(), n, vals.data());
-        if (rc != B200ZK_OK) return finish(rc);
+        if (!sh.on()) {
+            rc = eval_batch_run(ctx, bp.data(), bx.data(), bp.size(), n, vals.data());
+            if (rc != B200ZK_OK) return finish(rc);
+        } else {                                                  // evaluation i on rank i mod G, 32 bytes each back to everybody
+            std::vector<const fe_t*> mp; std::vector<HFr> mx;
+            for (size_t i = 0; i < bp.size(); ++i) if (sh.mine((uint32_t)i)) { mp.push_back(bp[i]); mx.push_back(bx[i]); }
+            const size_t slots = (bp.size() + sh.G - 1) / sh.G;
+            std::vector<HFr> mv(slots, HFr::zero()), all(slots * sh.G);
+            rc = eval_batch_run(ctx, mp.data(), mx.data(), mp.size(), n, mv.data());
+            if (rc != B200ZK_OK) return finish(rc);
+            for (size_t b0 = 0; b0 < slots; b0 += COMM_HOST_MAX / sizeof(HFr)) {       // in pieces the staging buffers hold
+                const size_t m = std::min(slots - b0, COMM_HOST_MAX / sizeof(HFr));
+                std::vector<HFr> part(m * sh.G);
+                rc = sh.cm->allgather_host(ctx, mv.data() + b0, m * sizeof(HFr), part.data(), st);
+                if (rc != B200ZK_OK) return finish(rc);
+                for (int r = 0; r < sh.G; ++r) for (size_t i = 0; i < m; ++i) all[(size_t)r * slots + b0 + i] = part[(size_t)r * m + i];
+            }
+            for (size_t i = 0; i < bp.size(); ++i) vals[i] = all[(i % sh.G) * slots + i / sh.G];
+        }
         for (size_t i = 0; i < bp.size(); ++i) eval_cache[{bp[i], {bx[i].v[0], bx[i].v[1], bx[i].v[2], bx[i].v[3]}}] = vals[i];
     }
     for (size_t i = 0; i < cs.adv_q.size() && rc == B200ZK_OK; i += 2) {
@@ -922,11 +1061,11 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         }
     }
     {
-        delete open_timer; open_timer = nullptr;
-        HAffine pt;
-        ZK_TRY(commit_dev(pk, hx, n, false, &pt));
-        tr.write_point(pt);
-        open_timer = new PhaseTimer(pk, PH_OPEN);
+        open_timer.reset();
+        std::vector<HAffine> pt;
+        ZK_TRY(commit_multi_range(pk, sh, {hx}, n, false, pt));
+        tr.write_point(pt[0]);
+        open_timer.reset(new PhaseTimer(pk, PH_OPEN));
     }
     const HFr su = tr.squeeze_challenge();
     {
@@ -956,10 +1095,10 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         scale_kernel<<<nb(n - 1), PK_THREADS, 0, st>>>(t0, to_dev(z0_diff.inv()), n - 1);
         ctx->launches++;
         ZK_CUDA(ctx, cudaGetLastError());
-        delete open_timer; open_timer = nullptr;
-        HAffine pt;
-        ZK_TRY(commit_dev(pk, t0, n - 1, false, &pt));
-        tr.write_point(pt);
+        open_timer.reset();
+        std::vector<HAffine> pt;
+        ZK_TRY(commit_multi_range(pk, sh, {t0}, n - 1, false, pt));
+        tr.write_point(pt[0]);
     }
     phase_timers_collect(pk);
     proof_out = tr.proof();
@@ -1233,6 +1372,8 @@ int32_t b200zk_pk_create(b200zk_params* params, const uint32_t* cs_blob, size_t 
 }
 
 static int32_t finish_proof(b200zk_pk* pk, int32_t rc, const std::vector<uint8_t>& proof, uint8_t* proof_out, size_t cap, size_t* proof_len) {
+    // a rank that fails on its own (not the collective ConstraintSystemFailure / InstanceTooLarge) releases its peers
+    if (rc != B200ZK_OK && rc != B200ZK_ESYNTH && pk->ctx->comm) pk->ctx->comm->abort();
     if (rc != B200ZK_OK) {
         // a failed proof may have left column uploads in flight: the caller's buffers are borrowed for the call only
         if (pk->copy_stream) cudaStreamSynchronize(pk->copy_stream);
@@ -1260,6 +1401,56 @@ int32_t b200zk_create_proof_dev(b200zk_pk* pk, const void* d_advice, const void*
     std::vector<uint8_t> proof;
     int32_t rc = prove(pk, (const fe_t*)d_advice, true, nullptr, instance_columns, instance_lens, d_rng_wide, true, HFr::from_limbs(transcript_repr), proof);
     return finish_proof(pk, rc, proof, proof_out, proof_cap, proof_len);
+}
+
+// ---- one create_proof over the GPUs of a group (b200zk_group_create): rank r = thread r on pks[r]'s device.
+// Every rank gets the same inputs; the proof (identical on every rank) is rank 0's.
+static int32_t group_prove(b200zk_group* g, b200zk_pk* const* pks, const void* const* d_advice_per_rank, const void* const* advice_columns,
+                           const void* const* instance_columns, const uint32_t* instance_lens, const void* const* d_rng_per_rank,
+                           const void* rng_wide, const void* transcript_repr, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+    const uint32_t G = b200zk_group_size(g);
+    if (!G || !pks || !transcript_repr || !proof_out) return B200ZK_EINVAL;
+    for (uint32_t r = 0; r < G; ++r) {
+        if (!pks[r] || pks[r]->ctx != b200zk_group_ctx(g, r)) return B200ZK_EINVAL;
+        if (pks[r]->cs.I && (!instance_columns || !instance_lens)) return B200ZK_EINVAL;
+        if (d_advice_per_rank ? (!d_rng_per_rank || (pks[r]->cs.A && !d_advice_per_rank[r]) || !d_rng_per_rank[r]) : (!rng_wide || (pks[r]->cs.A && !advice_columns))) return B200ZK_EINVAL;
+    }
+    b200zk_group_reset(g);
+    std::vector<int32_t> rcs(G, B200ZK_OK);
+    std::vector<std::vector<uint8_t>> proofs(G);
+    const HFr repr = HFr::from_limbs(transcript_repr);
+    auto body = [&](uint32_t r) {
+        b200zk_pk* pk = pks[r];
+        cudaSetDevice(pk->ctx->device);
+        int32_t rc = d_advice_per_rank ? prove(pk, (const fe_t*)d_advice_per_rank[r], true, nullptr, instance_columns, instance_lens, d_rng_per_rank[r], true, repr, proofs[r])
+                                       : prove(pk, nullptr, false, advice_columns, instance_columns, instance_lens, rng_wide, false, repr, proofs[r]);
+        if (rc != B200ZK_OK && rc != B200ZK_ESYNTH) pk->ctx->comm->abort();
+        if (rc != B200ZK_OK && pk->copy_stream) cudaStreamSynchronize(pk->copy_stream);
+        rcs[r] = rc;
+    };
+    std::vector<std::thread> threads;
+    for (uint32_t r = 1; r < G; ++r) threads.emplace_back(body, r);
+    body(0);
+    for (auto& t : threads) t.join();
+    for (uint32_t r = 0; r < G; ++r) if (rcs[r] != B200ZK_OK) return rcs[r];
+    for (uint32_t r = 1; r < G; ++r) if (proofs[r] != proofs[0]) return fail(pks[0]->ctx, B200ZK_ECUDA, "group_create_proof", "internal: ranks disagree on the proof");
+    if (proof_len) *proof_len = proofs[0].size();
+    if (proofs[0].size() > proof_cap) return fail(pks[0]->ctx, B200ZK_EINVAL, "create_proof", "proof buffer too small");
+    memcpy(proof_out, proofs[0].data(), proofs[0].size());
+    return B200ZK_OK;
+}
+
+int32_t b200zk_group_create_proof(b200zk_group* g, b200zk_pk* const* pks, const void* const* advice_columns, const void* const* instance_columns,
+                                  const uint32_t* instance_lens, const void* rng_wide, const void* transcript_repr,
+                                  uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+    return group_prove(g, pks, nullptr, advice_columns, instance_columns, instance_lens, nullptr, rng_wide, transcript_repr, proof_out, proof_cap, proof_len);
+}
+
+int32_t b200zk_group_create_proof_dev(b200zk_group* g, b200zk_pk* const* pks, const void* const* d_advice_per_rank, const void* const* instance_columns,
+                                      const uint32_t* instance_lens, const void* const* d_rng_wide_per_rank, const void* transcript_repr,
+                                      uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+    if (!d_advice_per_rank || !d_rng_wide_per_rank) return B200ZK_EINVAL;
+    return group_prove(g, pks, d_advice_per_rank, nullptr, instance_columns, instance_lens, d_rng_wide_per_rank, nullptr, transcript_repr, proof_out, proof_cap, proof_len);
 }
 
 }  // extern "C"

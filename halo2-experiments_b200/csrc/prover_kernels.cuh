@@ -81,7 +81,8 @@ struct QuotPermAArgs {
     fe_t* h;
     fe_t y;
     const fe_t *l0, *l_last;
-    uint32_t rows;                      // C * n
+    uint32_t rows;                      // rows evaluated: [row0, row0 + rows) of the C * n (a rank of a sharded proof owns whole cosets)
+    uint32_t row0;
     uint32_t nsets, log_ext, rot_scale; // log_ext = log2 of the rotation block (k)
     int32_t last_rot;                   // -(blinding_factors + 1)
     const fe_t* z[ZK_MAXC];             // permutation_product_coset per set
@@ -111,7 +112,7 @@ struct QuotPermBArgs {
     fe_t y, beta, gamma;
     const fe_t* l_active;
     const fe_t* z;
-    uint32_t rows, ncols, log_ext, rot_scale;
+    uint32_t rows, row0, ncols, log_ext, rot_scale;
     const fe_t* values[ZK_MAXC];        // column cosets
     const fe_t* sigma[ZK_MAXC];         // permutation cosets
     fe_t cdelta[ZK_MAXC];               // beta * zeta * delta^(global column index)
@@ -138,7 +139,7 @@ struct QuotLookupArgs {
     const fe_t *l0, *l_last, *l_active;
     const fe_t *z, *a, *s;              // product / permuted input / permuted table cosets
     const fe_t* table_value;            // (compressed input + beta)(compressed table + gamma)
-    uint32_t log_ext, rot_scale, rows;
+    uint32_t log_ext, rot_scale, rows, row0;
     fe_t ypow[4];                       // y^2, y^3, y^4, y^5
 };
 // The five terms upstream folds one by one (h <- h*y + term):

@@ -200,9 +200,49 @@ int32_t b200zk_create_proof(b200zk_pk* pk, const void* const* advice_columns, co
 int32_t b200zk_create_proof_dev(b200zk_pk* pk, const void* d_advice, const void* const* instance_columns,
                                 const uint32_t* instance_lens, const void* d_rng_wide, const void* transcript_repr,
                                 uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+/* ---- one create_proof sharded over several GPUs (BASELINE config 5) ---------------
+ * The reference's single prover call (/root/reference/src/circuits/utils.rs:40-48) spread over G GPUs of
+ * one NVLink / NVSwitch box.  Every rank holds the SRS and the proving key (b200zk_params_* / b200zk_pk_create
+ * on its own ctx) and receives the same inputs; inside the call each rank commits its share of the
+ * columns, runs its lookups, extends and evaluates its quotient cosets and multiplies its point range of the
+ * dense commitments (h pieces, random polynomial, SHPLONK), exchanging polynomials device to device and
+ * 64-byte partial sums through the host, so that every rank's Blake2b transcript absorbs the same bytes.
+ * The proof is byte-identical to the single-GPU one.
+ *
+ * (a) One process per GPU (torchrun / MPI style hosts): rank 0 calls b200zk_comm_unique_id and
+ *     distributes the 128 bytes; every rank calls b200zk_ctx_comm_init (NCCL; collective), after which
+ *     b200zk_create_proof[_dev] on that ctx is one rank of the sharded proof: all ranks call it with the
+ *     same arguments and all receive the proof.  libnccl.so.2 is loaded on first use.
+ * (b) One process driving several GPUs (what a Rust `create_proof` caller uses): b200zk_group_create
+ *     makes one ctx per listed device with peer access between them; build params / pk on every
+ *     b200zk_group_ctx(g, r), then b200zk_group_create_proof runs the ranks on internal threads (no
+ *     NCCL, NVLink peer copies).  A device may be listed more than once (the ranks then share it):
+ *     that is how the sharded prover is tested on a single GPU. */
+typedef struct b200zk_group b200zk_group;
+int32_t b200zk_comm_unique_id(void* id_out128);
+int32_t b200zk_ctx_comm_init(b200zk_ctx* ctx, uint32_t world, uint32_t rank, const void* id128);
+int32_t b200zk_ctx_comm_destroy(b200zk_ctx* ctx);
+uint32_t b200zk_ctx_comm_world(const b200zk_ctx* ctx);
+uint32_t b200zk_ctx_comm_rank(const b200zk_ctx* ctx);
+int32_t b200zk_group_create(const int32_t* devices, uint32_t n, b200zk_group** out);
+void b200zk_group_destroy(b200zk_group* g);            /* destroys the group's ctxs: free their params / pks first */
+uint32_t b200zk_group_size(const b200zk_group* g);
+b200zk_ctx* b200zk_group_ctx(b200zk_group* g, uint32_t rank);
+int32_t b200zk_group_reset(b200zk_group* g);           /* after a failed group call */
+/* pks[r] = the proving key built on b200zk_group_ctx(g, r) */
+int32_t b200zk_group_create_proof(b200zk_group* g, b200zk_pk* const* pks, const void* const* advice_columns,
+                                  const void* const* instance_columns, const uint32_t* instance_lens, const void* rng_wide,
+                                  const void* transcript_repr, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+/* d_advice_per_rank[r] / d_rng_wide_per_rank[r]: the inputs resident on rank r's device */
+int32_t b200zk_group_create_proof_dev(b200zk_group* g, b200zk_pk* const* pks, const void* const* d_advice_per_rank,
+                                      const void* const* instance_columns, const uint32_t* instance_lens,
+                                      const void* const* d_rng_wide_per_rank, const void* transcript_repr,
+                                      uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+
 /* debugging aid: copy a named device buffer of the last proof (32-byte elements) to the host */
 int32_t b200zk_pk_debug_buffer(b200zk_pk* pk, const char* name, void* host_out, size_t max_elems, size_t* count);
-/* per-phase device times (ms) of the last create_proof: msm, ntt, quotient, lookup, permutation, evals+shplonk, other */
+/* per-phase device times (ms) of the last create_proof: msm, ntt, quotient, lookup, permutation, evals+shplonk,
+ * other (= time spent in / waiting at the exchanges of a sharded proof) */
 int32_t b200zk_pk_last_phase_ms(const b200zk_pk* pk, float* out7);
 
 /* ---- plonk::keygen_vk / plonk::verify_proof (src/plonk/keygen.rs, src/plonk/verifier.rs,
