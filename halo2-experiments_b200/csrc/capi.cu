@@ -76,7 +76,10 @@ static int32_t build_sum_table(b200zk_params* p, int which, const affine_t* base
     fe_t one;
     memcpy(one.l, host::HFr::one().v, 32);
     std::vector<fe_t> h(n, one);
-    cudaError_t e = cudaMemcpy(ones, h.data(), n * sizeof(fe_t), cudaMemcpyHostToDevice);
+    // on the ctx stream: a plain cudaMemcpy from pageable memory may return before its DMA has landed, and the
+    // non-blocking ctx stream does not order itself after the legacy stream (a 64 KB column of ones was read stale)
+    cudaError_t e = cudaMemcpyAsync(ones, h.data(), n * sizeof(fe_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     host::HAffine sum;
     int32_t rc = e != cudaSuccess ? fail(ctx, B200ZK_ECUDA, "sum_table", cudaGetErrorString(e))
                                   : (table ? msm_run_ex(ctx, ones, table, n, &p->pre, &sum) : msm_run(ctx, ones, bases, n, &sum));
@@ -426,7 +429,8 @@ int32_t b200zk_domain_create(b200zk_ctx* ctx, uint32_t j, uint32_t k, b200zk_dom
     for (size_t i = 0; i < m; ++i) { t[i] = (cur - HFr::one()).inv(); cur = cur * step; }
     cudaError_t e = cudaMalloc(&d->d_t_evaluations, m * sizeof(fe_t));
     if (e != cudaSuccess) { delete d; return fail(ctx, B200ZK_ENOMEM, "cudaMalloc", cudaGetErrorString(e)); }
-    e = cudaMemcpy(d->d_t_evaluations, t.data(), m * sizeof(fe_t), cudaMemcpyHostToDevice);
+    e = cudaMemcpyAsync(d->d_t_evaluations, t.data(), m * sizeof(fe_t), cudaMemcpyHostToDevice, ctx->stream);   // ordered before this ctx's kernels
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { cudaFree(d->d_t_evaluations); delete d; return fail(ctx, B200ZK_ECUDA, "cudaMemcpy", cudaGetErrorString(e)); }
     *out = d;
     return B200ZK_OK;
@@ -599,11 +603,12 @@ int32_t b200zk_params_load(b200zk_ctx* ctx, uint32_t k, const void* g, const voi
     p->ctx = ctx; p->k = k; p->d_g = nullptr; p->d_g_lagrange = nullptr;
     size_t bytes = sizeof(affine_t) << k;
     cudaError_t e = cudaMalloc(&p->d_g, bytes);
-    if (e == cudaSuccess) e = cudaMemcpy(p->d_g, g, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_g, g, bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && g_lagrange) {
         e = cudaMalloc(&p->d_g_lagrange, bytes);
-        if (e == cudaSuccess) e = cudaMemcpy(p->d_g_lagrange, g_lagrange, bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_g_lagrange, g_lagrange, bytes, cudaMemcpyHostToDevice, ctx->stream);
     }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);             // the caller's buffers are borrowed for the call only
     if (e != cudaSuccess) {
         cudaFree(p->d_g); cudaFree(p->d_g_lagrange); delete p;
         return fail(ctx, B200ZK_ECUDA, "params_load", cudaGetErrorString(e));
@@ -628,11 +633,12 @@ int32_t b200zk_params_read(b200zk_params* p, void* g_out, void* g_lagrange_out) 
     size_t bytes = sizeof(affine_t) << p->k;
     ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (g_out) ZK_CUDA(ctx, cudaMemcpy(g_out, p->d_g, bytes, cudaMemcpyDeviceToHost));
+    if (g_out) ZK_CUDA(ctx, cudaMemcpyAsync(g_out, p->d_g, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (g_lagrange_out) {
         if (!p->d_g_lagrange) return fail(ctx, B200ZK_EINVAL, "params_read", "no lagrange basis loaded");
-        ZK_CUDA(ctx, cudaMemcpy(g_lagrange_out, p->d_g_lagrange, bytes, cudaMemcpyDeviceToHost));
+        ZK_CUDA(ctx, cudaMemcpyAsync(g_lagrange_out, p->d_g_lagrange, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return B200ZK_OK;
 }
 

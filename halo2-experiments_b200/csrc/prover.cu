@@ -1136,7 +1136,8 @@ int32_t b200zk_pk_debug_buffer(b200zk_pk* pk, const char* name, void* host_out, 
     if (it == pk->dbg.end()) return fail(pk->ctx, B200ZK_EINVAL, "debug_buffer", "unknown buffer");
     size_t c = std::min(max_elems, it->second.second);
     if (count) *count = it->second.second;
-    ZK_CUDA(pk->ctx, cudaMemcpy(host_out, it->second.first, c * sizeof(fe_t), cudaMemcpyDeviceToHost));
+    ZK_CUDA(pk->ctx, cudaMemcpyAsync(host_out, it->second.first, c * sizeof(fe_t), cudaMemcpyDeviceToHost, pk->ctx->stream));
+    ZK_CUDA(pk->ctx, cudaStreamSynchronize(pk->ctx->stream));
     return B200ZK_OK;
 }
 

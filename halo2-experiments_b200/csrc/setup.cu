@@ -95,7 +95,8 @@ static int32_t ensure_gen_table(b200zk_ctx* ctx) {
         aff[i] = {pts[i].x * t.sqr(), pts[i].y * iz};
     }
     ZK_CUDA(ctx, cudaMalloc(&ctx->d_gen_table, aff.size() * sizeof(affine_t)));
-    ZK_CUDA(ctx, cudaMemcpy(ctx->d_gen_table, aff.data(), aff.size() * sizeof(affine_t), cudaMemcpyHostToDevice));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->d_gen_table, aff.data(), aff.size() * sizeof(affine_t), cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return B200ZK_OK;
 }
 
