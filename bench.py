@@ -343,6 +343,11 @@ def run_gpu(args):
     launches = (be.launch_count() - l0) // args.steps
     if args.workload == "prove":
         extra["phase_ms"] = pk.last_phase_ms()
+        extra["timeline_ms"] = pk.last_trace()
+        if dist is not None:
+            tl = [None] * world
+            dist.all_gather_object(tl, [round(v, 2) for _, v in extra["timeline_ms"]])
+            extra["timeline_ms_all_ranks"] = {"labels": [a for a, _ in extra["timeline_ms"]], "ms": tl}
         extra["phase_note"] = "device time per phase; the advice-coset NTTs run on a side stream concurrently with the lookup / permutation phases, so the phases overlap and sum to more than the step"
     # ---- end-to-end region: host buffers through the C ABI ---------------------------
     for _ in range(2):

@@ -403,6 +403,12 @@ class ProvingKey:
         self.backend._check(lib().b200zk_pk_vk_commitments(self._h, _p(fixed), _p(sigma)))
         return fixed[: self.cs.num_fixed], sigma[: len(self.cs.permutation)]
 
+    def last_trace(self):
+        """[(label, ms since the call)] at the synchronisation points of the last create_proof (host wall clock)."""
+        buf = ctypes.create_string_buffer(4096)
+        self.backend._check(lib().b200zk_pk_last_trace(self._h, buf, ctypes.c_size_t(4096)))
+        return [(a, float(b)) for a, b in (item.split(":") for item in buf.value.decode().split(";") if item)]
+
     def last_phase_ms(self):
         out = (ctypes.c_float * 7)()
         self.backend._check(lib().b200zk_pk_last_phase_ms(self._h, out))

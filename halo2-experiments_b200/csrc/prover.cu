@@ -16,6 +16,7 @@
 #include <memory>
 #include <new>
 #include <set>
+#include <chrono>
 #include <string>
 #include <thread>
 
@@ -142,6 +143,7 @@ struct b200zk_pk {
     cudaEvent_t ev_rnd = nullptr;
     std::vector<cudaEvent_t> col_events;
     std::map<std::string, std::pair<const void*, size_t>> dbg;     // buffers of the last proof, for b200zk_pk_debug_buffer
+    std::vector<std::pair<const char*, double>> trace;             // host time (ms since the call) at the proof's synchronisation points
 };
 
 namespace b200zk {
@@ -512,6 +514,11 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     pk->timer_used = 0;
     ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     const Shard sh(pk);
+    pk->trace.clear();
+    const auto t_start = std::chrono::steady_clock::now();
+    auto mark = [&](const char* label) {              // called right after a host synchronisation: where the wall clock of the proof goes
+        pk->trace.push_back({label, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count()});
+    };
     // quotient cosets this rank extends and evaluates
     const uint32_t cj0 = sh.coset_lo(sh.R), cj1 = sh.coset_lo(sh.R + 1);
     if (sh.on()) ZK_TRY(sh.cm->set_window(ctx, pk->arena, pk->arena_bytes));
@@ -582,10 +589,25 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     for (uint32_t c = 0; c < I; ++c) ZK_TRY(lagrange_to_coeff(pk, inst_polys + (size_t)c * n));
 
     // ---- randomness: Fr::random = from_u512 of the caller's 64-byte draws, consumed in upstream order
-    if (rng_on_device) ZK_CUDA(ctx, cudaMemcpyAsync(wide, rng_wide, draws * 64, cudaMemcpyDeviceToDevice, st));
-    else ZK_CUDA(ctx, cudaMemcpyAsync(wide, rng_wide, draws * 64, cudaMemcpyHostToDevice, st));
-    from_u512_kernel<<<nb(draws), PK_THREADS, 0, st>>>(wide, rnd, draws);
-    ctx->launches++;
+    // Sharded proof from host buffers: the host -> device traffic is split as well — every rank uploads 1/G of the rng
+    // stream and its own advice columns over its PCIe link, and the ranks exchange them over NVLink.
+    const bool split_upload = sh.on() && !advice_on_device && !rng_on_device;
+    if (split_upload) {
+        const size_t d0 = draws * (size_t)sh.R / sh.G, d1 = draws * (size_t)(sh.R + 1) / sh.G;
+        ZK_CUDA(ctx, cudaMemcpyAsync(wide + d0 * 16, (const char*)rng_wide + d0 * 64, (d1 - d0) * 64, cudaMemcpyHostToDevice, st));
+        if (d1 > d0) { from_u512_kernel<<<nb(d1 - d0), PK_THREADS, 0, st>>>(wide + d0 * 16, rnd + d0, d1 - d0); ctx->launches++; }
+        std::vector<CommPiece> pieces;
+        for (int r = 0; r < sh.G; ++r) {
+            const size_t a0 = draws * (size_t)r / sh.G, a1 = draws * (size_t)(r + 1) / sh.G;
+            pieces.push_back({rnd + a0, (a1 - a0) * sizeof(fe_t), r});
+        }
+        ZK_TRY(share(pieces));
+    } else {
+        if (rng_on_device) ZK_CUDA(ctx, cudaMemcpyAsync(wide, rng_wide, draws * 64, cudaMemcpyDeviceToDevice, st));
+        else ZK_CUDA(ctx, cudaMemcpyAsync(wide, rng_wide, draws * 64, cudaMemcpyHostToDevice, st));
+        from_u512_kernel<<<nb(draws), PK_THREADS, 0, st>>>(wide, rnd, draws);
+        ctx->launches++;
+    }
     size_t rpos = 0;
     auto rng_take = [&](size_t count) { fe_t* p = rnd + rpos; rpos += count; return p; };
     auto copy_rows = [&](fe_t* dst, const fe_t* src, size_t count) {
@@ -615,20 +637,11 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     ZK_CUDA(ctx, cudaStreamWaitEvent(pk->copy_stream, pk->ev_rnd, 0));      // rnd (and the arena's previous users on st) first
     for (uint32_t c = 0; c < A; ++c) {
         fe_t* col = advice_values + (size_t)c * n;
+        if (split_upload && !sh.mine(c)) continue;                // arrives from its owner below
         if (advice_on_device) ZK_CUDA(ctx, cudaMemcpyAsync(col, d_advice_in + (size_t)c * n, n * sizeof(fe_t), cudaMemcpyDeviceToDevice, pk->copy_stream));
         else ZK_CUDA(ctx, cudaMemcpyAsync(col, advice_host[c], n * sizeof(fe_t), cudaMemcpyHostToDevice, pk->copy_stream));
         ZK_CUDA(ctx, cudaMemcpyAsync(col + usable, rnd + rpos_advice + (size_t)c * (bf + 1), (bf + 1) * sizeof(fe_t), cudaMemcpyDeviceToDevice, pk->copy_stream));
         ZK_CUDA(ctx, cudaEventRecord(pk->col_events[c], pk->copy_stream));
-    }
-    {
-        SideStream side(ctx);
-        for (uint32_t c = 0; c < A; ++c) {
-            ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pk->col_events[c], 0));
-            ZK_CUDA(ctx, cudaMemcpyAsync(advice_polys + (size_t)c * n, advice_values + (size_t)c * n, n * sizeof(fe_t), cudaMemcpyDeviceToDevice, ctx->stream));
-            ZK_TRY(lagrange_to_coeff(pk, advice_polys + (size_t)c * n));
-            ZK_TRY(my_cosets(advice_polys + (size_t)c * n, advice_cosets + (size_t)c * ext, cj0, cj1));
-        }
-        for (uint32_t c = 0; c < I; ++c) ZK_TRY(my_cosets(inst_polys + (size_t)c * n, inst_cosets + (size_t)c * ext, cj0, cj1));
     }
     // position of the random polynomial in the rng stream (draw order: SURVEY.md 8(a7))
     const size_t rpos_random = rpos + (size_t)L * (2 * (bf + 1) + 2) + (size_t)S * (bf + 1) + (size_t)L * (bf + 1);
@@ -640,8 +653,27 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         random_pt = pts[0];
         return B200ZK_OK;
     };
-    if (random_early) ZK_TRY(commit_random());
-    if (A) ZK_CUDA(ctx, cudaStreamWaitEvent(st, pk->col_events[A - 1], 0));
+    if (split_upload) {                                           // random-polynomial commit under the upload, then the column exchange
+        ZK_TRY(commit_random());
+        std::vector<CommPiece> pieces;
+        for (uint32_t c = 0; c < A; ++c) {
+            if (sh.mine(c)) ZK_CUDA(ctx, cudaStreamWaitEvent(st, pk->col_events[c], 0));
+            pieces.push_back({advice_values + (size_t)c * n, n * sizeof(fe_t), sh.owner(c)});
+        }
+        ZK_TRY(share(pieces));
+    }
+    {
+        SideStream side(ctx);
+        for (uint32_t c = 0; c < A; ++c) {
+            if (!split_upload) ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pk->col_events[c], 0));
+            ZK_CUDA(ctx, cudaMemcpyAsync(advice_polys + (size_t)c * n, advice_values + (size_t)c * n, n * sizeof(fe_t), cudaMemcpyDeviceToDevice, ctx->stream));
+            ZK_TRY(lagrange_to_coeff(pk, advice_polys + (size_t)c * n));
+            ZK_TRY(my_cosets(advice_polys + (size_t)c * n, advice_cosets + (size_t)c * ext, cj0, cj1));
+        }
+        for (uint32_t c = 0; c < I; ++c) ZK_TRY(my_cosets(inst_polys + (size_t)c * n, inst_cosets + (size_t)c * ext, cj0, cj1));
+    }
+    if (random_early && !split_upload) ZK_TRY(commit_random());
+    if (A && !split_upload) ZK_CUDA(ctx, cudaStreamWaitEvent(st, pk->col_events[A - 1], 0));
     {
         std::vector<const fe_t*> cols;
         std::vector<int> owners;
@@ -649,6 +681,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         for (uint32_t c = 0; c < A; ++c) { cols.push_back(advice_values + (size_t)c * n); owners.push_back(sh.owner(c)); }
         ZK_TRY(commit_multi_split(pk, sh, cols, owners, n, true, pts));
         for (uint32_t c = 0; c < A; ++c) tr.write_point(pts[c]);
+        mark("advice_commits");
     }
     HFr ch[4];                                                    // theta, beta, gamma, y
     ch[EXF_THETA] = tr.squeeze_challenge();
@@ -687,6 +720,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
             for (uint32_t l = 0; l < L; ++l) { cols.push_back(LK(l, 2)); cols.push_back(LK(l, 3)); owners.push_back(sh.owner(l)); owners.push_back(sh.owner(l)); }
             ZK_TRY(commit_multi_split(pk, sh, cols, owners, n, true, pts, &err));
             for (auto& pt : pts) tr.write_point(pt);
+            mark("lookup_permuted_commits");
         }
         if (err) return fail(ctx, B200ZK_ESYNTH, "create_proof", "ConstraintSystemFailure: lookup input not in table");
         // the permuted polynomials in coefficient form: every rank opens them, the coset owners extend them
@@ -706,33 +740,61 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         return type == 0 ? advice_cosets + (size_t)idx * ext : type == 1 ? pk->fixed_cosets + (size_t)idx * ext : inst_cosets + (size_t)idx * ext;
     };
     {
+        // Upstream chains the sets through z_s[0] = z_{s-1}[n - (bf + 1)].  On one GPU that is a 32-byte read-back per
+        // set.  Sharded, set s lives on rank s mod G: every rank runs its sets from z[0] = 1, the S totals
+        // t_s = z'_s[n - (bf + 1)] are exchanged, and set s is scaled by t_0 ... t_{s-1} — the same field elements.
         HFr last_z = HFr::one(), deltaomega = HFr::one();
+        std::vector<const fe_t*> blind_rows(S);
         for (uint32_t s = 0; s < S; ++s) {
             fe_t* z = perm_polys + (size_t)s * n;
             uint32_t c0 = s * pk->chunk, c1 = std::min<uint32_t>(c0 + pk->chunk, pk->P);
+            PermLagArgs pa{};
+            pa.ncols = c1 - c0; pa.n = (uint32_t)n;
+            for (uint32_t j = c0; j < c1; ++j) {
+                pa.values[j - c0] = column_values(cs.perm[j].first, cs.perm[j].second);
+                pa.sigma[j - c0] = pk->perm_values + (size_t)j * n;
+                pa.coef[j - c0] = to_dev(deltaomega * beta);
+                deltaomega = deltaomega * host::fr_delta();
+            }
+            blind_rows[s] = rng_take(bf);
+            rng_take(1);
+            if (!sh.mine(s)) continue;
             {
                 PhaseTimer t(pk, PH_PERM);
-                PermLagArgs pa{};
-                pa.ncols = c1 - c0; pa.n = (uint32_t)n;
-                for (uint32_t j = c0; j < c1; ++j) {
-                    pa.values[j - c0] = column_values(cs.perm[j].first, cs.perm[j].second);
-                    pa.sigma[j - c0] = pk->perm_values + (size_t)j * n;
-                    pa.coef[j - c0] = to_dev(deltaomega * beta);
-                    deltaomega = deltaomega * host::fr_delta();
-                }
                 pa.beta = to_dev(beta); pa.gamma = to_dev(gamma); pa.omega_pows = pk->omega_pows; pa.out = tmp_n;
                 perm_den_kernel<<<nb(n), PK_THREADS, 0, st>>>(pa);
                 ctx->launches++;
                 ZK_TRY(batch_invert_run(ctx, tmp_n, n, 0));
                 perm_num_kernel<<<nb(n), PK_THREADS, 0, st>>>(pa);
                 ctx->launches++;
-                ZK_TRY(prefix_product_run(ctx, tmp_n, z, n, last_z));
+                ZK_TRY(prefix_product_run(ctx, tmp_n, z, n, sh.on() ? HFr::one() : last_z));
             }
-            ZK_CUDA(ctx, copy_rows(z + (n - bf), rng_take(bf), bf));
-            ZK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, z + (n - (bf + 1)), sizeof(fe_t), cudaMemcpyDeviceToHost, st));
+            ZK_CUDA(ctx, cudaMemcpyAsync((fe_t*)ctx->pinned + (sh.on() ? s / sh.G : 0), z + (n - (bf + 1)), sizeof(fe_t), cudaMemcpyDeviceToHost, st));
+            if (!sh.on()) {
+                ZK_CUDA(ctx, copy_rows(z + (n - bf), blind_rows[s], bf));
+                ZK_CUDA(ctx, cudaStreamSynchronize(st));
+                last_z = HFr::from_limbs(ctx->pinned);
+            }
+        }
+        if (sh.on() && S) {
+            const size_t slots = (S + sh.G - 1) / sh.G;
+            std::vector<HFr> mine_t(slots, HFr::one()), all_t(slots * sh.G);
             ZK_CUDA(ctx, cudaStreamSynchronize(st));
-            last_z = HFr::from_limbs(ctx->pinned);
-            rng_take(1);
+            for (uint32_t s = 0; s < S; ++s) if (sh.mine(s)) mine_t[s / sh.G] = HFr::from_limbs((const fe_t*)ctx->pinned + s / sh.G);
+            {
+                PhaseTimer t(pk, PH_OTHER);
+                ZK_TRY(sh.cm->allgather_host(ctx, mine_t.data(), slots * sizeof(HFr), all_t.data(), st));
+            }
+            HFr carry = HFr::one();
+            for (uint32_t s = 0; s < S; ++s) {
+                fe_t* z = perm_polys + (size_t)s * n;
+                if (sh.mine(s)) {
+                    if (s) { scale_kernel<<<nb(n - bf), PK_THREADS, 0, st>>>(z, to_dev(carry), n - bf); ctx->launches++; }
+                    ZK_CUDA(ctx, copy_rows(z + (n - bf), blind_rows[s], bf));
+                }
+                carry = carry * all_t[(size_t)sh.owner(s) * slots + s / sh.G];
+            }
+            mark("perm_products");
         }
         if (S) {                                                  // the S grand products: one batch of commitments, then coefficients and cosets
             std::vector<const fe_t*> cols;
@@ -741,11 +803,17 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
             for (uint32_t s = 0; s < S; ++s) { cols.push_back(perm_polys + (size_t)s * n); owners.push_back(sh.owner(s)); }
             ZK_TRY(commit_multi_split(pk, sh, cols, owners, n, true, pts));
             for (auto& pt : pts) tr.write_point(pt);
+            mark("permutation_commits");
         }
-        for (uint32_t s = 0; s < S; ++s) {
-            fe_t* z = perm_polys + (size_t)s * n;
-            ZK_TRY(lagrange_to_coeff(pk, z));
-            ZK_TRY(my_cosets(z, perm_cosets + (size_t)s * ext, cj0, cj1));
+        {
+            std::vector<CommPiece> pieces;
+            for (uint32_t s = 0; s < S; ++s) {
+                fe_t* z = perm_polys + (size_t)s * n;
+                if (sh.mine(s)) ZK_TRY(lagrange_to_coeff(pk, z));
+                pieces.push_back({z, n * sizeof(fe_t), sh.owner(s)});
+            }
+            ZK_TRY(share(pieces));
+            for (uint32_t s = 0; s < S; ++s) ZK_TRY(my_cosets(perm_polys + (size_t)s * n, perm_cosets + (size_t)s * ext, cj0, cj1));
         }
     }
 
@@ -774,6 +842,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         for (uint32_t l = 0; l < L; ++l) { cols.push_back(LK(l, 6)); owners.push_back(sh.owner(l)); pieces.push_back({LK(l, 6), n * sizeof(fe_t), sh.owner(l)}); }
         ZK_TRY(commit_multi_split(pk, sh, cols, owners, n, true, pts));
         for (auto& pt : pts) tr.write_point(pt);
+        mark("lookup_product_commits");
         for (uint32_t l = 0; l < L; ++l) if (sh.mine(l)) ZK_TRY(lagrange_to_coeff(pk, LK(l, 6)));
         ZK_TRY(share(pieces));
     }
@@ -896,6 +965,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         for (uint32_t i = 0; i < q; ++i) cols.push_back(h + (size_t)i * n);
         ZK_TRY(commit_multi_range(pk, sh, cols, n, false, pts));
         for (auto& pt : pts) tr.write_point(pt);
+        mark("quotient_and_h_commits");
     }
     if (rpos != draws) return fail(ctx, B200ZK_EINVAL, "create_proof", "internal: rng draw count mismatch");
     const HFr x = tr.squeeze_challenge();
@@ -961,6 +1031,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
             for (size_t i = 0; i < bp.size(); ++i) vals[i] = all[(i % sh.G) * slots + i / sh.G];
         }
         for (size_t i = 0; i < bp.size(); ++i) eval_cache[{bp[i], {bx[i].v[0], bx[i].v[1], bx[i].v[2], bx[i].v[3]}}] = vals[i];
+        mark("evaluations");
     }
     for (size_t i = 0; i < cs.adv_q.size() && rc == B200ZK_OK; i += 2) {
         HFr e; rc = eval_at(advice_polys + (size_t)cs.adv_q[i] * n, rotate_omega(dom, x, cs.adv_q[i + 1]), &e);
@@ -1065,6 +1136,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         std::vector<HAffine> pt;
         ZK_TRY(commit_multi_range(pk, sh, {hx}, n, false, pt));
         tr.write_point(pt[0]);
+        mark("shplonk_h1_commit");
         open_timer.reset(new PhaseTimer(pk, PH_OPEN));
     }
     const HFr su = tr.squeeze_challenge();
@@ -1101,6 +1173,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         tr.write_point(pt[0]);
     }
     phase_timers_collect(pk);
+    mark("end");
     proof_out = tr.proof();
     return B200ZK_OK;
 }
@@ -1138,6 +1211,16 @@ int32_t b200zk_pk_debug_buffer(b200zk_pk* pk, const char* name, void* host_out, 
     if (count) *count = it->second.second;
     ZK_CUDA(pk->ctx, cudaMemcpyAsync(host_out, it->second.first, c * sizeof(fe_t), cudaMemcpyDeviceToHost, pk->ctx->stream));
     ZK_CUDA(pk->ctx, cudaStreamSynchronize(pk->ctx->stream));
+    return B200ZK_OK;
+}
+
+// host wall clock of the last create_proof at its synchronisation points: "label:ms;label:ms;..." (ms since the call)
+int32_t b200zk_pk_last_trace(const b200zk_pk* pk, char* out, size_t cap) {
+    if (!pk || !out || cap == 0) return B200ZK_EINVAL;
+    std::string t;
+    for (auto& kv : pk->trace) { char buf[96]; snprintf(buf, sizeof buf, "%s:%.3f;", kv.first, kv.second); t += buf; }
+    if (t.size() + 1 > cap) return B200ZK_EINVAL;
+    memcpy(out, t.c_str(), t.size() + 1);
     return B200ZK_OK;
 }
 
