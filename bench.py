@@ -217,7 +217,7 @@ def run_gpu(args):
         else:
             rank_seed = rank
         job = build_job(zk, args.circuit, k, 1 + rank_seed)
-        params = zk.ParamsKZG.setup(be, k, random_scalars(1, 4242)[0])
+        params = zk.ParamsKZG.setup(be, k, random_scalars(1, SRS_SEED)[0])
         pk = zk.ProvingKey(params, job.cs, k, job.fixed, job.map_col, job.map_row)
         A = job.cs.num_advice
         h_adv = be.pinned_empty((A * n, 4))
@@ -225,7 +225,7 @@ def run_gpu(args):
             h_adv[c * n:(c + 1) * n] = job.advice[c]
         h_cols = [h_adv[c * n:(c + 1) * n] for c in range(A)]
         h_wide = be.pinned_empty((pk.rng_draws, 8))
-        h_wide[:] = np.random.Generator(np.random.PCG64(99 + rank_seed)).integers(0, 1 << 64, size=(pk.rng_draws, 8), dtype=np.uint64)
+        h_wide[:] = np.random.Generator(np.random.PCG64(RNG_SEED + rank_seed)).integers(0, 1 << 64, size=(pk.rng_draws, 8), dtype=np.uint64)
         d_adv, d_wide = be.to_device(h_adv), be.to_device(h_wide)
         lut = synth.mont_from_ints(job.instances[0] + [job.transcript_repr])
         inst, tr_repr = [lut[:-1]], lut[-1]
@@ -458,7 +458,9 @@ def run_gpu(args):
         except Exception as e:                                      # the headline number stands on its own
             line["sharded"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
-        line["cpu_baseline"] = cpu_baseline(args)
+        if not args.no_cpu_baseline:
+            # prove: rank 0's circuit, witness, SRS secret and rng stream are the CPU arm's, so the two proofs must be the same bytes
+            line["cpu_baseline"] = cpu_baseline(args, gpu_proof=last if args.workload == "prove" else None)
         emit(line)
     barrier(dist, be)
     be.close()
@@ -583,84 +585,99 @@ def sharded_sweep(zk, be, dist, rank, world, local, args):
 
 
 # --------------------------------------------------------------------------- CPU legs
+SRS_SEED, RNG_SEED = 4242, 99         # both arms: SRS secret = random_scalars(1, SRS_SEED)[0], rng stream = PCG64(RNG_SEED)
+
+
 def cpu_sample(args):
-    """(callable, units, description, scale) for the oracle's restatement on a bounded sample."""
+    """(callable, units, description) for the CPU restatement.  prove: the SAME configuration as the GPU arm
+    — same circuit, witness (seed 1), size k, SRS secret and rng stream — through oracle/prover.cpp, the threaded
+    C++ restatement of halo2's CPU prover; no extrapolation.  msm / ntt: a bounded sample size."""
     from __graft_entry__ import load_package
     from oracle import binding as orc
     from oracle import pyref
     orc.build()
     if args.workload == "prove":
-        from oracle import prover as OP
         zk = load_package()
-        ks = min(args.k, args.cpu_k)
+        ks = args.k if args.cpu_k is None else min(args.k, args.cpu_k)
         job = build_job(zk, args.circuit, ks, 1)
-        g, gl = orc.params_setup(ks, orc.random_fr(1, 4242)[0])
-        pk = OP.keygen_pk(job.cs, ks, job.fixed, job.map_col, job.map_row)
-        wide = np.random.Generator(np.random.PCG64(99)).integers(0, 1 << 64, size=(OP.rng_draws_needed(job.cs, ks), 8), dtype=np.uint64)
-        fn = lambda: OP.create_proof(g, gl, pk, job.advice, job.instances, wide, job.transcript_repr)
-        # scale from the sample to the full size: a complete oracle run of this circuit at k = 20 took
-        # 147.7 s on the 16 host cores of the GPU box against 3.5 s at k = 14 (profiles/
-        # r01_parity_mst_k20_gpu_vs_oracle.json), i.e. x42 rather than the x64 of the row count
-        scale = float(1 << (args.k - ks))
-        if args.circuit == "mst" and args.k == 20 and ks == 14:
-            scale = 42.2
-        if args.circuit == "mst_dense" and args.k == 20 and ks == 14:
-            scale = 47.0                                         # 112.8 s at k = 20 (r01_parity_mst_dense_k20_gpu_vs_oracle.json) / 2.4 s
-        return fn, None, f"oracle create_proof (restatement of halo2 v2023_02_02 CPU prover) on the same circuit at k={ks}", scale
+        g, gl = orc.params_setup(ks, random_scalars(1, SRS_SEED)[0])
+        pk = orc.CppProvingKey(job.cs, ks, job.fixed, job.map_col, job.map_row)
+        wide = np.random.Generator(np.random.PCG64(RNG_SEED)).integers(0, 1 << 64, size=(pk.rng_draws, 8), dtype=np.uint64)
+        fn = lambda: pk.create_proof(g, gl, job.advice, job.instances, wide, job.transcript_repr)
+        return fn, None, (f"oracle/prover.cpp create_proof — threaded C++ restatement of halo2 v2023_02_02's CPU prover (best_multiexp, best_fft, "
+                          f"evaluate_h on the 2^extended_k domain) — on the same circuit, witness, SRS and rng stream at k={ks}"), ks
     Ls = min(args.log_n, args.cpu_log_n)
     ns = 1 << Ls
     if args.workload == "msm":
         bases, _ = orc.params_setup(Ls, orc.random_fr(1, 4242)[0], with_lagrange=False)
         sc = random_scalars(ns, 7)
-        return (lambda: orc.best_multiexp(sc, bases)), ns / 1e6, f"best_multiexp restatement on 2^{Ls} points", 1.0
+        return (lambda: orc.best_multiexp(sc, bases)), ns / 1e6, f"best_multiexp restatement on 2^{Ls} points", Ls
     a = random_scalars(ns, 8)
     w = orc.ints_to_mont([pyref.omega_for_k(Ls)])[0]
-    return (lambda: orc.best_fft(a, w, Ls)), 64.0 * ns / 1e9, f"best_fft restatement on 2^{Ls} elements", 1.0
+    return (lambda: orc.best_fft(a, w, Ls)), 64.0 * ns / 1e9, f"best_fft restatement on 2^{Ls} elements", Ls
 
 
-def cpu_baseline(args):
+def cpu_baseline(args, gpu_proof=None):
+    """One pass of the CPU restatement on rank 0 (prove: one complete proof at the benchmarked size, whose bytes are
+    also compared with the GPU proof of the same inputs)."""
+    import hashlib
     from oracle import binding as orc
-    fn, units, desc, scale = cpu_sample(args)
+    fn, units, desc, size = cpu_sample(args)
     t0 = time.perf_counter()
-    fn()
+    res = fn()
     dt = time.perf_counter() - t0
     cores = orc.get_threads()
     if args.workload == "prove":
-        return {"value": dt * 1e3 * scale, "unit": "ms", "cores": cores, "kind": "port", "measured_ms": dt * 1e3,
-                "sample": f"{desc}: {dt:.1f} s measured, x{scale:g} to k={args.k} (factor measured once with a complete k=20 oracle run: 147.7 s on 16 cores, profiles/r01_parity_mst_k20_gpu_vs_oracle.json; x2^(k-ks) for other sizes)"}
+        out = {"value": dt * 1e3, "unit": "ms", "cores": cores, "kind": "port", "k": size, "same_config": size == args.k,
+               "sample": f"{desc}: one complete proof, {dt:.1f} s, no scaling"}
+        if gpu_proof is not None and size == args.k:
+            out["proof_sha256"] = hashlib.sha256(res).hexdigest()
+            out["gpu_proof_bytes_identical"] = bool(res == gpu_proof)
+        return out
     return {"value": units / dt, "unit": "Mpts/s" if args.workload == "msm" else "GB/s", "cores": cores, "kind": "port",
             "sample": f"{desc}, {dt:.2f} s"}
 
 
 def run_reference(args):
-    """--impl reference: halo2's CPU algorithm (oracle restatement; the Rust crate cannot be built
-    here) on this box's host cores, same metric/config, each step a bounded sample."""
+    """--impl reference: halo2's CPU algorithm (oracle restatement; the Rust crate cannot be built here) on this
+    box's host cores, same metric and config.  prove: every step is one complete create_proof at the benchmarked k
+    (tens of seconds on 16 cores), so the run times as many of the requested steps as fit in --ref-budget-s
+    (at least one) and says how many in `steps_timed`; nothing is extrapolated."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle import binding as orc
-    fn, units, desc, scale = cpu_sample(args)
+    fn, units, desc, size = cpu_sample(args)
     cores = orc.get_threads()
+    budget = args.ref_budget_s if args.workload == "prove" else float("inf")
+    t_begin = time.perf_counter()
+    warm = 0
     for _ in range(min(args.warmup, 1)):
+        fn(); warm += 1
+    per = (time.perf_counter() - t_begin) / max(warm, 1)
+    times = []
+    while len(times) < args.steps:
+        if times and (time.perf_counter() - t_begin) + max(per, np.mean(times)) > budget:
+            break
+        t0 = time.perf_counter()
         fn()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        fn()
-    dt = (time.perf_counter() - t0) / args.steps
+        times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times))
     if args.workload == "prove":
-        v, unit, metric, hib = dt * 1e3 * scale, "ms", "create_proof_ms", False
-        workload = WORKLOAD_TEXT["prove"].format(circuit=CIRCUITS[args.circuit][1].format(k=args.k))
-        sample = f"{desc}: {dt:.1f} s per step measured, x{scale:g} to k={args.k} (factor from a complete k=20 oracle run, profiles/r01_parity_mst_k20_gpu_vs_oracle.json)"
+        v, unit, metric, hib = dt * 1e3, "ms", "create_proof_ms", False
+        workload = WORKLOAD_TEXT["prove"].format(circuit=CIRCUITS[args.circuit][1].format(k=size))
+        sample = f"{desc}: {len(times)} complete proof(s) timed, mean {dt:.1f} s, no scaling"
     else:
         v = units / dt
         unit, metric, hib = ("Mpts/s", "msm_mpts_per_s", True) if args.workload == "msm" else ("GB/s", "ntt_gb_per_s", True)
-        workload = WORKLOAD_TEXT[args.workload].format(L=args.log_n)
+        workload = WORKLOAD_TEXT[args.workload].format(L=size)
         sample = f"{desc} per step"
     emit({"impl": "reference", "metric": metric, "unit": unit, "value": v, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": hib,
-                      "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 Montgomery (CPU)", "data": "synthetic",
-                      "config": {"workload": workload},
-                      "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
-                      "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+          "steps": args.steps, "steps_timed": len(times), "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": hib,
+          "scaling": "strong" if int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.workload == "prove" else "weak", "vs_baseline": None,
+          "dtype": "u64x4 Montgomery (CPU)", "data": "synthetic",
+          "config": {"workload": workload, "same_config_as_gpu_arm": size == (args.k if args.workload == "prove" else args.log_n)},
+          "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+          "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 _JSON_OUT = None
@@ -688,7 +705,9 @@ def main():
     ap.add_argument("--workload", default="prove", choices=["prove", "msm", "ntt"])
     ap.add_argument("--k", type=int, default=20, help="prove: circuit size")
     ap.add_argument("--circuit", default="mst", choices=sorted(CIRCUITS), help="prove: circuit shape")
-    ap.add_argument("--cpu-k", type=int, default=14, help="prove: size of the bounded CPU sample")
+    ap.add_argument("--cpu-k", type=int, default=None, help="prove: size of the CPU arm's proof (default: the benchmarked k; smaller only for quick local runs)")
+    ap.add_argument("--ref-budget-s", type=float, default=600.0, help="--impl reference, prove: wall-clock budget; at least one complete proof is timed")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--log-n", type=int, default=24, help="msm / ntt size")
     ap.add_argument("--cpu-log-n", type=int, default=None, help="msm / ntt: size of the bounded CPU sample")
     ap.add_argument("--profile-step", action="store_true", help="bracket one extra step with cudaProfilerStart/Stop (ncu --profile-from-start off)")

@@ -9,27 +9,37 @@ static constexpr uint32_t NTT_THREADS = 512;
 static constexpr uint32_t NTT_MAX_LOG_M = 10;      // <= 1024-point DFT per tile
 static constexpr uint32_t NTT_MAX_LOG_TW = 3;      // <= 8 columns = 256 B contiguous
 static constexpr uint32_t NTT_TILE_CAP_LOG = 12;   // 4096 elements = 128 KiB of shared memory
+static constexpr int NTT_WARP_CFG_DEFAULT = 0;     // launch shape of the warp-level kernel, see ntt_warp_launch
 
 __global__ void __launch_bounds__(NTT_THREADS, 1) ntt_pass_kernel(const NttPassArgs a) {
     extern __shared__ half_t ntt_sm[];
     ntt_pass_block(a, blockIdx.x, blockDim.x, ntt_sm);
 }
 
-// one warp per 128-element tile, 4 KB of warp-private shared memory each.  8 warps per block and
-// 3 blocks per SM measured best (2^20: 0.217 ms vs 0.234 ms with 4 x 6 or 2 x 12; 64-register
-// variants with 32 warps per SM spill and lose) — profiles/r01_ntt_warp_vs_block.txt
-__global__ void __launch_bounds__(32 * NTT_WARPS_PER_BLOCK, 3) ntt_warp_pass_kernel(const NttPassArgs a, uint32_t ntiles) {
-    __shared__ half_t sm[NTT_WARPS_PER_BLOCK][256];
-    const uint32_t w = threadIdx.x >> 5, wid = blockIdx.x * NTT_WARPS_PER_BLOCK + w;
-    if (wid < ntiles) ntt_pass_warp<false>(a, wid, threadIdx.x & 31, sm[w]);
+// one warp per 128-element tile, 4 KB of warp-private shared memory each.  Launch shapes (warps per block x
+// resident blocks per SM), selected per launch by ntt_warp_launch below:
+//   8 x 3  80 registers, 24 warps / SM, no spills
+//   4 x 7  72 registers (two spilled), 28 warps / SM: 148 x 28 = 4144 resident warps, so the 8192 tiles of one
+//          2^20 pass are 1.98 waves instead of the 2.31 (= 3 rounds, a quarter of the last one idle) of 8 x 3
+// SPARSE: first pass of lagrange_to_coeff (ctx->ntt_sparse_hint): all-zero tiles skip the arithmetic.  The witness
+// columns of a padded circuit are zero outside the used rows and the blinding rows, and a first-pass tile gathers
+// rows at stride n / 128: 262 of 8192 tiles are live for the Merkle Sum Tree circuit at k = 20.
+template <int WPB, int MINB, bool SPARSE>
+__global__ void __launch_bounds__(32 * WPB, MINB) ntt_warp_pass_kernel(const NttPassArgs a, uint32_t ntiles) {
+    __shared__ half_t sm[WPB][256];
+    const uint32_t w = threadIdx.x >> 5, wid = blockIdx.x * WPB + w;
+    if (wid < ntiles) ntt_pass_warp<SPARSE>(a, wid, threadIdx.x & 31, sm[w]);
 }
-// first pass of lagrange_to_coeff (ctx->ntt_sparse_hint): all-zero tiles skip the arithmetic.  The witness columns
-// of a padded circuit are zero outside the used rows and the blinding rows, and a first-pass tile gathers rows at
-// stride n / 128: 262 of 8192 tiles are live for the Merkle Sum Tree circuit at k = 20.
-__global__ void __launch_bounds__(32 * NTT_WARPS_PER_BLOCK, 3) ntt_warp_pass_sparse_kernel(const NttPassArgs a, uint32_t ntiles) {
-    __shared__ half_t sm[NTT_WARPS_PER_BLOCK][256];
-    const uint32_t w = threadIdx.x >> 5, wid = blockIdx.x * NTT_WARPS_PER_BLOCK + w;
-    if (wid < ntiles) ntt_pass_warp<true>(a, wid, threadIdx.x & 31, sm[w]);
+template <int WPB, int MINB> static void ntt_warp_launch_t(const NttPassArgs& a, uint32_t ntiles, bool sparse, cudaStream_t st) {
+    const uint32_t grid = (ntiles + WPB - 1) / WPB;
+    if (sparse) ntt_warp_pass_kernel<WPB, MINB, true><<<grid, 32 * WPB, 0, st>>>(a, ntiles);
+    else ntt_warp_pass_kernel<WPB, MINB, false><<<grid, 32 * WPB, 0, st>>>(a, ntiles);
+}
+static void ntt_warp_launch(b200zk_ctx* ctx, const NttPassArgs& a, uint32_t ntiles, bool sparse) {
+    static const int cfg = [] { const char* e = getenv("B200ZK_NTT_WARP_CFG"); return e ? atoi(e) : NTT_WARP_CFG_DEFAULT; }();
+    if (cfg == 1) ntt_warp_launch_t<4, 7>(a, ntiles, sparse, ctx->stream);
+    else if (cfg == 2) ntt_warp_launch_t<7, 4>(a, ntiles, sparse, ctx->stream);
+    else ntt_warp_launch_t<8, 3>(a, ntiles, sparse, ctx->stream);
 }
 
 __global__ void ntt_pow_table_kernel(fe_t* out, const fe_t base, uint32_t count, uint32_t shift) {
@@ -157,10 +167,7 @@ static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, f
         uint32_t tile = 1u << (q.log_m + q.log_tw);
         uint32_t threads = tile / 2 < NTT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : NTT_THREADS;
         if (plan.warp) {
-            const uint32_t ntiles = q.blocks * batch;
-            const uint32_t grid = (ntiles + NTT_WARPS_PER_BLOCK - 1) / NTT_WARPS_PER_BLOCK;
-            if (ctx->ntt_sparse_hint && p == 0) ntt_warp_pass_sparse_kernel<<<grid, 32 * NTT_WARPS_PER_BLOCK, 0, ctx->stream>>>(a, ntiles);
-            else ntt_warp_pass_kernel<<<grid, 32 * NTT_WARPS_PER_BLOCK, 0, ctx->stream>>>(a, ntiles);
+            ntt_warp_launch(ctx, a, q.blocks * batch, ctx->ntt_sparse_hint && p == 0);
         } else {
             ntt_pass_kernel<<<q.blocks * batch, threads, smem, ctx->stream>>>(a);
         }

@@ -159,17 +159,37 @@ inline void butterfly_layer(Fr* left, Fr* right, size_t half, size_t twiddle_chu
         right[i] = left[i]; left[i] += t2; right[i] -= t2;
     }
 }
+// The combining layer of a node split over `threads` workers (disjoint index ranges, same arithmetic).
+void butterfly_layer_par(Fr* left, Fr* right, size_t half, size_t twiddle_chunk, const Fr* tw, int threads) {
+    if (threads <= 1 || half < 4096) { butterfly_layer(left, right, half, twiddle_chunk, tw); return; }
+    auto range = [=](size_t s, size_t e) {
+        for (size_t i = s; i < e; ++i) {
+            if (i == 0) { Fr t = right[0]; right[0] = left[0]; left[0] += t; right[0] -= t; continue; }
+            Fr t2 = right[i] * tw[i * twiddle_chunk];
+            right[i] = left[i]; left[i] += t2; right[i] -= t2;
+        }
+    };
+    std::vector<std::thread> th;
+    size_t chunk = (half + threads - 1) / threads;
+    for (int t = 1; t < threads; ++t) { size_t s = t * chunk, e = std::min(half, s + chunk); if (s < e) th.emplace_back(range, s, e); }
+    range(0, std::min(half, chunk));
+    for (auto& t : th) t.join();
+}
+// arithmetic::recursive_butterfly_arithmetic: rayon::join on the halves down to par_depth levels.  Upstream's tag runs
+// the combining butterflies of a node on the joining thread; here the 2^par_depth worker budget is also spent on
+// that layer (as later halo2 releases do), which changes the schedule and nothing else.
 void recursive_butterfly(Fr* a, size_t n, size_t twiddle_chunk, const Fr* tw, int par_depth) {
     if (n == 2) { Fr t = a[1]; a[1] = a[0]; a[0] += t; a[1] -= t; return; }
     if (par_depth > 0) {                                // rayon::join
         std::thread other([=] { recursive_butterfly(a, n / 2, twiddle_chunk * 2, tw, par_depth - 1); });
         recursive_butterfly(a + n / 2, n / 2, twiddle_chunk * 2, tw, par_depth - 1);
         other.join();
+        butterfly_layer_par(a, a + n / 2, n / 2, twiddle_chunk, tw, 1 << par_depth);
     } else {
         recursive_butterfly(a, n / 2, twiddle_chunk * 2, tw, 0);
         recursive_butterfly(a + n / 2, n / 2, twiddle_chunk * 2, tw, 0);
+        butterfly_layer(a, a + n / 2, n / 2, twiddle_chunk, tw);
     }
-    butterfly_layer(a, a + n / 2, n / 2, twiddle_chunk, tw);
 }
 }  // namespace
 
@@ -177,10 +197,11 @@ void best_fft(Fr* a, const Fr& omega, unsigned log_n) {
     size_t n = (size_t)1 << log_n;
     int threads = num_threads();
     unsigned log_threads = 0; while ((2 << log_threads) <= threads) ++log_threads;
-    for (size_t k = 0; k < n; ++k) { size_t rk = bitreverse(k, log_n); if (k < rk) std::swap(a[rk], a[k]); }
+    // bit-reversal permutation and twiddle table omega^i, i < n/2 (chunked over the workers: same values)
+    parallelize(n, [&](size_t s, size_t e) { for (size_t k = s; k < e; ++k) { size_t rk = bitreverse(k, log_n); if (k < rk) std::swap(a[rk], a[k]); } });
     std::vector<Fr> tw(n / 2 ? n / 2 : 1);
-    Fr w = Fr::one();
-    for (size_t i = 0; i < n / 2; ++i) { tw[i] = w; w *= omega; }
+    parallelize(n / 2, [&](size_t s, size_t e) { Fr w = omega.pow_u64(s); for (size_t i = s; i < e; ++i) { tw[i] = w; w *= omega; } });
+    if (n / 2 == 0) tw[0] = Fr::one();
     if (log_n <= log_threads) {
         size_t chunk = 2, twiddle_chunk = n / 2;
         for (unsigned l = 0; l < log_n; ++l) {
@@ -245,9 +266,8 @@ void Domain::lagrange_to_coeff(Fr* a) const {
 }
 
 void Domain::coeff_to_extended(const Fr* a, Fr* out) const {
-    memcpy(out, a, n * sizeof(Fr));
+    parallelize(extended_len(), [&](size_t s, size_t e) { for (size_t i = s; i < e; ++i) out[i] = i < n ? a[i] : Fr::zero(); });
     distribute_powers_zeta(out, n, true);
-    for (size_t i = n; i < extended_len(); ++i) out[i] = Fr::zero();
     best_fft(out, extended_omega, extended_k);
 }
 

@@ -352,3 +352,52 @@ class Domain:
         out = _arr(1)
         lib().orc_domain_rotate_omega(self._h, _p(np.ascontiguousarray(x)), ctypes.c_int(rot), _p(out))
         return out[0]
+
+
+# ---- threaded C++ restatement of keygen_pk + create_proof (oracle/prover.cpp) ----
+class CppProvingKey:
+    """keygen_pk of oracle/prover.cpp: same inputs as oracle.prover.keygen_pk (cs must offer to_blob(k))."""
+
+    def __init__(self, cs, k, fixed, map_col, map_row):
+        L = lib()
+        L.orc_pk_create.restype = ctypes.c_void_p
+        L.orc_pk_rng_draws.restype = ctypes.c_size_t
+        self.k, self.n = k, 1 << k
+        blob = np.ascontiguousarray(cs.to_blob(k), dtype=np.uint32)
+        cols = [np.ascontiguousarray(f, dtype=np.uint64).reshape(self.n, 4) for f in fixed]
+        ptrs = (ctypes.c_void_p * max(len(cols), 1))(*[c.ctypes.data for c in cols])
+        mc = None if map_col is None else np.ascontiguousarray(map_col, dtype=np.uint32)
+        mr = None if map_row is None else np.ascontiguousarray(map_row, dtype=np.uint32)
+        self._h = L.orc_pk_create(_p(blob), ctypes.c_size_t(blob.shape[0]), ptrs, None if mc is None else _p(mc), None if mr is None else _p(mr))
+        if not self._h:
+            raise ValueError("orc_pk_create: malformed constraint-system blob")
+        self.rng_draws = int(L.orc_pk_rng_draws(ctypes.c_void_p(self._h)))
+        self.num_advice, self.num_instance = cs.num_advice, cs.num_instance
+
+    def close(self):
+        if self._h:
+            lib().orc_pk_destroy(ctypes.c_void_p(self._h))
+            self._h = None
+
+    def create_proof(self, g, g_lagrange, advice, instances, rng_wide, transcript_repr):
+        """plonk::create_proof; instances = lists of Python ints, transcript_repr = Python int (as oracle.prover)."""
+        n = self.n
+        adv = [np.ascontiguousarray(a, dtype=np.uint64).reshape(n, 4) for a in advice]
+        adv_ptrs = (ctypes.c_void_p * max(len(adv), 1))(*[a.ctypes.data for a in adv])
+        P = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+        inst = [ints_to_mont([v % P for v in col]) if len(col) else np.zeros((1, 4), dtype=np.uint64) for col in instances]
+        inst_ptrs = (ctypes.c_void_p * max(len(inst), 1))(*[a.ctypes.data for a in inst])
+        lens = np.array([len(col) for col in instances] + [0], dtype=np.uint32)
+        wide = np.ascontiguousarray(rng_wide, dtype=np.uint64).reshape(-1, 8)
+        g = np.ascontiguousarray(g, dtype=np.uint64)
+        gl = np.ascontiguousarray(g_lagrange, dtype=np.uint64)
+        repr_m = ints_to_mont([transcript_repr % P])
+        out = np.zeros(1 << 16, dtype=np.uint8)
+        ln = ctypes.c_size_t()
+        rc = lib().orc_create_proof(ctypes.c_void_p(self._h), _p(g), _p(gl), adv_ptrs, inst_ptrs, _p(lens), _p(wide), ctypes.c_size_t(wide.shape[0]),
+                                    _p(repr_m), _p(out), ctypes.c_size_t(out.shape[0]), ctypes.byref(ln))
+        if rc == 1:
+            raise ValueError("ConstraintSystemFailure: lookup input not in table")
+        if rc:
+            raise ValueError(f"orc_create_proof failed with code {rc}")
+        return bytes(out[: ln.value])

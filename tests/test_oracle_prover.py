@@ -99,3 +99,50 @@ def test_frontend_montgomery_conversion(zk, orc):
     got = synth.mont_from_u64(vals)
     assert np.array_equal(got, orc.ints_to_mont([int(v) for v in vals]))
     assert np.array_equal(synth.mont_from_small(vals), got)
+
+
+@pytest.mark.parametrize("name,k", [("small", 5), ("v3_shaped", 6), ("mst_shaped", 7), ("generic_shapes", 6)])
+def test_cpp_prover_matches_python_prover(zk, orc, name, k):
+    """oracle/prover.cpp (the threaded restatement the CPU arm of the bench and the full-size parity checks run)
+    emits exactly the bytes of oracle/prover.py (the readable restatement the verifier restatement is tested on)."""
+    job = _job(zk, name, k)
+    s, g, pk, want, _ = _prove(orc, job)
+    _, gl = orc.params_setup(job.k, s)
+    cpk = orc.CppProvingKey(job.cs, job.k, job.fixed, job.map_col, job.map_row)
+    assert cpk.rng_draws == OP.rng_draws_needed(job.cs, job.k)
+    wide = orc.XorShiftWide().draw(cpk.rng_draws)
+    got = cpk.create_proof(g, gl, job.advice, job.instances, wide, job.transcript_repr)
+    cpk.close()
+    assert got == want
+
+
+def test_cpp_prover_real_circuits(zk, orc):
+    """The reference's circuits through both restatements: Merkle Sum Tree (test_full_prover's instance, k = 9),
+    LessThan (dynamic lookup, k = 10), SafeAccumulator (16 quotient cosets, k = 8); and the failure path."""
+    import importlib
+    fe = importlib.import_module(zk.__name__ + ".frontend")
+    chips = importlib.import_module(zk.__name__ + ".chips")
+    leaf, elements, indices = (10, 100), [(1, 10), (5, 50), (6, 60), (9, 90), (9, 90)], [0] * 5
+    root = chips.compute_merkle_sum_root(leaf, elements, indices)
+    circuit = chips.MerkleSumTreeCircuit(leaf[0], leaf[1], [e[0] for e in elements], [e[1] for e in elements], indices, 500)
+    jobs = [fe.synthesize_job(circuit, 9, [[leaf[0], leaf[1], root[0], 500]]),
+            fe.synthesize_job(chips.LessThanCircuit(755), 10, [list(range(800))]),
+            fe.synthesize_job(chips.SafeAccumulatorCircuit([1, 3], [0, 0, 14, 13]), 8, [[0, 0, 15, 1]])]
+    for job in jobs:
+        s, g, pk, want, _ = _prove(orc, job)
+        _, gl = orc.params_setup(job.k, s)
+        cpk = orc.CppProvingKey(job.cs, job.k, job.fixed, job.map_col, job.map_row)
+        wide = orc.XorShiftWide().draw(cpk.rng_draws)
+        assert cpk.create_proof(g, gl, job.advice, job.instances, wide, job.transcript_repr) == want
+        cpk.close()
+    synth = importlib.import_module(zk.__name__ + ".circuits_synth")
+    job = synth.small(6)
+    bad = np.array(job.advice[5 + 3 + 2])
+    bad[3] = orc.ints_to_mont([100000])[0]
+    job.advice[5 + 3 + 2] = bad
+    s = orc.random_fr(1, 77)[0]
+    g, gl = orc.params_setup(job.k, s)
+    cpk = orc.CppProvingKey(job.cs, job.k, job.fixed, job.map_col, job.map_row)
+    with pytest.raises(ValueError, match="ConstraintSystemFailure"):
+        cpk.create_proof(g, gl, job.advice, job.instances, orc.XorShiftWide().draw(cpk.rng_draws), job.transcript_repr)
+    cpk.close()
