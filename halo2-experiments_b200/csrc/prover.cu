@@ -121,6 +121,9 @@ struct b200zk_pk {
     std::vector<HFr> coset_t;                                  // 1 / (c_j^n - 1): the vanishing polynomial on coset j
     // lookup terms on lk_cosets_n < q cosets (prover_kernels.cuh, lookup_extrapolate_row); == q: not split
     uint32_t lk_cosets_n = 0;
+    // lookup cosets and table values of ALL lookups kept side by side (4 arrays of lk_cosets_n * n per lookup), so that they
+    // are computed on the side stream while the transcript-bound phases run; false = one lookup at a time after y (less memory)
+    bool lk_early = false;
     fe_t *lk_lambda = nullptr, *coset_t_dev = nullptr;        // extrapolation weights [(q - CL) x CL]; coset_t on the device [q]
     // device program data
     uint32_t* d_prog = nullptr;                       // gates program | lookup programs
@@ -182,6 +185,7 @@ static size_t arena_need(const b200zk_pk* pk) {
     size_t elems = 2 * A * n + 2 * I * n + draws + 7 * L * n + S * n + S * ext + 3 * n   // columns, lookups, perm, tmp
                    + ext * (1 + A + I + 4 + 1)                                            // h, cosets, lookup cosets + table_value, h_L
                    + n * (1 + 8 + 4);                                                     // h_poly, shplonk set sums, hx/lx/tmp
+    if (pk->lk_early) elems += 4 * L * (size_t)pk->lk_cosets_n * n + 64;
     return elems * sizeof(fe_t) + (size_t)draws * 64 + (64 << 10);
 }
 
@@ -553,6 +557,22 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     fe_t* inst_cosets = ar.take<fe_t>(I * ext);
     fe_t* lk_cosets = ar.take<fe_t>(4 * ext);                    // z, a', s', table_value
     fe_t* h_lk = ar.take<fe_t>(ext);                             // lookup part of the quotient when it runs on fewer cosets
+    const uint32_t CL = pk->lk_cosets_n;
+    const bool lk_split = L && CL < pk->q;
+    const size_t lk_span = (size_t)(lk_split ? CL : pk->q) * n;  // rows of one lookup coset array
+    fe_t* lk_all = pk->lk_early ? ar.take<fe_t>(4 * (size_t)L * lk_span) : nullptr;
+    // arrays of lookup l: product z, permuted input a', permuted table s', table value (all indexed by global coset row)
+    auto LKC = [&](uint32_t l, uint32_t which) { return pk->lk_early ? lk_all + ((size_t)l * 4 + which) * lk_span : lk_cosets + (size_t)which * ext; };
+    // this rank's share of the cosets the lookup terms run on
+    const uint32_t lj0 = std::min(cj0, lk_split ? CL : pk->q), lj1 = std::min(cj1, lk_split ? CL : pk->q);
+    const uint32_t lk_row0 = lj0 * (uint32_t)n, lk_rows = (lj1 - lj0) * (uint32_t)n;
+    auto lookup_table_value = [&](uint32_t l, const HFr* chv) {  // (compressed input + beta)(compressed table + gamma) on this rank's lookup cosets
+        PhaseTimer t(pk, PH_QUOT);
+        ExprArgs ea = expr_args(pk, pk->lookup_prog[l].first, pk->lookup_prog[l].second, true, EXM_LOOKUP_PROD, chv, LKC(l, 3), nullptr);
+        ea.row0 = lk_row0; ea.rows = lk_rows;
+        expr_kernel<<<nb(lk_rows), PK_THREADS, 0, ctx->stream>>>(ea);
+        ctx->launches++;
+    };
     fe_t* h_poly = ar.take<fe_t>(n);
     fe_t* set_sums = ar.take<fe_t>(8 * n);
     fe_t* sh_tmp = ar.take<fe_t>(4 * n);
@@ -731,6 +751,14 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     ch[EXF_BETA] = tr.squeeze_challenge();
     ch[EXF_GAMMA] = tr.squeeze_challenge();
     const HFr beta = ch[EXF_BETA], gamma = ch[EXF_GAMMA];
+    if (pk->lk_early && lk_rows) {                               // side stream: a', s' cosets and the table values (theta, beta, gamma known)
+        SideStream side(ctx);
+        for (uint32_t l = 0; l < L; ++l) {
+            ZK_TRY(my_cosets(LK(l, 4), LKC(l, 1), lj0, lj1));
+            ZK_TRY(my_cosets(LK(l, 5), LKC(l, 2), lj0, lj1));
+            lookup_table_value(l, ch);
+        }
+    }
 
     // ---- step 6: permutation argument
     auto column_values = [&](uint32_t type, uint32_t idx) -> const fe_t* {
@@ -845,6 +873,10 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         mark("lookup_product_commits");
         for (uint32_t l = 0; l < L; ++l) if (sh.mine(l)) ZK_TRY(lagrange_to_coeff(pk, LK(l, 6)));
         ZK_TRY(share(pieces));
+        if (pk->lk_early && lk_rows) {                           // side stream: the product cosets
+            SideStream side(ctx);
+            for (uint32_t l = 0; l < L; ++l) ZK_TRY(my_cosets(LK(l, 6), LKC(l, 0), lj0, lj1));
+        }
     }
 
     // ---- step 8: vanishing argument, random polynomial
@@ -899,28 +931,23 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     }
     // lookup terms: on all q cosets straight into h, or — when their degree allows — on the first CL cosets into
     // h_lk, extended to the other cosets after the per-coset iNTT (lookup_extrapolate_row)
-    const uint32_t CL = pk->lk_cosets_n;
-    const bool lk_split = L && CL < pk->q;
-    // this rank's share of the cosets the lookup terms run on
-    const uint32_t lj0 = std::min(cj0, lk_split ? CL : pk->q), lj1 = std::min(cj1, lk_split ? CL : pk->q);
-    const uint32_t lk_row0 = lj0 * (uint32_t)n, lk_rows = (lj1 - lj0) * (uint32_t)n;
     if (lk_split && lk_rows) ZK_CUDA(ctx, cudaMemsetAsync(h_lk + lk_row0, 0, (size_t)lk_rows * sizeof(fe_t), st));
     for (uint32_t l = 0; l < L && lk_rows; ++l) {
-        fe_t *zc = lk_cosets, *ac = lk_cosets + ext, *sc = lk_cosets + 2 * ext, *tv = lk_cosets + 3 * ext;
-        ZK_TRY(my_cosets(LK(l, 6), zc, lj0, lj1));
-        ZK_TRY(my_cosets(LK(l, 4), ac, lj0, lj1));
-        ZK_TRY(my_cosets(LK(l, 5), sc, lj0, lj1));
+        fe_t *zc = LKC(l, 0), *ac = LKC(l, 1), *sc = LKC(l, 2), *tv = LKC(l, 3);
+        if (!pk->lk_early) {
+            ZK_TRY(my_cosets(LK(l, 6), zc, lj0, lj1));
+            ZK_TRY(my_cosets(LK(l, 4), ac, lj0, lj1));
+            ZK_TRY(my_cosets(LK(l, 5), sc, lj0, lj1));
+            lookup_table_value(l, ch);
+        }
         PhaseTimer t(pk, PH_QUOT);
-        ExprArgs ea = expr_args(pk, pk->lookup_prog[l].first, pk->lookup_prog[l].second, true, EXM_LOOKUP_PROD, ch, tv, nullptr);
-        ea.row0 = lk_row0; ea.rows = lk_rows;
-        expr_kernel<<<nb(lk_rows), PK_THREADS, 0, st>>>(ea);
         QuotLookupArgs ql{};
         ql.h = lk_split ? h_lk : h; ql.y = to_dev(y); ql.beta = to_dev(beta); ql.gamma = to_dev(gamma);
         ql.l0 = pk->l0; ql.l_last = pk->l_last; ql.l_active = pk->l_active; ql.z = zc; ql.a = ac; ql.s = sc; ql.table_value = tv;
         ql.log_ext = dom->k; ql.rot_scale = rot_scale; ql.rows = lk_rows; ql.row0 = lk_row0;
         { HFr yp = y * y; for (int i = 0; i < 4; ++i) { ql.ypow[i] = to_dev(yp); yp = yp * y; } }
         quot_lookup_kernel<<<nb(lk_rows), PK_THREADS, 0, st>>>(ql);
-        ctx->launches += 2;
+        ctx->launches++;
     }
     ZK_CUDA(ctx, cudaGetLastError());
 
@@ -1444,6 +1471,14 @@ int32_t b200zk_pk_create(b200zk_params* params, const uint32_t* cs_blob, size_t 
         PK_CUDA(cudaStreamSynchronize(st));
         PtrTab pt{cs.F, cs.A, cs.I};
         PK_TRY(dev_alloc(pk, &pk->d_ptrs, pt.total()));
+    }
+    {
+        // early lookup cosets when their 4 L CL n elements are a modest share of the device (B200ZK_LOOKUP_EARLY=0/1 overrides)
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t extra = 4 * (size_t)pk->L * pk->lk_cosets_n * pk->n * sizeof(fe_t);
+        pk->lk_early = pk->L > 0 && extra <= free_b / 4;
+        if (const char* e = getenv("B200ZK_LOOKUP_EARLY")) pk->lk_early = pk->L > 0 && e[0] != '0';
     }
     pk->arena_bytes = arena_need(pk);
     PK_TRY(dev_alloc(pk, &pk->arena, pk->arena_bytes));
