@@ -501,6 +501,26 @@ class ParamsKZG:
         self.backend._check(lib().b200zk_params_read(self._h, _p(g), _p(gl)))
         return g, gl
 
+    def to_bytes(self, g2, s_g2):
+        """ParamsKZG::write into memory -> bytes: k | g | g_lagrange (compressed G1) | g2 | s_g2 (compressed G2)."""
+        lib().b200zk_params_serialized_size.restype = ctypes.c_size_t
+        cap = int(lib().b200zk_params_serialized_size(ctypes.c_uint32(self.k), ctypes.c_int32(1)))
+        out = np.zeros(cap, dtype=np.uint8)
+        ln = ctypes.c_size_t()
+        self.backend._check(lib().b200zk_params_serialize(self._h, _p(np.ascontiguousarray(g2, dtype=np.uint64)), _p(np.ascontiguousarray(s_g2, dtype=np.uint64)),
+                                                          _p(out), ctypes.c_size_t(cap), ctypes.byref(ln)))
+        return out[: ln.value].tobytes()
+
+    @classmethod
+    def from_bytes(cls, backend, data):
+        """ParamsKZG::read from memory -> (params, g2, s_g2); raises on a malformed or off-curve encoding."""
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        h = ctypes.c_void_p()
+        g2, s_g2 = np.zeros(16, dtype=np.uint64), np.zeros(16, dtype=np.uint64)
+        backend._check(lib().b200zk_params_deserialize(backend._ctx, _p(buf), ctypes.c_size_t(buf.shape[0]), ctypes.byref(h), _p(g2), _p(s_g2)))
+        k = int(np.frombuffer(buf[:4].tobytes(), dtype="<u4")[0])
+        return cls(backend, h, k), g2, s_g2
+
     def commit(self, poly):
         poly = _fr(poly)
         out = np.zeros(12, dtype=np.uint64)
@@ -566,8 +586,47 @@ class VerifyingKey:
         if self.fixed.shape[0] != cs.num_fixed or self.sigma.shape[0] != len(cs.permutation):
             raise B200zkError("commitment counts do not match the constraint system")
 
-    def verify_proof(self, instances, proof, transcript_repr):
-        """plonk::verify_proof(..).is_ok() with VerifierSHPLONK / SingleStrategy / Blake2bRead."""
+    @property
+    def transcript_repr(self):
+        """The library-derived vk.transcript_repr (b200zk_vk_transcript_repr): a hash of k, the constraint system and the
+        fixed / permutation commitments.  Not upstream's value (a hash of Rust's Debug rendering) — a Rust host passes its own."""
+        out = np.zeros(4, dtype=np.uint64)
+        fixed = self.fixed if self.fixed.shape[0] else np.zeros((1, 8), dtype=np.uint64)
+        sigma = self.sigma if self.sigma.shape[0] else np.zeros((1, 8), dtype=np.uint64)
+        rc = lib().b200zk_vk_transcript_repr(_p(self.blob), ctypes.c_size_t(self.blob.shape[0]), _p(fixed), _p(sigma), _p(out))
+        if rc != OK:
+            raise B200zkError(f"b200zk_vk_transcript_repr: error {rc}")
+        return out
+
+    def commitments_to_bytes(self):
+        """The commitments part of VerifyingKey::write: fixed count (u32 BE) | fixed | permutation commitments (compressed)."""
+        lib().b200zk_vk_serialized_size.restype = ctypes.c_size_t
+        nf, ns = self.fixed.shape[0], self.sigma.shape[0]
+        out = np.zeros(int(lib().b200zk_vk_serialized_size(ctypes.c_uint32(nf), ctypes.c_uint32(ns))), dtype=np.uint8)
+        fixed = self.fixed if nf else np.zeros((1, 8), dtype=np.uint64)
+        sigma = self.sigma if ns else np.zeros((1, 8), dtype=np.uint64)
+        rc = lib().b200zk_vk_serialize(_p(fixed), ctypes.c_uint32(nf), _p(sigma), ctypes.c_uint32(ns), _p(out), ctypes.c_size_t(out.shape[0]))
+        if rc != OK:
+            raise B200zkError(f"b200zk_vk_serialize: error {rc}")
+        return out.tobytes()
+
+    @staticmethod
+    def commitments_from_bytes(data, num_sigma):
+        """-> (fixed (F, 8), sigma (P, 8)); raises on an invalid point encoding."""
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        cap = max((buf.shape[0] - 4) // 32, 1)
+        fixed, sigma = np.zeros((cap, 8), dtype=np.uint64), np.zeros((max(num_sigma, 1), 8), dtype=np.uint64)
+        nf = ctypes.c_uint32()
+        rc = lib().b200zk_vk_deserialize(_p(buf), ctypes.c_size_t(buf.shape[0]), ctypes.c_uint32(num_sigma), _p(fixed), ctypes.c_uint32(cap), ctypes.byref(nf), _p(sigma))
+        if rc != OK:
+            raise B200zkError(f"b200zk_vk_deserialize: error {rc}")
+        return fixed[: nf.value], sigma[:num_sigma]
+
+    def verify_proof(self, instances, proof, transcript_repr=None):
+        """plonk::verify_proof(..).is_ok() with VerifierSHPLONK / SingleStrategy / Blake2bRead.  transcript_repr: the value the
+        prover absorbed (default: the library-derived one, self.transcript_repr)."""
+        if transcript_repr is None:
+            transcript_repr = self.transcript_repr
         cols = [np.ascontiguousarray(c, dtype=np.uint64).reshape(-1, 4) for c in instances]
         lens = np.array([c.shape[0] for c in cols] + [0], dtype=np.uint32)
         keep = [c if c.shape[0] else np.zeros((1, 4), dtype=np.uint64) for c in cols]

@@ -276,6 +276,32 @@ int32_t b200zk_g2_mul(const void* g2_or_null, const void* s_fr, void* out_g2);
  * G1Affine 64 B, G2Affine 128 B each). */
 int32_t b200zk_pairing_check(const void* g1_points, const void* g2_points, size_t count);
 
+/* ---- formats: halo2_proofs v2023_02_02 ParamsKZG::write / read (src/poly/kzg/commitment.rs),
+ *      VerifyingKey::write / read commitments (src/plonk.rs), halo2curves G1Affine / G2Affine to_bytes / from_bytes,
+ *      and vk.transcript_repr -------------------------------------------------------------------------------------
+ * params_serialize = ParamsKZG::write: k (u32 LE) | n compressed G1 (g) | n compressed G1 (g_lagrange) | g2 | s_g2
+ * (64-byte compressed G2 each); the 2n points are compressed / decompressed on the device (one Fq exponentiation per
+ * point to recover y).  g2 / s_g2 cross as 128-byte G2Affine (x.c0, x.c1, y.c0, y.c1 Montgomery limbs).  deserialize
+ * rejects non-canonical coordinates and points off the curve (B200ZK_EINVAL).
+ * vk_serialize = the commitments VerifyingKey::write emits: fixed count (u32 BE) | fixed | permutation commitments.
+ * vk_transcript_repr: the Fr create_proof / verify_proof absorb first.  Upstream hashes Rust's `{:?}` rendering of the
+ * pinned key, which cannot be restated outside Rust, so a Rust host passes upstream's value; this entry derives a
+ * value with the same role for other hosts: Blake2b-512 (personal "Halo2-Verify-Key") over (len u64 LE) | cs blob |
+ * fixed | permutation commitments (uncompressed), then from_bytes_wide.  It binds k, the constraint system and the
+ * commitments into every challenge; it is NOT upstream's value. */
+size_t b200zk_params_serialized_size(uint32_t k, int32_t with_lagrange);
+int32_t b200zk_params_serialize(b200zk_params* p, const void* g2, const void* s_g2, uint8_t* out, size_t cap, size_t* len);
+int32_t b200zk_params_deserialize(b200zk_ctx* ctx, const uint8_t* in, size_t len, b200zk_params** out, void* g2_out, void* s_g2_out);
+int32_t b200zk_g1_to_bytes(const void* affine_points, size_t count, uint8_t* out32);
+int32_t b200zk_g1_from_bytes(const uint8_t* in32, size_t count, void* affine_out);     /* B200ZK_EVERIFY for an invalid encoding */
+size_t b200zk_vk_serialized_size(uint32_t num_fixed, uint32_t num_sigma);
+int32_t b200zk_vk_serialize(const void* fixed_commitments, uint32_t num_fixed, const void* sigma_commitments, uint32_t num_sigma,
+                            uint8_t* out, size_t cap);
+int32_t b200zk_vk_deserialize(const uint8_t* in, size_t len, uint32_t num_sigma, void* fixed_out, uint32_t fixed_cap,
+                              uint32_t* num_fixed, void* sigma_out);
+int32_t b200zk_vk_transcript_repr(const uint32_t* cs_blob, size_t blob_words, const void* fixed_commitments,
+                                  const void* sigma_commitments, void* out_fr);
+
 #ifdef __cplusplus
 }
 #endif
