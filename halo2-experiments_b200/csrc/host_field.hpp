@@ -6,6 +6,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 namespace b200zk {
 namespace host {
@@ -152,6 +153,20 @@ inline HAffine hx_to_affine(const HXyzz& p) {
     HFq zi3 = p.zzz.inv();                              // 1/Z^3
     HFq zi = zi3 * p.zz, zi2 = zi.sqr();                // ZZ/ZZZ = 1/Z ; 1/Z^2 = 1/ZZ
     return {p.x * zi2, p.y * zi3};
+}
+// Curve::batch_normalize: one field inversion for the whole batch (Montgomery's trick)
+inline void hx_batch_to_affine(const HXyzz* in, size_t n, HAffine* out) {
+    std::vector<HFq> pre(n);
+    HFq acc = HFq::one();
+    for (size_t i = 0; i < n; ++i) { pre[i] = acc; if (!hx_is_identity(in[i])) acc = acc * in[i].zzz; }
+    acc = acc.inv();
+    for (size_t i = n; i-- > 0;) {
+        if (hx_is_identity(in[i])) { out[i] = {HFq::zero(), HFq::zero()}; continue; }
+        HFq zi3 = acc * pre[i];
+        acc = acc * in[i].zzz;
+        HFq zi = zi3 * in[i].zz, zi2 = zi.sqr();
+        out[i] = {in[i].x * zi2, in[i].y * zi3};
+    }
 }
 inline HXyzz hx_from_affine(const HAffine& a) {
     if (a.x.is_zero() && a.y.is_zero()) return hx_identity();

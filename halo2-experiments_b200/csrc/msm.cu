@@ -3,6 +3,7 @@
 #include "msm.cuh"
 #include <cmath>
 #include <cstdlib>
+#include <vector>
 
 namespace b200zk {
 
@@ -306,10 +307,12 @@ int32_t msm_run_multi(b200zk_ctx* ctx, const fe_t* const* d_cols, uint32_t ncols
     ZK_CUDA(ctx, cudaGetLastError());
     ZK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, a.window_sums, (size_t)nsums * ncols * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
     ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    std::vector<host::HXyzz> sums(ncols);
     for (uint32_t b = 0; b < ncols; ++b) {
         const char* ws = (const char*)ctx->pinned + (size_t)b * nsums * sizeof(xyzz_t);
-        outs[b] = pre ? msm_finish_bits(ws, s.c) : msm_finish(ws, s.nwin, s.c);
+        sums[b] = pre ? msm_finish_bits(ws, s.c) : msm_finish(ws, s.nwin, s.c);
     }
+    host::hx_batch_to_affine(sums.data(), ncols, outs);          // one inversion per batch of commitments
     return B200ZK_OK;
 }
 

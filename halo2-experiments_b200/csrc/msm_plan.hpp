@@ -51,17 +51,17 @@ inline MsmShape msm_pre_shape(size_t n_table) {
     return s;
 }
 
-// sum_t 2^t * bit_sums[t]  -> affine  (fixed-base mode; c XYZZ points)
-inline host::HAffine msm_finish_bits(const void* bit_sums, uint32_t c) {
+// sum_t 2^t * bit_sums[t]  (fixed-base mode; c XYZZ points)
+inline host::HXyzz msm_finish_bits(const void* bit_sums, uint32_t c) {
     using namespace host;
     const HXyzz* s = (const HXyzz*)bit_sums;
     HXyzz acc = hx_identity();
     for (uint32_t t = c; t-- > 0;) { acc = hx_dbl(acc); acc = hx_add(acc, s[t]); }
-    return hx_to_affine(acc);
+    return acc;
 }
 
-// sum_j 2^(c j) * window_sums[j]  -> affine.  window_sums: nwin XYZZ points (device format).
-inline host::HAffine msm_finish(const void* window_sums, uint32_t nwin, uint32_t c) {
+// sum_j 2^(c j) * window_sums[j].  window_sums: nwin XYZZ points (device format).
+inline host::HXyzz msm_finish(const void* window_sums, uint32_t nwin, uint32_t c) {
     using namespace host;
     const HXyzz* w = (const HXyzz*)window_sums;
     HXyzz acc = hx_identity();
@@ -69,7 +69,7 @@ inline host::HAffine msm_finish(const void* window_sums, uint32_t nwin, uint32_t
         for (uint32_t i = 0; i < c; ++i) acc = hx_dbl(acc);
         acc = hx_add(acc, w[j]);
     }
-    return hx_to_affine(acc);
+    return acc;
 }
 
 }  // namespace b200zk

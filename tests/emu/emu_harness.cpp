@@ -126,7 +126,7 @@ void emu_msm(const fe_t* scalars, const affine_t* bases, uint32_t n, int force_c
     for (uint32_t g = 0; g < (s.nwin << s.log_t); ++g) msm_reduce_thread(a, g);
     std::vector<xyzz_t> smx(8);
     for (uint32_t j = 0; j < s.nwin; ++j) msm_fold_block(a, j, 8, smx.data());
-    host::HAffine r = msm_finish(wsum.data(), s.nwin, s.c);
+    host::HAffine r = host::hx_to_affine(msm_finish(wsum.data(), s.nwin, s.c));
     memcpy(out_affine64, &r, 64);
 }
 
@@ -180,7 +180,7 @@ void emu_msm_pre(const fe_t* scalars, const affine_t* bases, uint32_t n, uint32_
     for (uint32_t g = 0; g < (s.c << s.log_t); ++g) msm_reduce_bits_thread(a, g);
     std::vector<xyzz_t> smx(4);
     for (uint32_t t = 0; t < s.c; ++t) msm_fold_block(a, t, 4, smx.data());
-    host::HAffine r = msm_finish_bits(wsum.data(), s.c);
+    host::HAffine r = host::hx_to_affine(msm_finish_bits(wsum.data(), s.c));
     memcpy(out_affine64, &r, 64);
 }
 
