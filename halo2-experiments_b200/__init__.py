@@ -403,6 +403,12 @@ class ProvingKey:
         self.backend._check(lib().b200zk_pk_vk_commitments(self._h, _p(fixed), _p(sigma)))
         return fixed[: self.cs.num_fixed], sigma[: len(self.cs.permutation)]
 
+    def quotient_muls(self):
+        """{gates, permutation, lookups} field multiplications per row of evaluate_h, and the coset counts."""
+        out = (ctypes.c_uint32 * 5)()
+        self.backend._check(lib().b200zk_pk_quotient_muls(self._h, out))
+        return {"gates": out[0], "permutation": out[1], "lookups": out[2], "cosets": out[3], "lookup_cosets": out[4]}
+
     def last_trace(self):
         """[(label, ms since the call)] at the synchronisation points of the last create_proof (host wall clock)."""
         buf = ctypes.create_string_buffer(4096)

@@ -1250,6 +1250,39 @@ int32_t b200zk_pk_debug_buffer(b200zk_pk* pk, const char* name, void* host_out, 
     return B200ZK_OK;
 }
 
+// Field multiplications evaluate_h executes per row, as launched: out[0] custom gates (one row of every quotient coset),
+// out[1] permutation terms (same rows), out[2] all lookups together (rows of the lk_cosets_n cosets the lookup terms run
+// on), out[3] = q, out[4] = lk_cosets_n.  bench.py's roofline_quotient: work = n * (q * (gates + perm) + CL * lookups).
+int32_t b200zk_pk_quotient_muls(const b200zk_pk* pk, uint32_t out5[5]) {
+    if (!pk || !out5) return B200ZK_EINVAL;
+    std::vector<uint32_t> prog(pk->gates_len + 1);
+    // the programs live on the device; count from a host copy
+    uint32_t total = pk->gates_len;
+    for (auto& lp : pk->lookup_prog) total = std::max(total, lp.first + lp.second);
+    prog.resize(total);
+    if (total && cudaMemcpy(prog.data(), pk->d_prog, total * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return B200ZK_ECUDA;
+    auto count = [&](uint32_t off, uint32_t len) {
+        uint32_t m = 0;
+        for (uint32_t i = off; i < off + len; ++i) {
+            uint32_t op = prog[i] & 0xff;
+            if (op == EX_MUL || op == EX_SCALE || op == EX_FOLD) m += 1;
+            else if (op == EX_GROUP) m += 2;
+        }
+        return m;
+    };
+    out5[0] = count(0, pk->gates_len);
+    uint32_t perm = 0;
+    if (pk->S) {
+        perm = 5 + 2 * (pk->S - 1);
+        for (uint32_t s = 0; s < pk->S; ++s) { uint32_t c0 = s * pk->chunk, c1 = std::min<uint32_t>(c0 + pk->chunk, pk->P); perm += 3 + 4 * (c1 - c0); }
+    }
+    out5[1] = perm;
+    uint32_t lk = 0;
+    for (auto& lp : pk->lookup_prog) lk += count(lp.first, lp.second) + 1 + 13;       // table value product + quot_lookup_row
+    out5[2] = lk; out5[3] = pk->q; out5[4] = pk->lk_cosets_n;
+    return B200ZK_OK;
+}
+
 // host wall clock of the last create_proof at its synchronisation points: "label:ms;label:ms;..." (ms since the call)
 int32_t b200zk_pk_last_trace(const b200zk_pk* pk, char* out, size_t cap) {
     if (!pk || !out || cap == 0) return B200ZK_EINVAL;

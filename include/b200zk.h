@@ -248,6 +248,9 @@ int32_t b200zk_pk_last_phase_ms(const b200zk_pk* pk, float* out7);
  * "label:ms;label:ms;...": advice_commits, lookup_permuted_commits, permutation_commits, lookup_product_commits,
  * quotient_and_h_commits, evaluations, shplonk_h1_commit, end */
 int32_t b200zk_pk_last_trace(const b200zk_pk* pk, char* out, size_t cap);
+/* field multiplications evaluate_h executes per row: {custom gates, permutation terms, all lookups, q, lookup cosets}
+ * (the work model of bench.py's roofline_quotient) */
+int32_t b200zk_pk_quotient_muls(const b200zk_pk* pk, uint32_t out5[5]);
 
 /* ---- plonk::keygen_vk / plonk::verify_proof (src/plonk/keygen.rs, src/plonk/verifier.rs,
  *      src/poly/kzg/multiopen/shplonk/verifier.rs, src/poly/kzg/strategy.rs) ----------------------
