@@ -446,6 +446,22 @@ class Group:
             for b in self.backends:
                 b._ctx = None
 
+    def best_multiexp(self, coeffs, bases):
+        """arithmetic::best_multiexp split by point range over the group's GPUs (partial sums combined in the library)."""
+        coeffs = _fr(coeffs)
+        bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+        if coeffs.shape[0] != bases.shape[0]:
+            raise B200zkError("best_multiexp: coeffs.len() != bases.len()")
+        out = np.zeros(12, dtype=np.uint64)
+        self.backends[0]._check(lib().b200zk_group_msm(self._h, _p(coeffs), _p(bases), ctypes.c_size_t(coeffs.shape[0]), _p(out)))
+        return out
+
+    def best_fft(self, a, omega, log_n):
+        """arithmetic::best_fft, four-step over the group's GPUs with the exchange fused into the column-step kernel."""
+        a = np.array(_fr(a, 1 << log_n))
+        self.backends[0]._check(lib().b200zk_group_fft(self._h, _p(a), _p(_fr(omega, 1)), ctypes.c_uint32(log_n)))
+        return a
+
     def create_proof(self, pks, advice_columns, instances, rng_wide, transcript_repr):
         """One plonk::create_proof over all ranks from host inputs (pks[r] built on backends[r])."""
         pk0 = pks[0]

@@ -7,7 +7,9 @@
 #include <condition_variable>
 #include <memory>
 #include <mutex>
+#include <algorithm>
 #include <new>
+#include <thread>
 #include <vector>
 
 namespace b200zk {
@@ -279,6 +281,96 @@ b200zk_ctx* b200zk_group_ctx(b200zk_group* g, uint32_t rank) { return g && rank 
 int32_t b200zk_group_reset(b200zk_group* g) {
     if (!g) return B200ZK_EINVAL;
     g->state->reset();
+    return B200ZK_OK;
+}
+
+// ---- arithmetic::best_multiexp / best_fft over the GPUs of a group (host buffers in and out) -----------------------
+// best_multiexp: rank r multiplies the point range [len r / G, len (r + 1) / G) on its device (one thread per rank:
+// upload of its slices, Pippenger, 64-byte result), the G partial sums are added on the host.
+int32_t b200zk_group_msm(b200zk_group* g, const void* coeffs, const void* bases, size_t len, void* out_g1) {
+    if (!g || !out_g1 || (len && (!coeffs || !bases))) return B200ZK_EINVAL;
+    const uint32_t G = (uint32_t)g->ctxs.size();
+    std::vector<int32_t> rcs(G, B200ZK_OK);
+    std::vector<uint64_t> parts((size_t)G * 12, 0);
+    auto body = [&](uint32_t r) {
+        const size_t lo = len * r / G, hi = len * (r + 1) / G;
+        rcs[r] = b200zk_msm(g->ctxs[r], (const char*)coeffs + lo * 32, (const char*)bases + lo * 64, hi - lo, parts.data() + (size_t)r * 12);
+    };
+    std::vector<std::thread> th;
+    for (uint32_t r = 1; r < G; ++r) th.emplace_back(body, r);
+    body(0);
+    for (auto& t : th) t.join();
+    for (uint32_t r = 0; r < G; ++r) if (rcs[r] != B200ZK_OK) { g->ctxs[0]->err = g->ctxs[r]->err; return rcs[r]; }
+    return b200zk_g1_sum(parts.data(), G, out_g1);
+}
+
+namespace b200zk {
+// rows [R/G][C] (k_c fastest) -> [C][R/G]: the transposed block is a strided slice of the natural-order output
+__global__ void group_fft_transpose_kernel(const fe_t* in, fe_t* out, uint32_t rows, uint32_t cols) {
+    __shared__ fe_t tile[8][9];
+    const uint32_t c0 = blockIdx.x * 8, r0 = blockIdx.y * 8;
+    uint32_t c = c0 + threadIdx.x, r = r0 + threadIdx.y;
+    if (r < rows && c < cols) tile[threadIdx.y][threadIdx.x] = in[(size_t)r * cols + c];
+    __syncthreads();
+    c = c0 + threadIdx.y; r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][threadIdx.y];
+}
+}  // namespace b200zk
+
+// best_fft of 2^log_n elements as a four-step transform over the group's devices (G a power of two <= 8): rank r uploads
+// its block of C / G columns, runs the R-point column transforms with the exchange fused into the kernel's store phase
+// (every transformed row goes straight into its owner's buffer over NVLink), then the C-point row transforms of the R / G
+// rows it received, and writes them to their natural-order positions X[k_r + R k_c] of the host array.  Small sizes
+// (log_n < 16) and a group of one run on rank 0.
+int32_t b200zk_group_fft(b200zk_group* g, void* a, const void* omega, uint32_t log_n) {
+    if (!g || !a || !omega) return B200ZK_EINVAL;
+    const uint32_t G = (uint32_t)g->ctxs.size();
+    if (G == 1 || log_n < 16 || (G & (G - 1)) || G > 8) return b200zk_fft(g->ctxs[0], a, omega, log_n);
+    uint32_t lw = 0; while ((1u << lw) < G) ++lw;
+    const uint32_t log_r = std::min<uint32_t>(10, log_n / 2), log_c = log_n - log_r;
+    const size_t R = (size_t)1 << log_r, C = (size_t)1 << log_c, cg = C / G, rg = R / G;
+    const host::HFr w = host::HFr::from_limbs(omega);
+    const host::HFr wc = w.pow_u64(R);                                    // omega^R: root of order C for the row step
+    std::vector<fe_t*> blocks(G, nullptr), rows(G, nullptr), rows_t(G, nullptr);
+    std::vector<int32_t> rcs(G, B200ZK_OK);
+    g->state->reset();
+    // phase 0: allocate (all pointers must exist before any rank scatters into its peers)
+    for (uint32_t r = 0; r < G; ++r) {
+        cudaSetDevice(g->ctxs[r]->device);
+        if (cudaMalloc(&blocks[r], R * cg * sizeof(fe_t)) != cudaSuccess || cudaMalloc(&rows[r], rg * C * sizeof(fe_t)) != cudaSuccess ||
+            cudaMalloc(&rows_t[r], rg * C * sizeof(fe_t)) != cudaSuccess) rcs[r] = B200ZK_ENOMEM;
+    }
+    bool ok = true;
+    for (uint32_t r = 0; r < G; ++r) ok &= rcs[r] == B200ZK_OK;
+    auto body = [&](uint32_t r) {
+        b200zk_ctx* ctx = g->ctxs[r];
+        cudaSetDevice(ctx->device);
+        cudaStream_t st = ctx->stream;
+        auto step = [&](cudaError_t e) { if (e != cudaSuccess && rcs[r] == B200ZK_OK) rcs[r] = fail(ctx, B200ZK_ECUDA, "group_fft", cudaGetErrorString(e)); };
+        // column block: input element (row i, column c) sits at a[i * C + c]
+        step(cudaMemcpy2DAsync(blocks[r], cg * sizeof(fe_t), (const char*)a + (size_t)r * cg * sizeof(fe_t), C * sizeof(fe_t), cg * sizeof(fe_t), R,
+                               cudaMemcpyHostToDevice, st));
+        if (rcs[r] == B200ZK_OK) rcs[r] = ntt_colstep_run(ctx, blocks[r], log_r, log_c - lw, (uint32_t)(r * cg), w, log_n, rows.data(), G);
+        step(cudaStreamSynchronize(st));
+        if (!g->state->barrier()) { if (rcs[r] == B200ZK_OK) rcs[r] = B200ZK_ECUDA; return; }      // every rank's rows have arrived
+        if (rcs[r] == B200ZK_OK) rcs[r] = ntt_rows_run(ctx, rows[r], (uint32_t)rg, wc, log_c);
+        dim3 grid((unsigned)((C + 7) / 8), (unsigned)((rg + 7) / 8)), block(8, 8);
+        group_fft_transpose_kernel<<<grid, block, 0, st>>>(rows[r], rows_t[r], (uint32_t)rg, (uint32_t)C);
+        ctx->launches++;
+        // rows_t[k_c][k_r local] -> a[k_r + R k_c]
+        step(cudaMemcpy2DAsync((char*)a + (size_t)r * rg * sizeof(fe_t), R * sizeof(fe_t), rows_t[r], rg * sizeof(fe_t), rg * sizeof(fe_t), C,
+                               cudaMemcpyDeviceToHost, st));
+        step(cudaStreamSynchronize(st));
+        if (rcs[r] != B200ZK_OK) g->state->abort_all();
+    };
+    if (ok) {
+        std::vector<std::thread> th;
+        for (uint32_t r = 1; r < G; ++r) th.emplace_back(body, r);
+        body(0);
+        for (auto& t : th) t.join();
+    }
+    for (uint32_t r = 0; r < G; ++r) { cudaSetDevice(g->ctxs[r]->device); cudaFree(blocks[r]); cudaFree(rows[r]); cudaFree(rows_t[r]); }
+    for (uint32_t r = 0; r < G; ++r) if (rcs[r] != B200ZK_OK) { g->ctxs[0]->err = g->ctxs[r]->err; return rcs[r]; }
     return B200ZK_OK;
 }
 

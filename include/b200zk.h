@@ -229,6 +229,11 @@ void b200zk_group_destroy(b200zk_group* g);            /* destroys the group's c
 uint32_t b200zk_group_size(const b200zk_group* g);
 b200zk_ctx* b200zk_group_ctx(b200zk_group* g, uint32_t rank);
 int32_t b200zk_group_reset(b200zk_group* g);           /* after a failed group call */
+/* arithmetic::best_multiexp / best_fft over the group's GPUs, host buffers in and out: the multiexp is split by point
+ * range (partial sums added inside the call); the fft runs four-step with the exchange fused into the column-step
+ * kernel (NVLink peer stores) when the group is 2, 4 or 8 devices and log_n >= 16, on rank 0 otherwise. */
+int32_t b200zk_group_msm(b200zk_group* g, const void* coeffs, const void* bases, size_t len, void* out_g1);
+int32_t b200zk_group_fft(b200zk_group* g, void* a, const void* omega, uint32_t log_n);
 /* pks[r] = the proving key built on b200zk_group_ctx(g, r) */
 int32_t b200zk_group_create_proof(b200zk_group* g, b200zk_pk* const* pks, const void* const* advice_columns,
                                   const void* const* instance_columns, const uint32_t* instance_lens, const void* rng_wide,

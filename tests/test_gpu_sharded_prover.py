@@ -101,3 +101,26 @@ def test_sharded_lookup_failure_is_collective(zk, orc):
             group.create_proof(pks, job.advice, inst, wide, orc.ints_to_mont([job.transcript_repr])[0])
     finally:
         group.close()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_group_best_multiexp_and_best_fft(zk, backend, orc, world):
+    """b200zk_group_msm / b200zk_group_fft: one best_multiexp by point range and one best_fft four-step (exchange fused into
+    the column-step kernel) over the ranks of a group, host buffers in and out, against the oracle."""
+    from oracle import pyref
+    n = (1 << 14) + 37
+    g, _ = orc.params_setup(15, orc.random_fr(1, 1234)[0], with_lagrange=False)
+    coeffs = orc.random_fr(n, 77)
+    want = orc.g1_batch_normalize(orc.best_multiexp(coeffs, g[:n]))[0]
+    group = zk.Group(_devices(world))
+    try:
+        assert np.array_equal(group.best_multiexp(coeffs, g[:n])[:8], want)
+        for k in (16, 17):
+            a = orc.random_fr(1 << k, 90 + k)
+            w = orc.ints_to_mont([pyref.omega_for_k(k)])[0]
+            assert np.array_equal(group.best_fft(a, w, k), orc.best_fft(a, w, k)), f"k={k}"
+        a = orc.random_fr(1 << 10, 5)                                      # below the four-step threshold: rank 0 alone
+        w = orc.ints_to_mont([pyref.omega_for_k(10)])[0]
+        assert np.array_equal(group.best_fft(a, w, 10), orc.best_fft(a, w, 10))
+    finally:
+        group.close()
