@@ -208,7 +208,7 @@ void b200zk_ctx_destroy(b200zk_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && ctx->comm_owned) delete ctx->comm;
     ctx->comm = nullptr;
-    for (auto& kv : ctx->ntt_plans) { cudaFree(kv.second.roots); cudaFree(kv.second.tw_lo); cudaFree(kv.second.tw_hi); cudaFree(kv.second.tw_full); }
+    for (auto& kv : ctx->ntt_plans) { cudaFree(kv.second.roots); cudaFree(kv.second.tw_lo); cudaFree(kv.second.tw_hi); cudaFree(kv.second.tw_full); cudaFree(kv.second.roots_s); cudaFree(kv.second.tw_full_s); }
     for (Workspace* w : {&ctx->ntt_scratch, &ctx->ntt_scratch2, &ctx->msm_ws, &ctx->msm_ws2, &ctx->lookup_ws, &ctx->io_a, &ctx->io_b, &ctx->poly_ws, &ctx->poly_heads, &ctx->poly_batch, &ctx->setup_ws}) if (w->p) cudaFree(w->p);
     if (ctx->d_gen_table) cudaFree(ctx->d_gen_table);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -23,7 +23,11 @@ struct NttPlan {
     fe_t* tw_hi = nullptr;
     fe_t* tw_full = nullptr;    // omega^E for all E < N (multi-pass plans up to 2^24)
     bool warp = false;          // passes run on ntt_warp_pass_kernel (ntt_warp.cuh)
+    struct fe2_t* roots_s = nullptr;    // {plain value, floor(value * 2^256 / r)} forms of roots / tw_full for Field::mul_shoup
+    struct fe2_t* tw_full_s = nullptr;  // (warp plans only; null = CIOS multiplications against the Montgomery tables)
 };
+
+struct fe2_t;
 
 struct Workspace {
     void* p = nullptr;

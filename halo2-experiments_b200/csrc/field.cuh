@@ -176,6 +176,92 @@ template <class C> struct Field {
     }
     ZK_D static T sqr(const T& a) { return mul(a, a); }
 
+    // ---- multiplication by a constant with a precomputed quotient (Shoup / Barrett with a fixed operand) --------------
+    // For a constant w < p stored with wq = floor(w * 2^256 / p):   x * w mod p  =  x*w - q*p  (mod 2^256),  q = floor(x * wq / 2^256),
+    // which lies in [0, 2p); with q taken from the columns >= 6 of the 16-limb product only (the dropped low columns sum to
+    // less than 2^256, so the estimate is q or q - 1) it lies in [0, 3p) < 2^256, and two conditional subtractions finish.
+    // When x is in Montgomery form and w is the PLAIN value of the constant, the result is the Montgomery form of the
+    // product — no domain change — so this replaces mul(x, w_mont) wherever the second operand comes from a table (every
+    // multiplication of an NTT: butterfly roots and inter-pass twiddles).  Cost: 43 (high part of x*wq) + 28 (low half of
+    // x*w) + 28 (low half of q*p) wide multiply-adds + 16 low-half multiplies, against 128 + 8 for the CIOS product.
+    // Same even/odd accumulator scheme as `round`: products landing on even limb positions go to one accumulator, odd ones
+    // to the other, each row is one carry chain per accumulator, so every (lo, hi) pair is one IMAD.WIDE.U32 with carry.
+    //
+    // chain: acc[off + j], acc[off + j + 1] += a[j] * b for j = j0, j0 + 2, ... < jn;  lo_last: the last product contributes
+    // its low half only (its high half falls outside the kept window);  carry_out: the carry leaving the last pair is added
+    // to the limb above it (which no earlier row of the same accumulator has touched).
+    ZK_D static void mad_chain(uint32_t* acc, int off, const uint32_t* a, uint32_t b, int j0, int jn, bool lo_last, bool carry_out) {
+        if (j0 >= jn) return;
+        int jl = j0;
+#pragma unroll
+        for (int j = j0; j < jn; j += 2) {
+            const bool first = j == j0, last = j + 2 >= jn;
+            uint32_t* q = acc + off + j;
+            if (last && lo_last) {
+                q[0] = first ? ptx::mad_lo(a[j], b, q[0]) : ptx::madc_lo(a[j], b, q[0]);
+            } else {
+                q[0] = first ? ptx::mad_lo_cc(a[j], b, q[0]) : ptx::madc_lo_cc(a[j], b, q[0]);
+                q[1] = (last && !carry_out) ? ptx::madc_hi(a[j], b, q[1]) : ptx::madc_hi_cc(a[j], b, q[1]);
+            }
+            jl = j;
+        }
+        if (carry_out && !lo_last) acc[off + jl + 2] = ptx::addc(acc[off + jl + 2], 0);
+    }
+    // low 8 limbs of a * b (a, b: 8 limbs)
+    ZK_D static void mul_low(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+        uint32_t E[8], O[9];                                   // E: positions 0..7 ; O[k]: position k (1..8; O[0] unused)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) E[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) O[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            // product (i, j) sits at position i + j <= 7;  even position -> E, odd -> O
+            const int je = i & 1, jo = (i & 1) ^ 1;            // first j of each parity class
+            mad_chain(E, i, a, b[i], je, 8 - i, false, false);              // ends at pair (6, 7): carry out of the window dropped
+            mad_chain(O, i, a, b[i], jo, 8 - i, true, false);               // ends with the low half at position 7
+        }
+        r[0] = E[0];
+        r[1] = ptx::add_cc(E[1], O[1]);
+#pragma unroll
+        for (int k = 2; k < 7; ++k) r[k] = ptx::addc_cc(E[k], O[k]);
+        r[7] = ptx::addc(E[7], O[7]);
+    }
+    // limbs 8..15 of the part of x * b made of the products at positions >= 6 (see above): floor(x*b / 2^256) or one less
+    ZK_D static void mul_high_approx(uint32_t* r, const uint32_t* x, const uint32_t* b) {
+        uint32_t E[12], O[12];                                 // E[k]: position 6 + k (pairs (6,7) .. (14,15)); O[k]: position 7 + k
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { E[i] = 0; O[i] = 0; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int jmin = i >= 6 ? 0 : 6 - i;               // products with i + j >= 6
+            const int je = ((jmin + i) & 1) ? jmin + 1 : jmin; // first j with i + j even
+            const int jo = ((jmin + i) & 1) ? jmin : jmin + 1; // first j with i + j odd
+            mad_chain(E, i - 6, x, b[i], je, 8, false, true);
+            mad_chain(O, i - 7, x, b[i], jo, 8, false, true);
+        }
+        (void)ptx::add_cc(E[1], O[0]);                         // position 7: only its carry matters
+        r[0] = ptx::addc_cc(E[2], O[1]);
+#pragma unroll
+        for (int k = 1; k < 7; ++k) r[k] = ptx::addc_cc(E[2 + k], O[1 + k]);
+        r[7] = ptx::addc(E[9], O[8]);
+    }
+    ZK_D static T mul_shoup(const T& x, const T& w, const T& wq) {
+        const uint32_t P[8] = {C::p(0), C::p(1), C::p(2), C::p(3), C::p(4), C::p(5), C::p(6), C::p(7)};
+        uint32_t q[8], t1[8], t2[8];
+        mul_high_approx(q, x.l, wq.l);
+        mul_low(t1, P, q);                                     // q * p mod 2^256 (p's limbs are immediates)
+        mul_low(t2, x.l, w.l);                                 // x * w mod 2^256
+        T r;
+        r.l[0] = ptx::sub_cc(t2[0], t1[0]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) r.l[i] = ptx::subc_cc(t2[i], t1[i]);
+        r.l[7] = ptx::subc(t2[7], t1[7]);
+        reduce_once(r);
+        reduce_once(r);
+        return r;
+    }
+
     ZK_D static T from_mont(const T& a) {                // a * 1 * R^-1 : canonical integer
         T o = zero(); o.l[0] = 1; return mul(a, o);
     }

@@ -24,21 +24,30 @@ __global__ void __launch_bounds__(NTT_THREADS, 1) ntt_pass_kernel(const NttPassA
 // SPARSE: first pass of lagrange_to_coeff (ctx->ntt_sparse_hint): all-zero tiles skip the arithmetic.  The witness
 // columns of a padded circuit are zero outside the used rows and the blinding rows, and a first-pass tile gathers
 // rows at stride n / 128: 262 of 8192 tiles are live for the Merkle Sum Tree circuit at k = 20.
-template <int WPB, int MINB, bool SPARSE>
+// SHOUP: butterfly and inter-pass twiddle multiplications through Field::mul_shoup against the {w, wq} tables of the
+// plan (a.roots_s / a.tw_full_s): 99 wide + 16 low multiply-adds instead of 128 + 8 per multiplication.
+template <int WPB, int MINB, bool SPARSE, bool SHOUP>
 __global__ void __launch_bounds__(32 * WPB, MINB) ntt_warp_pass_kernel(const NttPassArgs a, uint32_t ntiles) {
     __shared__ half_t sm[WPB][256];
     const uint32_t w = threadIdx.x >> 5, wid = blockIdx.x * WPB + w;
-    if (wid < ntiles) ntt_pass_warp<SPARSE>(a, wid, threadIdx.x & 31, sm[w]);
+    if (wid < ntiles) ntt_pass_warp<SPARSE, SHOUP>(a, wid, threadIdx.x & 31, sm[w]);
 }
 template <int WPB, int MINB> static void ntt_warp_launch_t(const NttPassArgs& a, uint32_t ntiles, bool sparse, cudaStream_t st) {
     const uint32_t grid = (ntiles + WPB - 1) / WPB;
-    if (sparse) ntt_warp_pass_kernel<WPB, MINB, true><<<grid, 32 * WPB, 0, st>>>(a, ntiles);
-    else ntt_warp_pass_kernel<WPB, MINB, false><<<grid, 32 * WPB, 0, st>>>(a, ntiles);
+    const bool shoup = a.roots_s != nullptr && (a.is_last || a.tw_full_s != nullptr);
+    if (shoup) {
+        if (sparse) ntt_warp_pass_kernel<WPB, MINB, true, true><<<grid, 32 * WPB, 0, st>>>(a, ntiles);
+        else ntt_warp_pass_kernel<WPB, MINB, false, true><<<grid, 32 * WPB, 0, st>>>(a, ntiles);
+    } else {
+        if (sparse) ntt_warp_pass_kernel<WPB, MINB, true, false><<<grid, 32 * WPB, 0, st>>>(a, ntiles);
+        else ntt_warp_pass_kernel<WPB, MINB, false, false><<<grid, 32 * WPB, 0, st>>>(a, ntiles);
+    }
 }
 static void ntt_warp_launch(b200zk_ctx* ctx, const NttPassArgs& a, uint32_t ntiles, bool sparse) {
     static const int cfg = [] { const char* e = getenv("B200ZK_NTT_WARP_CFG"); return e ? atoi(e) : NTT_WARP_CFG_DEFAULT; }();
     if (cfg == 1) ntt_warp_launch_t<4, 7>(a, ntiles, sparse, ctx->stream);
     else if (cfg == 2) ntt_warp_launch_t<7, 4>(a, ntiles, sparse, ctx->stream);
+    else if (cfg == 3) ntt_warp_launch_t<4, 8>(a, ntiles, sparse, ctx->stream);
     else ntt_warp_launch_t<8, 3>(a, ntiles, sparse, ctx->stream);
 }
 
@@ -51,6 +60,34 @@ __global__ void fr_scale_periodic_kernel(fe_t* a, size_t n, const fe_t* m, uint3
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) { fe_t x = a[i], y = m[i & (period - 1)]; a[i] = Fr::mul(x, y); }
+}
+
+// {w, wq} records from a Montgomery-form table: w = the plain value, wq = floor(w * 2^256 / r) by 256 steps of
+// shift-and-subtract long division (plan build time only)
+__global__ void ntt_shoup_table_kernel(const fe_t* mont, fe2_t* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe_t w = Fr::from_mont(mont[i]);
+    fe_t rem = w, q = Fr::zero();
+    for (int b = 0; b < 256; ++b) {
+        // rem <- 2 rem (rem < r < 2^254: no overflow); q <- 2 q + [rem >= r]
+        uint32_t carry = 0;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) { uint32_t v = rem.l[l]; rem.l[l] = (v << 1) | carry; carry = v >> 31; }
+        carry = 0;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) { uint32_t v = q.l[l]; q.l[l] = (v << 1) | carry; carry = v >> 31; }
+        bool ge = true;
+        for (int l = 7; l >= 0; --l) { uint32_t pl = FrCfg::p(l); if (rem.l[l] != pl) { ge = rem.l[l] > pl; break; } }
+        if (ge) {
+            uint32_t borrow = 0;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) { uint64_t d = (uint64_t)rem.l[l] - FrCfg::p(l) - borrow; rem.l[l] = (uint32_t)d; borrow = (uint32_t)(d >> 63); }
+            q.l[0] |= 1u;
+        }
+    }
+    fe2_t r; r.w = w; r.wq = q;
+    out[i] = r;
 }
 
 __global__ void ntt_tw_full_kernel(fe_t* out, size_t n, const fe_t* lo, const fe_t* hi, uint32_t bits) {
@@ -100,6 +137,21 @@ static int32_t build_plan(b200zk_ctx* ctx, uint32_t log_n, const host::HFr& omeg
             ntt_tw_full_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(plan.tw_full, N, plan.tw_lo, plan.tw_hi, s.tw_lo_bits);
             ctx->launches++;
         } else { plan.tw_full = nullptr; cudaGetLastError(); }
+    }
+    // constant-operand tables for the warp-level kernel (B200ZK_NTT_SHOUP=0 keeps the CIOS multiplications)
+    const char* es = getenv("B200ZK_NTT_SHOUP");
+    if (plan.warp && !(es && es[0] == '0') && (s.npass == 1 || plan.tw_full)) {
+        size_t N = (size_t)1 << log_n;
+        if (cudaMalloc(&plan.roots_s, n_roots * sizeof(fe2_t)) == cudaSuccess) {
+            ntt_shoup_table_kernel<<<(unsigned)((n_roots + 127) / 128), 128, 0, ctx->stream>>>(plan.roots, plan.roots_s, n_roots);
+            ctx->launches++;
+            if (s.npass > 1) {
+                if (cudaMalloc(&plan.tw_full_s, N * sizeof(fe2_t)) == cudaSuccess) {
+                    ntt_shoup_table_kernel<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(plan.tw_full, plan.tw_full_s, N);
+                    ctx->launches++;
+                } else { cudaGetLastError(); cudaFree(plan.roots_s); plan.roots_s = nullptr; plan.tw_full_s = nullptr; }
+            }
+        } else { plan.roots_s = nullptr; cudaGetLastError(); }
     }
     ZK_CUDA(ctx, cudaGetLastError());
     return B200ZK_OK;
@@ -163,6 +215,7 @@ static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, f
         a.tw_lo = plan.tw_lo; a.tw_hi = plan.tw_hi; a.tw_lo_bits = s.tw_lo_bits;
         a.tw_shift = log_n - q.log_m - q.log_l; a.l_offset = 0;
         a.tw_full = plan.tw_full;
+        a.roots_s = plan.roots_s; a.tw_full_s = plan.tw_full_s;
         size_t smem = sizeof(fe_t) << (q.log_m + q.log_tw);
         uint32_t tile = 1u << (q.log_m + q.log_tw);
         uint32_t threads = tile / 2 < NTT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : NTT_THREADS;

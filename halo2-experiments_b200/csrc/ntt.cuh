@@ -26,6 +26,8 @@ namespace b200zk {
 
 struct alignas(16) half_t { uint32_t v[4]; };
 
+struct alignas(64) fe2_t { fe_t w, wq; };        // a constant and its precomputed quotient, one 64-byte record
+
 struct NttPassArgs {
     const fe_t* in;
     fe_t* out;
@@ -55,6 +57,10 @@ struct NttPassArgs {
     // [k mod rows_per_rank][global column]; no staging buffer, no separate exchange.
     uint32_t scatter, log_rows_per_rank, log_c_total;
     fe_t* peers[8];
+    // Constant-operand (Shoup) form of the two twiddle tables — {plain value, floor(value * 2^256 / r)} records, see
+    // Field::mul_shoup — used by the warp-level kernel when non-null: every multiplication of a pass is by a table entry.
+    const struct fe2_t* roots_s;
+    const struct fe2_t* tw_full_s;
 };
 
 ZK_D uint32_t bitrev32(uint32_t v, uint32_t bits) {

@@ -41,7 +41,12 @@ template <int LAYOUT> __device__ __forceinline__ void ntt_warp_get(const half_t*
 #pragma unroll
     for (uint32_t e = 0; e < 4; ++e) x[e] = tile_ld(sm, 128, ntt_warp_slot(ntt_warp_u<LAYOUT>(lane, e)));
 }
-template <int LAYOUT, int B, int EB>
+// d * (table entry ix): CIOS against the Montgomery-form table, or the constant-operand product against the {w, wq} table
+template <bool SHOUP> __device__ __forceinline__ fe_t ntt_warp_mul_root(const NttPassArgs& a, const fe_t& d, size_t ix) {
+    if (SHOUP) { const fe2_t t = a.roots_s[ix]; return Fr::mul_shoup(d, t.w, t.wq); }
+    return Fr::mul(d, a.roots[ix]);
+}
+template <int LAYOUT, int B, int EB, bool SHOUP>
 __device__ __forceinline__ void ntt_warp_stage(const NttPassArgs& a, uint32_t lane, uint32_t log_tw, fe_t (&x)[4]) {
     if ((uint32_t)B < log_tw) return;
     const uint32_t lh = (uint32_t)B - log_tw;
@@ -51,14 +56,14 @@ __device__ __forceinline__ void ntt_warp_stage(const NttPassArgs& a, uint32_t la
         const uint32_t e1 = e0 | (1u << EB);
         const uint32_t j = (ntt_warp_u<LAYOUT>(lane, e0) >> log_tw) & ((1u << lh) - 1u);
         fe_t s = Fr::add(x[e0], x[e1]), d = Fr::sub(x[e0], x[e1]);
-        if (j != 0) d = Fr::mul(d, a.roots[(size_t)j << (a.log_roots - lh - 1)]);
+        if (j != 0) d = ntt_warp_mul_root<SHOUP>(a, d, (size_t)j << (a.log_roots - lh - 1));
         x[e0] = s; x[e1] = d;
     }
 }
 
 // SKIP: test the tile for all-zero inputs (first pass of an iNTT of Lagrange columns, see below); the dense
 // instantiation carries none of it.
-template <bool SKIP>
+template <bool SKIP, bool SHOUP>
 __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid, uint32_t lane, half_t* sm) {
     const uint32_t log_tw = NTT_WARP_TILE_LOG - a.log_m, TW = 1u << log_tw;
     uint32_t h = 0, l0 = 0, k1_0 = 0, rho_mid = 0;
@@ -102,18 +107,18 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
             if (a.pre_tab) x[e] = Fr::mul(x[e], a.pre_tab[g]);
         }
     }
-    ntt_warp_stage<0, 6, 1>(a, lane, log_tw, x);
-    ntt_warp_stage<0, 5, 0>(a, lane, log_tw, x);
+    ntt_warp_stage<0, 6, 1, SHOUP>(a, lane, log_tw, x);
+    ntt_warp_stage<0, 5, 0, SHOUP>(a, lane, log_tw, x);
     ntt_warp_put<0>(sm, lane, x);
     __syncwarp();
     ntt_warp_get<1>(sm, lane, x);
-    ntt_warp_stage<1, 4, 1>(a, lane, log_tw, x);
-    ntt_warp_stage<1, 3, 0>(a, lane, log_tw, x);
+    ntt_warp_stage<1, 4, 1, SHOUP>(a, lane, log_tw, x);
+    ntt_warp_stage<1, 3, 0, SHOUP>(a, lane, log_tw, x);
     __syncwarp();
     ntt_warp_put<1>(sm, lane, x);
     __syncwarp();
     ntt_warp_get<2>(sm, lane, x);
-    ntt_warp_stage<2, 2, 1>(a, lane, log_tw, x);
+    ntt_warp_stage<2, 2, 1, SHOUP>(a, lane, log_tw, x);
     if (log_tw == 0) {
         // Stage 1 of a 128-point tile: the twiddle index is the lane's parity, so even lanes have two trivial
         // butterflies and odd lanes two multiplications by w_4 — executed as written, the warp would spend two
@@ -124,12 +129,12 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
         fe_t y;
 #pragma unroll
         for (int i = 0; i < 8; ++i) y.l[i] = __shfl_xor_sync(0xffffffffu, d1.l[i], 1);
-        fe_t prod = Fr::mul(odd ? d0 : y, a.roots[(size_t)1 << (a.log_roots - 2)]);
+        fe_t prod = ntt_warp_mul_root<SHOUP>(a, odd ? d0 : y, (size_t)1 << (a.log_roots - 2));
 #pragma unroll
         for (int i = 0; i < 8; ++i) y.l[i] = __shfl_xor_sync(0xffffffffu, prod.l[i], 1);
         x[0] = s0; x[1] = odd ? prod : d0; x[2] = s1; x[3] = odd ? y : d1;
     } else {
-        ntt_warp_stage<2, 1, 0>(a, lane, log_tw, x);
+        ntt_warp_stage<2, 1, 0, SHOUP>(a, lane, log_tw, x);
     }
     if (log_tw == 0) {                                         // bit 0 carries a point: twiddle-free stage across lane pairs
         const bool odd = lane & 1u;
@@ -153,7 +158,10 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
             uint32_t l = l0 + c;
             g = ((size_t)h << (a.log_m + a.log_l)) + ((size_t)k << a.log_l) + l;
             uint64_t E = ((uint64_t)(l + a.l_offset) * k) << a.tw_shift;
-            if (E && live) v = Fr::mul(v, ntt_twiddle(a, (uint32_t)E));
+            if (E && live) {
+                if (SHOUP) { const fe2_t t = a.tw_full_s[(uint32_t)E]; v = Fr::mul_shoup(v, t.w, t.wq); }
+                else v = Fr::mul(v, ntt_twiddle(a, (uint32_t)E));
+            }
         } else {
             g = (size_t)(k1_0 + c) + ((size_t)rho_mid << a.log_m1) + ((size_t)k << (a.log_m1 + a.log_mid));
             if (a.use_post && live) v = Fr::mul(v, a.post[g % 3]);

@@ -44,6 +44,11 @@ void emu_field_op(int which, int op, const fe_t* a, const fe_t* b, fe_t* out, si
     }
 }
 
+// x * w mod p through the constant-operand multiplier: w plain, wq = floor(w * 2^256 / p)
+void emu_mul_shoup(int which, const fe_t* x, const fe_t* w, const fe_t* wq, fe_t* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) out[i] = which == 0 ? Fr::mul_shoup(x[i], w[i], wq[i]) : Fq::mul_shoup(x[i], w[i], wq[i]);
+}
+
 void emu_field_consts(int which, fe_t* one, fe_t* r2) {
     if (which == 0) { *one = Fr::one(); *r2 = Fr::r2(); } else { *one = Fq::one(); *r2 = Fq::r2(); }
 }
