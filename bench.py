@@ -434,16 +434,19 @@ def run_gpu(args):
                             "single": {"kernel": f"one 2^{k} transform = {ntt_passes(k)} launches (b200zk_fft_dev)", "ms_per_launch_group": ms_ntt,
                                        "achieved": ach / 1e12, "frac": ach / IMAD_WIDE_PEAK,
                                        "hbm_view": {"achieved": hbm, "frac": hbm / peaks["hbm_gbs"], "algorithmic_bytes": 64 * n}},
-                            "note": imad_note + "; work = non-trivial butterfly and inter-pass twiddle multiplications x 132 (DESIGN.md §4)"}
+                            "note": imad_note + "; work = non-trivial butterfly and inter-pass twiddle multiplications x 132, the cost of a generic (CIOS) field multiplication "
+                                    "— SURVEY 8(d)'s unit; the kernel's own constant-operand multiplier issues 99 wide + 16 low multiply-adds per product (DESIGN.md §4)"}
         # evaluate_h: multiplications per row as launched (b200zk_pk_quotient_muls) against the measured field-multiplication rate
         qm = pk.quotient_muls()
-        muls = n * (qm["cosets"] * (qm["gates"] + qm["permutation"]) + qm["lookup_cosets"] * qm["lookups"])
-        line["roofline_quotient"] = {"bound": "imad", "kernel": "expr_kernel + quot_perm_a/b + quot_lookup (evaluate_h on the quotient cosets)",
-                                     "muls_per_row": qm, "field_muls": muls, "ms": ph["quotient"],
-                                     "achieved": muls * 132 / (ph["quotient"] / 1e3) / 1e12 if ph["quotient"] else None, "peak": IMAD_WIDE_PEAK / 1e12,
-                                     "unit": "T IMAD.WIDE.U32/s", "frac": muls * 132 / (ph["quotient"] / 1e3) / IMAD_WIDE_PEAK if ph["quotient"] else None,
-                                     "share_of_step": ph["quotient"] / max(sum(ph.values()), 1e-9),
-                                     "note": "rank 0's cosets only when the proof is sharded" if sharded_proof else ""}
+        if sharded_proof:                                         # rank 0 evaluates only its own cosets: the count below would not describe its kernels
+            qm = None
+        if qm is not None:
+            muls = n * (qm["cosets"] * (qm["gates"] + qm["permutation"]) + qm["lookup_cosets"] * qm["lookups"])
+            line["roofline_quotient"] = {"bound": "imad", "kernel": "expr_kernel + quot_perm_a/b + quot_lookup (evaluate_h on the quotient cosets)",
+                                         "muls_per_row": qm, "field_muls": muls, "ms": ph["quotient"],
+                                         "achieved": muls * 132 / (ph["quotient"] / 1e3) / 1e12 if ph["quotient"] else None, "peak": IMAD_WIDE_PEAK / 1e12,
+                                         "unit": "T IMAD.WIDE.U32/s", "frac": muls * 132 / (ph["quotient"] / 1e3) / IMAD_WIDE_PEAK if ph["quotient"] else None,
+                                         "share_of_step": ph["quotient"] / max(sum(ph.values()), 1e-9)}
         d_dense = be.to_device(random_scalars(n, 6))
         for _ in range(3):
             params.commit_dev(d_dense, n, lagrange=False)

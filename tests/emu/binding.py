@@ -139,3 +139,13 @@ def coset_interpolate(g, inv_pow, vinv, C, n, extra=None):
     lib().emu_coset_interpolate(_p(np.ascontiguousarray(g, dtype=np.uint64)), _p(np.ascontiguousarray(inv_pow, dtype=np.uint64)),
                                 _p(np.ascontiguousarray(vinv, dtype=np.uint64)), ctypes.c_uint32(C), ctypes.c_size_t(n), _p(out), _p(ex) if ex is not None else None)
     return out
+
+
+def mul_shoup(which, x, w, wq):
+    """Field::mul_shoup: x * w mod p with w plain and wq = floor(w * 2^256 / p); raw limb arrays (n, 4) uint64."""
+    x = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1, 4)
+    w = np.ascontiguousarray(w, dtype=np.uint64).reshape(-1, 4)
+    wq = np.ascontiguousarray(wq, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros_like(x)
+    lib().emu_mul_shoup(which, _p(x), _p(w), _p(wq), _p(out), ctypes.c_size_t(x.shape[0]))
+    return out

@@ -32,6 +32,25 @@ def test_field_limbs_match_oracle(orc, which):
     assert orc.mont_to_ints(emu.field_op(which, "mul", m, m), which) == [1] * 4
 
 
+@pytest.mark.parametrize("which", [0, 1])
+def test_constant_operand_multiplication(orc, which):
+    """Field::mul_shoup (the NTT's twiddle multiplier): for a constant w with wq = floor(w 2^256 / p) it returns x w mod p
+    for every x < p — with x in Montgomery form and w plain that is the Montgomery form of the product — fully reduced.
+    Edge cases cover the quotient estimate being one short (result in [2p, 3p) before the two conditional subtractions)."""
+    p = P.R_MOD if which == 0 else P.Q_MOD
+    rnd = random.Random(20 + which)
+    edge = [0, 1, 2, p - 1, p - 2, p >> 1, (p >> 1) + 1, (1 << 253) % p, (1 << 32) - 1, (1 << 224) - 1, 1 << 192]
+    xs = [a for a in edge for _ in edge] + [rnd.randrange(p) for _ in range(4000)]
+    ws = [b for _ in edge for b in edge] + [rnd.randrange(p) for _ in range(4000)]
+    wq = [(w << 256) // p for w in ws]
+    got = orc.raw_to_ints(emu.mul_shoup(which, orc.ints_to_raw(xs), orc.ints_to_raw(ws), orc.ints_to_raw(wq)))
+    assert got == [x * w % p for x, w in zip(xs, ws)]
+    # the Montgomery-domain use: x_mont * w_plain = (x w)_mont
+    X = orc.ints_to_mont(xs[:200], which)
+    want = orc.ints_to_mont([x * w % p for x, w in zip(xs[:200], ws[:200])], which)
+    assert np.array_equal(emu.mul_shoup(which, X, orc.ints_to_raw(ws[:200]), orc.ints_to_raw(wq[:200])), want)
+
+
 @pytest.mark.parametrize("log_n,max_log_m,max_log_tw,cap", [
     (0, 10, 2, 12), (1, 10, 2, 12), (3, 10, 2, 12), (6, 10, 2, 12),      # single pass
     (6, 3, 1, 12), (7, 4, 2, 12), (8, 4, 3, 5),                           # two passes, tile cap binding
