@@ -46,7 +46,9 @@ inline MsmShape msm_pre_shape(size_t n_table) {
     s.c = c;
     s.nwin = (255 + c - 1) / c;
     uint32_t log_b = c - 1;
-    s.log_t = log_b > 5 ? log_b - 5 : 0;                // 32 buckets per reduce thread
+    uint32_t log_m = 5;                                 // 32 buckets per reduce thread
+    if (const char* e = getenv("B200ZK_MSM_PRE_REDUCE_M")) { long v = strtol(e, nullptr, 10); if (v >= 1 && v <= 8) log_m = (uint32_t)v; }
+    s.log_t = log_b > log_m ? log_b - log_m : 0;
     s.nbuckets = (size_t)1 << (c - 1);
     return s;
 }

@@ -87,6 +87,17 @@ __global__ void __launch_bounds__(PK_THREADS) scale_kernel(fe_t* a, const fe_t s
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) scale_row(a, s, i);
 }
+// acc[i] = (init ? 0 : acc[i]) + sum_j s[j] * p[j][i] for up to 16 polynomials per launch: the linear combinations of
+// SHPLONK (A_i = sum_j y^j P_ij over the ~50 polynomials opened at x alone) read every polynomial once and touch the
+// accumulator once per 16 of them, instead of one axpy launch (and one accumulator round trip) per polynomial.
+struct LinCombArgs { const fe_t* p[16]; fe_t s[16]; uint32_t m; };
+__global__ void __launch_bounds__(PK_THREADS) lincomb_kernel(fe_t* acc, const LinCombArgs a, size_t n, int init) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe_t t = init ? Fr::zero() : acc[i];
+    for (uint32_t j = 0; j < a.m; ++j) { fe_t v = a.p[j][i]; t = Fr::add(t, Fr::mul(v, a.s[j])); }
+    acc[i] = t;
+}
 struct LowCoeffs { fe_t c[8]; uint32_t m; };
 __global__ void sub_low_kernel(fe_t* a, const LowCoeffs lc) {
     uint32_t i = threadIdx.x;
@@ -184,7 +195,7 @@ static size_t arena_need(const b200zk_pk* pk) {
     size_t draws = b200zk_pk_rng_draws(pk);
     size_t elems = 2 * A * n + 2 * I * n + draws + 7 * L * n + S * n + S * ext + 3 * n   // columns, lookups, perm, tmp
                    + ext * (1 + A + I + 4 + 1)                                            // h, cosets, lookup cosets + table_value, h_L
-                   + n * (1 + 8 + 4);                                                     // h_poly, shplonk set sums, hx/lx/tmp
+                   + n * (1 + 8 + 4 + 8);                                                 // h_poly, shplonk set sums, hx/lx/tmp, per-set quotients (sharded)
     if (pk->lk_early) elems += 4 * L * (size_t)pk->lk_cosets_n * n + 64;
     return elems * sizeof(fe_t) + (size_t)draws * 64 + (64 << 10);
 }
@@ -441,6 +452,28 @@ struct Shard {
     int coset_owner(uint32_t j) const { for (int r = 0; r < G; ++r) if (j >= coset_lo(r) && j < coset_lo(r + 1)) return r; return 0; }
     // point range of a dense commit
     size_t pt_lo(size_t len, int r) const { return len * (size_t)r / (size_t)G; }
+    // Lookup arguments and permutation sets go to the least loaded rank, the load being what a rank already carries for its
+    // quotient cosets (q is rarely a multiple of G: with 8 ranks and 5 cosets three ranks own none and would otherwise idle
+    // through half of the proof).  Weights are in units of one size-n transform: a coset costs its column extensions plus the
+    // quotient kernels, a lookup its sort, grand product, three transforms and commitments, a permutation set its product.
+    std::vector<int> lk_own, set_own;
+    std::vector<uint32_t> set_slot;                     // index of set s among its owner's sets
+    uint32_t set_slots = 0;
+    void assign(uint32_t L, uint32_t S, uint32_t columns) {
+        std::vector<uint64_t> load((size_t)G, 0);
+        const uint64_t w_coset = columns + 30, w_lookup = 15, w_set = 8;
+        for (int r = 0; r < G; ++r) load[r] = (uint64_t)(coset_lo(r + 1) - coset_lo(r)) * w_coset;
+        auto lightest = [&]() { int b = 0; for (int r = 1; r < G; ++r) if (load[r] < load[b]) b = r; return b; };
+        lk_own.resize(L); set_own.resize(S); set_slot.resize(S);
+        for (uint32_t l = 0; l < L; ++l) { int r = lightest(); lk_own[l] = r; load[r] += w_lookup; }
+        std::vector<uint32_t> used((size_t)G, 0);
+        for (uint32_t t = 0; t < S; ++t) { int r = lightest(); set_own[t] = r; set_slot[t] = used[r]++; load[r] += w_set; }
+        for (uint32_t u : used) set_slots = std::max(set_slots, u);
+    }
+    int lk_owner(uint32_t l) const { return lk_own[l]; }
+    bool lk_mine(uint32_t l) const { return lk_own[l] == R; }
+    int set_owner(uint32_t t) const { return set_own[t]; }
+    bool set_mine(uint32_t t) const { return set_own[t] == R; }
 };
 
 // Commitments to `cols`, column i computed by rank owners[i]; every rank ends up with all of them.  `flag` (optional)
@@ -517,7 +550,8 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     for (float& f : pk->phase_ms) f = 0;
     pk->timer_used = 0;
     ZK_CUDA(ctx, cudaSetDevice(ctx->device));
-    const Shard sh(pk);
+    Shard sh(pk);
+    sh.assign(pk->L, pk->S, pk->cs.A + pk->cs.I + pk->S + 3 * pk->L);
     pk->trace.clear();
     const auto t_start = std::chrono::steady_clock::now();
     auto mark = [&](const char* label) {              // called right after a host synchronisation: where the wall clock of the proof goes
@@ -576,6 +610,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     fe_t* h_poly = ar.take<fe_t>(n);
     fe_t* set_sums = ar.take<fe_t>(8 * n);
     fe_t* sh_tmp = ar.take<fe_t>(4 * n);
+    fe_t* set_quot = ar.take<fe_t>(8 * n);                       // sharded proof: Q_i of every rotation set, computed by its owner
     if (!ar.ok) return fail(ctx, B200ZK_ENOMEM, "create_proof", "arena too small");
     auto LK = [&](uint32_t l, uint32_t which) { return lk_bufs + ((size_t)l * 7 + which) * n; };
     pk->dbg.clear();
@@ -711,7 +746,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     // lookup l lives on rank l mod G from here to its grand product; every rank walks the rng stream
     for (uint32_t l = 0; l < L; ++l) {
         fe_t *cin = LK(l, 0), *ctab = LK(l, 1), *pin = LK(l, 2), *ptab = LK(l, 3), *pin_poly = LK(l, 4), *ptab_poly = LK(l, 5);
-        if (!sh.mine(l)) { rng_take(2 * (bf + 1) + 2); continue; }
+        if (!sh.lk_mine(l)) { rng_take(2 * (bf + 1) + 2); continue; }
         {
             PhaseTimer t(pk, PH_LOOKUP);
             ExprArgs ea = expr_args(pk, pk->lookup_prog[l].first, pk->lookup_prog[l].second, false, EXM_ACC01, ch, cin, ctab);
@@ -737,7 +772,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
             std::vector<const fe_t*> cols;
             std::vector<int> owners;
             std::vector<HAffine> pts;
-            for (uint32_t l = 0; l < L; ++l) { cols.push_back(LK(l, 2)); cols.push_back(LK(l, 3)); owners.push_back(sh.owner(l)); owners.push_back(sh.owner(l)); }
+            for (uint32_t l = 0; l < L; ++l) { cols.push_back(LK(l, 2)); cols.push_back(LK(l, 3)); owners.push_back(sh.lk_owner(l)); owners.push_back(sh.lk_owner(l)); }
             ZK_TRY(commit_multi_split(pk, sh, cols, owners, n, true, pts, &err));
             for (auto& pt : pts) tr.write_point(pt);
             mark("lookup_permuted_commits");
@@ -745,7 +780,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         if (err) return fail(ctx, B200ZK_ESYNTH, "create_proof", "ConstraintSystemFailure: lookup input not in table");
         // the permuted polynomials in coefficient form: every rank opens them, the coset owners extend them
         std::vector<CommPiece> pieces;
-        for (uint32_t l = 0; l < L; ++l) { pieces.push_back({LK(l, 4), n * sizeof(fe_t), sh.owner(l)}); pieces.push_back({LK(l, 5), n * sizeof(fe_t), sh.owner(l)}); }
+        for (uint32_t l = 0; l < L; ++l) { pieces.push_back({LK(l, 4), n * sizeof(fe_t), sh.lk_owner(l)}); pieces.push_back({LK(l, 5), n * sizeof(fe_t), sh.lk_owner(l)}); }
         ZK_TRY(share(pieces));
     }
     ch[EXF_BETA] = tr.squeeze_challenge();
@@ -786,7 +821,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
             }
             blind_rows[s] = rng_take(bf);
             rng_take(1);
-            if (!sh.mine(s)) continue;
+            if (!sh.set_mine(s)) continue;
             {
                 PhaseTimer t(pk, PH_PERM);
                 pa.beta = to_dev(beta); pa.gamma = to_dev(gamma); pa.omega_pows = pk->omega_pows; pa.out = tmp_n;
@@ -797,7 +832,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
                 ctx->launches++;
                 ZK_TRY(prefix_product_run(ctx, tmp_n, z, n, sh.on() ? HFr::one() : last_z));
             }
-            ZK_CUDA(ctx, cudaMemcpyAsync((fe_t*)ctx->pinned + (sh.on() ? s / sh.G : 0), z + (n - (bf + 1)), sizeof(fe_t), cudaMemcpyDeviceToHost, st));
+            ZK_CUDA(ctx, cudaMemcpyAsync((fe_t*)ctx->pinned + (sh.on() ? sh.set_slot[s] : 0), z + (n - (bf + 1)), sizeof(fe_t), cudaMemcpyDeviceToHost, st));
             if (!sh.on()) {
                 ZK_CUDA(ctx, copy_rows(z + (n - bf), blind_rows[s], bf));
                 ZK_CUDA(ctx, cudaStreamSynchronize(st));
@@ -805,10 +840,10 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
             }
         }
         if (sh.on() && S) {
-            const size_t slots = (S + sh.G - 1) / sh.G;
+            const size_t slots = sh.set_slots;
             std::vector<HFr> mine_t(slots, HFr::one()), all_t(slots * sh.G);
             ZK_CUDA(ctx, cudaStreamSynchronize(st));
-            for (uint32_t s = 0; s < S; ++s) if (sh.mine(s)) mine_t[s / sh.G] = HFr::from_limbs((const fe_t*)ctx->pinned + s / sh.G);
+            for (uint32_t s = 0; s < S; ++s) if (sh.set_mine(s)) mine_t[sh.set_slot[s]] = HFr::from_limbs((const fe_t*)ctx->pinned + sh.set_slot[s]);
             {
                 PhaseTimer t(pk, PH_OTHER);
                 ZK_TRY(sh.cm->allgather_host(ctx, mine_t.data(), slots * sizeof(HFr), all_t.data(), st));
@@ -816,11 +851,11 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
             HFr carry = HFr::one();
             for (uint32_t s = 0; s < S; ++s) {
                 fe_t* z = perm_polys + (size_t)s * n;
-                if (sh.mine(s)) {
+                if (sh.set_mine(s)) {
                     if (s) { scale_kernel<<<nb(n - bf), PK_THREADS, 0, st>>>(z, to_dev(carry), n - bf); ctx->launches++; }
                     ZK_CUDA(ctx, copy_rows(z + (n - bf), blind_rows[s], bf));
                 }
-                carry = carry * all_t[(size_t)sh.owner(s) * slots + s / sh.G];
+                carry = carry * all_t[(size_t)sh.set_owner(s) * slots + sh.set_slot[s]];
             }
             mark("perm_products");
         }
@@ -828,7 +863,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
             std::vector<const fe_t*> cols;
             std::vector<int> owners;
             std::vector<HAffine> pts;
-            for (uint32_t s = 0; s < S; ++s) { cols.push_back(perm_polys + (size_t)s * n); owners.push_back(sh.owner(s)); }
+            for (uint32_t s = 0; s < S; ++s) { cols.push_back(perm_polys + (size_t)s * n); owners.push_back(sh.set_owner(s)); }
             ZK_TRY(commit_multi_split(pk, sh, cols, owners, n, true, pts));
             for (auto& pt : pts) tr.write_point(pt);
             mark("permutation_commits");
@@ -837,8 +872,8 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
             std::vector<CommPiece> pieces;
             for (uint32_t s = 0; s < S; ++s) {
                 fe_t* z = perm_polys + (size_t)s * n;
-                if (sh.mine(s)) ZK_TRY(lagrange_to_coeff(pk, z));
-                pieces.push_back({z, n * sizeof(fe_t), sh.owner(s)});
+                if (sh.set_mine(s)) ZK_TRY(lagrange_to_coeff(pk, z));
+                pieces.push_back({z, n * sizeof(fe_t), sh.set_owner(s)});
             }
             ZK_TRY(share(pieces));
             for (uint32_t s = 0; s < S; ++s) ZK_TRY(my_cosets(perm_polys + (size_t)s * n, perm_cosets + (size_t)s * ext, cj0, cj1));
@@ -848,7 +883,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     // ---- step 7: lookups, commit_product
     for (uint32_t l = 0; l < L; ++l) {
         fe_t* z = LK(l, 6);
-        if (!sh.mine(l)) { rng_take(bf + 1); continue; }
+        if (!sh.lk_mine(l)) { rng_take(bf + 1); continue; }
         {
             PhaseTimer t(pk, PH_LOOKUP);
             LookupProdArgs la{LK(l, 2), LK(l, 3), LK(l, 0), LK(l, 1), to_dev(beta), to_dev(gamma), tmp_n, (uint32_t)n};
@@ -867,11 +902,11 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         std::vector<int> owners;
         std::vector<HAffine> pts;
         std::vector<CommPiece> pieces;
-        for (uint32_t l = 0; l < L; ++l) { cols.push_back(LK(l, 6)); owners.push_back(sh.owner(l)); pieces.push_back({LK(l, 6), n * sizeof(fe_t), sh.owner(l)}); }
+        for (uint32_t l = 0; l < L; ++l) { cols.push_back(LK(l, 6)); owners.push_back(sh.lk_owner(l)); pieces.push_back({LK(l, 6), n * sizeof(fe_t), sh.lk_owner(l)}); }
         ZK_TRY(commit_multi_split(pk, sh, cols, owners, n, true, pts));
         for (auto& pt : pts) tr.write_point(pt);
         mark("lookup_product_commits");
-        for (uint32_t l = 0; l < L; ++l) if (sh.mine(l)) ZK_TRY(lagrange_to_coeff(pk, LK(l, 6)));
+        for (uint32_t l = 0; l < L; ++l) if (sh.lk_mine(l)) ZK_TRY(lagrange_to_coeff(pk, LK(l, 6)));
         ZK_TRY(share(pieces));
         if (pk->lk_early && lk_rows) {                           // side stream: the product cosets
             SideStream side(ctx);
@@ -1139,16 +1174,26 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     fe_t *hx = sh_tmp, *lx = sh_tmp + n, *t0 = sh_tmp + 2 * n, *t1 = sh_tmp + 3 * n;
     ZK_CUDA(ctx, cudaMemsetAsync(hx, 0, n * sizeof(fe_t), st));
     {
+        // Sharded: rotation set i (its linear combination A_i and the Kate divisions that give Q_i) lives on rank i mod G; both
+        // polynomials are then broadcast — every rank needs A_i again for the linearisation polynomial — and h1 = sum v^i Q_i
+        // is formed everywhere.
         HFr v_pow = HFr::one();
         for (size_t i = 0; i < rot_sets.size(); ++i) {
             fe_t* sum = set_sums + i * n;                        // A_i = sum_j y^j P_ij
+            if (sh.on() && !sh.mine((uint32_t)i)) continue;
             HFr y_pow = HFr::one();
             std::vector<HFr> rlow(rot_sets[i].pts.size(), HFr::zero());   // R_i = sum_j y^j r_ij
-            for (size_t j = 0; j < rot_sets[i].polys.size(); ++j) {
-                axpy_kernel<<<nb(n), PK_THREADS, 0, st>>>(sum, rot_sets[i].polys[j], to_dev(y_pow), n, j == 0 ? 1 : 0);
+            for (size_t j0 = 0; j0 < rot_sets[i].polys.size(); j0 += 16) {
+                LinCombArgs la{};
+                la.m = (uint32_t)std::min<size_t>(16, rot_sets[i].polys.size() - j0);
+                for (uint32_t j = 0; j < la.m; ++j) {
+                    la.p[j] = rot_sets[i].polys[j0 + j];
+                    la.s[j] = to_dev(y_pow);
+                    for (size_t c = 0; c < low[i][j0 + j].size(); ++c) rlow[c] = rlow[c] + low[i][j0 + j][c] * y_pow;
+                    y_pow = y_pow * sy;
+                }
+                lincomb_kernel<<<nb(n), PK_THREADS, 0, st>>>(sum, la, n, j0 == 0 ? 1 : 0);
                 ctx->launches++;
-                for (size_t c = 0; c < low[i][j].size(); ++c) rlow[c] = rlow[c] + low[i][j][c] * y_pow;
-                y_pow = y_pow * sy;
             }
             // N_i = A_i - R_i ; Q_i = N_i / prod (X - p)
             ZK_CUDA(ctx, copy_rows(t0, sum, n));
@@ -1162,9 +1207,28 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
                 ZK_TRY(recurrence_run(ctx, src + 1, dst, len - 1, pt, nullptr));   // kate_division
                 --len; std::swap(src, dst);
             }
-            axpy_kernel<<<nb(len), PK_THREADS, 0, st>>>(hx, src, to_dev(v_pow), len, 0);
-            ctx->launches++;
-            v_pow = v_pow * sv;
+            if (sh.on()) {                                        // keep Q_i (zero-padded to n) for the exchange
+                ZK_CUDA(ctx, cudaMemsetAsync(set_quot + i * n, 0, n * sizeof(fe_t), st));
+                ZK_CUDA(ctx, copy_rows(set_quot + i * n, src, len));
+            } else {
+                axpy_kernel<<<nb(len), PK_THREADS, 0, st>>>(hx, src, to_dev(v_pow), len, 0);
+                ctx->launches++;
+                v_pow = v_pow * sv;
+            }
+        }
+        if (sh.on()) {
+            std::vector<CommPiece> pieces;
+            for (size_t i = 0; i < rot_sets.size(); ++i) {
+                pieces.push_back({set_sums + i * n, n * sizeof(fe_t), sh.owner((uint32_t)i)});
+                pieces.push_back({set_quot + i * n, n * sizeof(fe_t), sh.owner((uint32_t)i)});
+            }
+            rc = share(pieces);
+            if (rc != B200ZK_OK) return finish(rc);
+            for (size_t i = 0; i < rot_sets.size(); ++i) {
+                axpy_kernel<<<nb(n), PK_THREADS, 0, st>>>(hx, set_quot + i * n, to_dev(v_pow), n, 0);
+                ctx->launches++;
+                v_pow = v_pow * sv;
+            }
         }
     }
     {
