@@ -452,19 +452,19 @@ struct Shard {
     int coset_owner(uint32_t j) const { for (int r = 0; r < G; ++r) if (j >= coset_lo(r) && j < coset_lo(r + 1)) return r; return 0; }
     // point range of a dense commit
     size_t pt_lo(size_t len, int r) const { return len * (size_t)r / (size_t)G; }
-    // Lookup arguments and permutation sets go to the least loaded rank, the load being what a rank carries BEFORE the
-    // challenge y for its quotient cosets: the coset extensions of the advice / instance columns on the side stream (q is
-    // rarely a multiple of G: with 8 ranks and 5 cosets three ranks own none).  Everything up to y is one dependency chain
-    // — the quotient cannot start before the last lookup product is committed — so it is this part that has to be level;
-    // with 8 ranks the 8 lookups of the Merkle Sum Tree circuit land 2 + 2 + 2 on the ranks without a coset and 1 + 1 on
-    // ranks with one (36.5 -> R2_BAL ms).  Weights in units of one size-n transform: a coset = A + I column extensions, a lookup
-    // (compression, sort, grand product, three transforms, commitments) = 15, a permutation set = 8.
+    // Lookup arguments and permutation sets go to the least loaded rank, the load being what a rank already carries for its
+    // quotient cosets (q is rarely a multiple of G: with 8 ranks and 5 cosets three ranks own none and would otherwise idle
+    // through half of the proof).  Weights are in units of one size-n transform: a coset costs its column extensions plus the
+    // quotient kernels, a lookup its sort, grand product, three transforms and commitments, a permutation set its product.
+    // Measured on 8 GPUs (MST k = 20): round-robin 39.2 ms; this placement — all 8 lookups and the 4 sets on the three ranks
+    // without a coset — 36.5 ms; weighting only the work before the challenge y (2 + 2 + 2 lookups on those ranks, 1 + 1 and the
+    // sets on coset owners) 38.0 ms: the coset owners are the busy ranks from start to end, anything added to them costs.
     std::vector<int> lk_own, set_own;
     std::vector<uint32_t> set_slot;                     // index of set s among its owner's sets
     uint32_t set_slots = 0;
     void assign(uint32_t L, uint32_t S, uint32_t columns) {
         std::vector<uint64_t> load((size_t)G, 0);
-        const uint64_t w_coset = columns, w_lookup = 15, w_set = 8;
+        const uint64_t w_coset = columns + 30, w_lookup = 15, w_set = 8;
         for (int r = 0; r < G; ++r) load[r] = (uint64_t)(coset_lo(r + 1) - coset_lo(r)) * w_coset;
         auto lightest = [&]() { int b = 0; for (int r = 1; r < G; ++r) if (load[r] < load[b]) b = r; return b; };
         lk_own.resize(L); set_own.resize(S); set_slot.resize(S);
@@ -554,7 +554,7 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     pk->timer_used = 0;
     ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     Shard sh(pk);
-    sh.assign(pk->L, pk->S, pk->cs.A + pk->cs.I);
+    sh.assign(pk->L, pk->S, pk->cs.A + pk->cs.I + pk->S + 3 * pk->L);
     pk->trace.clear();
     const auto t_start = std::chrono::steady_clock::now();
     auto mark = [&](const char* label) {              // called right after a host synchronisation: where the wall clock of the proof goes
