@@ -156,11 +156,7 @@ ZK_D void ntt_pass_block(const NttPassArgs& a, uint32_t bid, uint32_t nthreads, 
             uint32_t s0 = (i0 << a.log_tw) + c, s1 = ((i0 + half) << a.log_tw) + c;
             fe_t x = tile_ld(sm, tile, s0), y = tile_ld(sm, tile, s1);
             fe_t s = Fr::add(x, y), d = Fr::sub(x, y);
-            if (j != 0) {
-                const size_t ix = (size_t)j << (a.log_roots - lh - 1);
-                if (a.roots_s) { const fe2_t t = a.roots_s[ix]; d = Fr::mul_shoup(d, t.w, t.wq); }       // constant-operand product (field.cuh)
-                else d = Fr::mul(d, a.roots[ix]);
-            }
+            if (j != 0) d = Fr::mul(d, a.roots[(size_t)j << (a.log_roots - lh - 1)]);
             tile_st(sm, tile, s0, s); tile_st(sm, tile, s1, d);
         }
         ZK_PHASE_END
@@ -177,10 +173,7 @@ ZK_D void ntt_pass_block(const NttPassArgs& a, uint32_t bid, uint32_t nthreads, 
             g = ((size_t)h << (a.log_m + a.log_l)) + ((size_t)k << a.log_l) + l;
             // w_{ML}^{l k} = omega^{l k N/(ML)}
             uint64_t E = ((uint64_t)(l + a.l_offset) * k) << a.tw_shift;
-            if (E) {
-                if (a.tw_full_s) { const fe2_t t = a.tw_full_s[(uint32_t)E]; v = Fr::mul_shoup(v, t.w, t.wq); }
-                else v = Fr::mul(v, ntt_twiddle(a, (uint32_t)E));
-            }
+            if (E) v = Fr::mul(v, ntt_twiddle(a, (uint32_t)E));
             if (a.scatter) {
                 const uint32_t dest = k >> a.log_rows_per_rank, row = k & ((1u << a.log_rows_per_rank) - 1);
                 a.peers[dest][((size_t)row << a.log_c_total) + l + a.l_offset] = v;
