@@ -30,6 +30,8 @@ for circuit, k in (("v3", 14), ("mst", 9), ("mst", 14)):
         pk.create_proof_dev(d_adv, inst, d_wide, tr)
     be.event_record(1); be.sync()
     ms = be.event_elapsed_ms(0, 1) / reps
+    if "--profile" in sys.argv and (circuit, k) == ("v3", 14):      # one proof inside cudaProfilerStart/Stop (ncu --profile-from-start off)
+        be.profiler_range(True); pk.create_proof_dev(d_adv, inst, d_wide, tr); be.profiler_range(False)
     print(json.dumps({"circuit": circuit, "k": k, "ms": round(ms, 3), "launches": (be.launch_count() - l0) // reps,
                       "timeline_ms": [(a, round(b, 2)) for a, b in pk.last_trace()], "phase_ms": {a: round(b, 2) for a, b in pk.last_phase_ms().items()}}), flush=True)
     d_adv.free(); d_wide.free(); pk.close(); params.close()
