@@ -40,13 +40,18 @@ inline MsmShape msm_pre_shape(size_t n_table) {
     // measured (profiles/r01_msm_fixed_base_window_sweep.txt): c = 16 is best up to 2^19 points,
     // 17 from 2^20; wider windows lose to the c * 2^(c-2) additions of the reduce
     uint32_t c = lg >= 20 ? 17 : 16;
-    if (lg < 12) c = lg + 4;
+    // small SRS (round 2): the bucket reduce costs c * 2^(c-2) additions whatever n is and runs far below the multiplication
+    // rate (a latency-bound tree: 0.42 ms per commit for 2^15 buckets), so below 2^18 points the window shrinks with n —
+    // Merkle tree v3 at k = 14: 6 reduce launches of 0.42 ms were 29 % of the 9.2 ms proof
+    // (profiles/r02_launches_v3_k14_summary.txt)
+    if (lg < 18) c = lg >= 10 ? lg - 2 : 8;
     if (c < 8) c = 8;
     if (const char* e = getenv("B200ZK_MSM_PRE_C")) { long v = strtol(e, nullptr, 10); if (v >= 4 && v <= 24) c = (uint32_t)v; }
     s.c = c;
     s.nwin = (255 + c - 1) / c;
     uint32_t log_b = c - 1;
-    uint32_t log_m = 5;                                 // 32 buckets per reduce thread
+    uint32_t log_m = 5;                                 // 32 buckets per reduce thread ...
+    if (log_b >= 7 && log_b < 12) log_m = log_b - 7;    // ... fewer when that would leave less than one 128-thread block per bit (the batched path needs log_t >= 7)
     if (const char* e = getenv("B200ZK_MSM_PRE_REDUCE_M")) { long v = strtol(e, nullptr, 10); if (v >= 1 && v <= 8) log_m = (uint32_t)v; }
     s.log_t = log_b > log_m ? log_b - log_m : 0;
     s.nbuckets = (size_t)1 << (c - 1);
