@@ -292,6 +292,126 @@ template <class C> struct Field {
         for (int i = 1; i < 8; ++i) e[i] = C::p(i);
         return pow(a, e);
     }
+
+    // ---- inversion by division steps ---------------------------------------------------------------
+    // Bernstein–Yang "safegcd" (the delta = 1/2 variant, 30 division steps per round on the low words, then one 2 x 2
+    // integer matrix applied to the 256-bit state): about 20 rounds of ~1100 simple integer instructions against the 384
+    // dependent field multiplications of Fermat — a sixth of the latency of a lone inversion, which is what a batch
+    // inversion of a short column waits for (profiles/r02_launches_v3_k14_summary.txt: 0.23 ms per launch).
+    //   state   f = p, g = x, d = 0, e = 1 with  f = d x,  g = e x  (mod p);  at g = 0, f = +-1 and x^-1 = +-d
+    //   limbs   9 signed limbs of 30 bits; d, e stay inside (-2p, p)
+    // Same result as inv(): the canonical Montgomery representative, inv_gcd(0) = 0.
+    static constexpr int32_t M30 = (int32_t)((1u << 30) - 1u);
+    ZK_D static constexpr int32_t p30(int i) {                // limb i of p in base 2^30
+        return (int32_t)((i == 8 ? (C::p(7) >> 16)
+                                 : ((C::p((30 * i) >> 5) >> ((30 * i) & 31)) |
+                                    (((30 * i) & 31) > 2 ? (C::p(((30 * i) >> 5) + 1) << (32 - ((30 * i) & 31))) : 0u))) & (uint32_t)M30);
+    }
+    ZK_D static void to30(const uint32_t* w, int32_t* o) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int bit = 30 * i, wd = bit >> 5, sh = bit & 31;
+            uint32_t v = w[wd] >> sh;
+            if (sh > 2 && wd + 1 < 8) v |= w[wd + 1] << (32 - sh);
+            o[i] = (int32_t)(v & (uint32_t)M30);
+        }
+    }
+    // 30 division steps on the low words; t = {u, v, q, r} with 2^30 (f', g') = t (f, g)
+    ZK_D static int32_t divsteps30(int32_t zeta, uint32_t f, uint32_t g, int32_t* t) {
+        uint32_t u = 1, v = 0, q = 0, r = 1;
+#pragma unroll 6
+        for (int i = 0; i < 30; ++i) {
+            uint32_t c1 = (uint32_t)(zeta >> 31), c2 = 0u - (g & 1u);
+            const uint32_t x = (f ^ c1) - c1, y = (u ^ c1) - c1, z = (v ^ c1) - c1;
+            g += x & c2; q += y & c2; r += z & c2;
+            c1 &= c2;
+            zeta = (int32_t)((uint32_t)zeta ^ c1) - 1;
+            f += g & c1; u += q & c1; v += r & c1;
+            g >>= 1; u <<= 1; v <<= 1;
+        }
+        t[0] = (int32_t)u; t[1] = (int32_t)v; t[2] = (int32_t)q; t[3] = (int32_t)r;
+        return zeta;
+    }
+    ZK_D static T inv_gcd(const T& a) {
+        int32_t f[9], g[9], d[9], e[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { f[i] = p30(i); d[i] = 0; e[i] = 0; }
+        e[0] = 1;
+        to30(a.l, g);
+        const uint32_t pinv = (0u - C::INV) & (uint32_t)M30;      // p^-1 mod 2^30
+        int32_t zeta = -1;
+        for (int round = 0; round < 24; ++round) {                // 590 steps suffice for 256-bit inputs: 20 rounds
+            int32_t nz = 0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) nz |= g[i];
+            if (nz == 0) break;
+            int32_t t[4];
+            zeta = divsteps30(zeta, (uint32_t)f[0] | ((uint32_t)f[1] << 30), (uint32_t)g[0] | ((uint32_t)g[1] << 30), t);
+            const int64_t u = t[0], v = t[1], q = t[2], r = t[3];
+            {   // (d, e) <- t (d, e) / 2^30 mod p
+                const int32_t sd = d[8] >> 31, se = e[8] >> 31;
+                int32_t md = (t[0] & sd) + (t[1] & se), me = (t[2] & sd) + (t[3] & se);
+                int64_t cd = u * d[0] + v * e[0], ce = q * d[0] + r * e[0];
+                md -= (int32_t)((pinv * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+                me -= (int32_t)((pinv * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+                cd += (int64_t)p30(0) * md; ce += (int64_t)p30(0) * me;
+                cd >>= 30; ce >>= 30;
+#pragma unroll
+                for (int i = 1; i < 9; ++i) {
+                    cd += u * d[i] + v * e[i] + (int64_t)p30(i) * md;
+                    ce += q * d[i] + r * e[i] + (int64_t)p30(i) * me;
+                    d[i - 1] = (int32_t)cd & M30; cd >>= 30;
+                    e[i - 1] = (int32_t)ce & M30; ce >>= 30;
+                }
+                d[8] = (int32_t)cd; e[8] = (int32_t)ce;
+            }
+            {   // (f, g) <- t (f, g) / 2^30
+                int64_t cf = u * f[0] + v * g[0], cg = q * f[0] + r * g[0];
+                cf >>= 30; cg >>= 30;
+#pragma unroll
+                for (int i = 1; i < 9; ++i) {
+                    cf += u * f[i] + v * g[i];
+                    cg += q * f[i] + r * g[i];
+                    f[i - 1] = (int32_t)cf & M30; cf >>= 30;
+                    g[i - 1] = (int32_t)cg & M30; cg >>= 30;
+                }
+                f[8] = (int32_t)cf; g[8] = (int32_t)cg;
+            }
+        }
+        // x^-1 = sign(f) d, brought from (-2p, 2p) into [0, p)
+        const int32_t sf = f[8] >> 31;
+        int32_t w[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) w[i] = (d[i] ^ sf) - sf;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {                    // + p while negative (twice), then - p if >= p
+            int32_t carry = 0, add[9];
+            const int32_t neg = w[8] >> 31;
+            if (pass == 2) {                                      // trial subtraction
+                int32_t c2 = 0, tr[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) { const int32_t s = w[i] - p30(i) + c2; tr[i] = s & M30; c2 = s >> 30; if (i == 8) tr[i] = s; }
+                const int32_t keep = tr[8] >> 31;                 // negative: w < p, keep w
+#pragma unroll
+                for (int i = 0; i < 9; ++i) w[i] = (w[i] & keep) | (tr[i] & ~keep);
+                break;
+            }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) add[i] = p30(i) & neg;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) { const int32_t s = w[i] + add[i] + carry; carry = s >> 30; w[i] = i == 8 ? s : (s & M30); }
+        }
+        T y;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                             // 9 x 30 -> 8 x 32
+            const int bit = 32 * i, lb = bit / 30, sh = bit % 30;
+            uint32_t v = (uint32_t)w[lb] >> sh;
+            v |= (uint32_t)w[lb + 1] << (30 - sh);              // sh <= 14: two limbs always cover the word
+            y.l[i] = v;
+        }
+        // x was a R (Montgomery form): y = a^-1 R^-1, and y * R^3 * R^-1 = a^-1 R
+        return mul(y, mul(r2(), r2()));
+    }
 };
 
 typedef Field<FrCfg> Fr;

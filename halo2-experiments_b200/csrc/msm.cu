@@ -252,7 +252,7 @@ int32_t msm_run_multi(b200zk_ctx* ctx, const fe_t* const* d_cols, uint32_t ncols
 
     uint32_t fast_max = MSM_FAST_MAX;
     if (const char* e = getenv("B200ZK_MSM_FAST_MAX")) fast_max = (uint32_t)strtoul(e, nullptr, 10);
-    uint32_t seg_min = 16;
+    uint32_t seg_min = n < ((size_t)1 << 18) ? 8 : 16;      // short columns are latency bound: shorter chains, one more level
     if (const char* e = getenv("B200ZK_MSM_SEG_MIN")) seg_min = (uint32_t)strtoul(e, nullptr, 10);
     if (maxcnt <= fast_max) {
         msm_accumulate_kernel<<<nb(B, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);

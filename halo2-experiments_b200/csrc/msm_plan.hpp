@@ -43,8 +43,8 @@ inline MsmShape msm_pre_shape(size_t n_table) {
     // small SRS (round 2): the bucket reduce costs c * 2^(c-2) additions whatever n is and runs far below the multiplication
     // rate (a latency-bound tree: 0.42 ms per commit for 2^15 buckets), so below 2^18 points the window shrinks with n —
     // Merkle tree v3 at k = 14: 6 reduce launches of 0.42 ms were 29 % of the 9.2 ms proof
-    // (profiles/r02_launches_v3_k14_summary.txt)
-    if (lg < 18) c = lg >= 10 ? lg - 2 : 8;
+    // (profiles/r02_launches_v3_k14_summary.txt); window sweep at k = 14: c = 10 / 11 / 12 / 13 -> 7.7 / 8.0 / 8.1 / 8.4 ms per proof
+    if (lg < 18) c = lg >= 12 ? lg - 4 : 8;
     if (c < 8) c = 8;
     if (const char* e = getenv("B200ZK_MSM_PRE_C")) { long v = strtol(e, nullptr, 10); if (v >= 4 && v <= 24) c = (uint32_t)v; }
     s.c = c;

@@ -45,8 +45,10 @@ static unsigned nblocks(size_t work, unsigned threads) { return (unsigned)((work
 int32_t batch_invert_run(b200zk_ctx* ctx, fe_t* d_a, size_t n, int field) {
     if (n == 0) return B200ZK_OK;
     ZK_TRY(ws_reserve(ctx, ctx->poly_ws, n * sizeof(fe_t)));
-    // enough lanes to fill the machine, at least ~32 elements per lane to amortise the inversion
-    size_t lanes = std::min<size_t>((n + 31) / 32, (size_t)ctx->sm_count * 1024);
+    // one inversion (Field::inv_gcd, about 40 multiplications' worth of instructions) per lane of 16 elements — 8 for a
+    // short column, where the kernel is one lane's latency; at most what fills the machine
+    const size_t per_lane = n <= ((size_t)1 << 16) ? 8 : 16;
+    size_t lanes = std::min<size_t>((n + per_lane - 1) / per_lane, (size_t)ctx->sm_count * 1024);
     if (lanes == 0) lanes = 1;
     if (field == 0) batch_invert_kernel<Fr><<<nblocks(lanes, POLY_THREADS), POLY_THREADS, 0, ctx->stream>>>(d_a, (fe_t*)ctx->poly_ws.p, n, lanes);
     else batch_invert_kernel<Fq><<<nblocks(lanes, POLY_THREADS), POLY_THREADS, 0, ctx->stream>>>(d_a, (fe_t*)ctx->poly_ws.p, n, lanes);

@@ -23,7 +23,7 @@ template <class F> ZK_D void batch_invert_lane(fe_t* a, fe_t* scratch, size_t n,
         scratch[i] = acc;
         if (!F::is_zero(v)) acc = F::mul(acc, v);
     }
-    acc = F::inv(acc);
+    acc = F::inv_gcd(acc);                                  // division-step inversion: ~6x shorter than the Fermat chain a lane would wait for
     size_t cnt = t < n ? (n - t + T - 1) / T : 0;
     for (size_t j = cnt; j-- > 0;) {
         size_t i = t + j * T;

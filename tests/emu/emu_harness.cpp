@@ -17,7 +17,7 @@ using namespace b200zk;
 
 extern "C" {
 
-// op: 0 add 1 sub 2 mul 3 sqr 4 inv 5 from_mont 6 to_mont ; which: 0 Fr 1 Fq
+// op: 0 add 1 sub 2 mul 3 sqr 4 inv 5 from_mont 6 to_mont 7 inv_gcd ; which: 0 Fr 1 Fq
 void emu_field_op(int which, int op, const fe_t* a, const fe_t* b, fe_t* out, size_t n) {
     for (size_t i = 0; i < n; ++i) {
         if (which == 0) {
@@ -29,6 +29,7 @@ void emu_field_op(int which, int op, const fe_t* a, const fe_t* b, fe_t* out, si
                 case 4: out[i] = Fr::inv(a[i]); break;
                 case 5: out[i] = Fr::from_mont(a[i]); break;
                 case 6: out[i] = Fr::to_mont(a[i]); break;
+                case 7: out[i] = Fr::inv_gcd(a[i]); break;
             }
         } else {
             switch (op) {
@@ -39,6 +40,7 @@ void emu_field_op(int which, int op, const fe_t* a, const fe_t* b, fe_t* out, si
                 case 4: out[i] = Fq::inv(a[i]); break;
                 case 5: out[i] = Fq::from_mont(a[i]); break;
                 case 6: out[i] = Fq::to_mont(a[i]); break;
+                case 7: out[i] = Fq::inv_gcd(a[i]); break;
             }
         }
     }

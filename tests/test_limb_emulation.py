@@ -51,6 +51,21 @@ def test_constant_operand_multiplication(orc, which):
     assert np.array_equal(emu.mul_shoup(which, X, orc.ints_to_raw(ws[:200]), orc.ints_to_raw(wq[:200])), want)
 
 
+@pytest.mark.parametrize("which", [0, 1])
+def test_division_step_inversion(orc, which):
+    """Field::inv_gcd (the inversion inside batch_invert): x^-1 in Montgomery form, identical to the Fermat chain Field::inv
+    and to pow(x, p - 2); 0 -> 0.  Edge values sit at limb boundaries of the 9 x 30-bit state."""
+    p = P.R_MOD if which == 0 else P.Q_MOD
+    rnd = random.Random(40 + which)
+    xs = [0, 1, 2, 3, p - 1, p - 2, p >> 1, (p >> 1) + 1, (1 << 253) % p, (1 << 255) % p, 1 << 30, (1 << 30) - 1, 1 << 60,
+          1 << 240, (1 << 240) - 1, (1 << 210) + 1]
+    xs += [rnd.randrange(p) for _ in range(3000)] + [rnd.randrange(1 << rnd.randrange(1, 254)) for _ in range(500)]
+    X = orc.ints_to_mont(xs, which)
+    got = emu.field_op(which, "inv_gcd", X)
+    assert np.array_equal(got, orc.ints_to_mont([pow(x, p - 2, p) for x in xs], which))
+    assert np.array_equal(got[:600], emu.field_op(which, "inv", X[:600]))
+
+
 @pytest.mark.parametrize("log_n,max_log_m,max_log_tw,cap", [
     (0, 10, 2, 12), (1, 10, 2, 12), (3, 10, 2, 12), (6, 10, 2, 12),      # single pass
     (6, 3, 1, 12), (7, 4, 2, 12), (8, 4, 3, 5),                           # two passes, tile cap binding
