@@ -384,6 +384,19 @@ def run_gpu(args):
                                     f"({pk.degree - 1} cosets), dense commits (h pieces, random polynomial, SHPLONK) by point range, evaluations by query; "
                                     "polynomial exchange = grouped ncclBroadcast, commitments / partial sums = 64-byte all-gathers")
             h2d = h2d * world                                         # every rank uploads the witness over its own PCIe link
+        elif rank == 0:
+            # the proof of the timed region and the one of the host-buffer entry point, checked by the product's own verifier
+            # (b200zk_verify_proof: transcript replay, SHPLONK, pairing) outside the timed region
+            import hashlib
+            e2e_proof = step_e2e()
+            fixed_c, sigma_c = pk.vk_commitments()
+            g, _ = params.read()
+            vk = zk.VerifyingKey(job.cs, k, fixed_c, sigma_c, g[0], zk.g2_mul(random_scalars(1, SRS_SEED)[0]))
+            extra["verified"] = bool(vk.verify_proof(inst, last, tr_repr) and vk.verify_proof(inst, e2e_proof, tr_repr))
+            extra["verification"] = {"what": "b200zk_verify_proof accepts the proof of the last timed step and the proof of the host-buffer entry point "
+                                             "(outside the timed region); byte identity with the CPU prover is in cpu_baseline.gpu_proof_bytes_identical",
+                                     "proof_sha256": hashlib.sha256(last).hexdigest(), "proof_bytes": len(last)}
+            del g
     else:
         value = units_per_step * world / (ms_per_step / 1e3)
         e2e_value = units_per_step * world / (e2e_ms / 1e3)

@@ -105,12 +105,7 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_reduce_bits_tree_kernel(c
     const uint32_t col = blockIdx.x / blocks_per_set;
     const uint32_t gid = (blockIdx.x % blocks_per_set) * blockDim.x + threadIdx.x;     // (bit t, chunk) inside the column
     const uint32_t t = gid >> a.log_t, chunk = gid & ((1u << a.log_t) - 1);
-    const uint32_t m = (1u << (a.c - 1)) >> a.log_t, b0 = chunk * m;
-    const xyzz_t* B = a.buckets + (size_t)col * a.set_buckets;
-    xyzz_t acc = xyzz_identity();
-    for (uint32_t b = b0; b < b0 + m; ++b)
-        if (((b + 1) >> t) & 1) xyzz_add(acc, B[b]);
-    sm[threadIdx.x] = acc;
+    sm[threadIdx.x] = msm_reduce_bits_chunk(a.buckets + (size_t)col * a.set_buckets, a.c, a.log_t, t, chunk);
     __syncthreads();
     for (uint32_t s = MSM_ACC_THREADS >> 1; s > 0; s >>= 1) {
         if (threadIdx.x < s) { xyzz_t v = sm[threadIdx.x]; xyzz_add(v, sm[threadIdx.x + s]); sm[threadIdx.x] = v; }

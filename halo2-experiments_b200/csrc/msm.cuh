@@ -288,14 +288,26 @@ ZK_D void msm_reduce_thread(const MsmArgs& a, uint32_t gid) {
 //   sum_v v B_v = sum_{t < c} 2^t * S_t,   S_t = sum of the buckets whose multiplier has bit t set.
 // gid -> (bit t, chunk); every S_t is a plain parallel sum (no serial running-sum chain), the c
 // values go back to the host which applies the powers of two (c - 1 doublings).
+// The multipliers with bit t set, in increasing order: the s-th is v = (s >> t) * 2^(t+1) + 2^t + (s mod 2^t); there are
+// 2^(c-2) of them below 2^(c-1) for t < c - 1, and the single v = 2^(c-1) for t = c - 1.  Chunk `chunk` of 2^log_t sums an equal
+// share of that list, so every lane of a warp has the same number of additions (walking all buckets and testing the bit left
+// half the lanes of a warp idle for every t above the chunk length).
+ZK_D xyzz_t msm_reduce_bits_chunk(const xyzz_t* B, uint32_t c, uint32_t log_t, uint32_t t, uint32_t chunk) {
+    const uint32_t nset = t == c - 1 ? 1u : (1u << (c - 2));
+    uint32_t per = c >= 2 ? ((1u << (c - 2)) >> log_t) : 1u;
+    if (per == 0) per = 1;
+    const uint32_t s0 = chunk * per;
+    xyzz_t acc = xyzz_identity();
+    for (uint32_t s = s0; s < s0 + per && s < nset; ++s) {
+        const uint32_t v = ((s >> t) << (t + 1)) + (1u << t) + (s & ((1u << t) - 1u));
+        xyzz_add(acc, B[v - 1]);
+    }
+    return acc;
+}
 ZK_D void msm_reduce_bits_thread(const MsmArgs& a, uint32_t gid) {
     if (gid >= (a.c << a.log_t)) return;
     uint32_t t = gid >> a.log_t, chunk = gid & ((1u << a.log_t) - 1);
-    uint32_t m = (1u << (a.c - 1)) >> a.log_t, b0 = chunk * m;
-    xyzz_t acc = xyzz_identity();
-    for (uint32_t b = b0; b < b0 + m; ++b)
-        if (((b + 1) >> t) & 1) xyzz_add(acc, a.buckets[b]);
-    a.partials[gid] = acc;
+    a.partials[gid] = msm_reduce_bits_chunk(a.buckets, a.c, a.log_t, t, chunk);
 }
 
 // One block per window: sum the 2^log_t chunk results.  sm: nthreads xyzz_t.

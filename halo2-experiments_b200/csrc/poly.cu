@@ -6,7 +6,9 @@ namespace b200zk {
 
 static constexpr uint32_t POLY_THREADS = 128;
 static constexpr uint32_t SCAN_THREADS = 512;
-static constexpr size_t CHUNK = 64;
+// elements per thread of the chunked scans: 64 keeps the single-block carry scan short on long columns; a short column is one
+// thread's chain of dependent multiplications, so it gets 16
+static size_t chunk_for(size_t n) { return n <= ((size_t)1 << 16) ? 16 : 64; }
 
 template <class F> __global__ void __launch_bounds__(POLY_THREADS) batch_invert_kernel(fe_t* a, fe_t* scratch, size_t n, size_t lanes) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,6 +63,7 @@ int32_t batch_invert_run(b200zk_ctx* ctx, fe_t* d_a, size_t n, int field) {
 // The head is left in ctx->poly_heads[0] on the device; *head_out (host) is filled if non-null.
 int32_t recurrence_run(b200zk_ctx* ctx, const fe_t* d_a, fe_t* d_y, size_t n, const host::HFr& b, host::HFr* head_out) {
     if (n == 0) { if (head_out) *head_out = host::HFr::zero(); return B200ZK_OK; }
+    const size_t CHUNK = chunk_for(n);
     size_t C = (n + CHUNK - 1) / CHUNK;
     ZK_TRY(ws_reserve(ctx, ctx->poly_heads, 2 * C * sizeof(fe_t)));
     fe_t* heads = (fe_t*)ctx->poly_heads.p;
@@ -102,6 +105,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) recur_carries_batch_kernel(fe_t*
 int32_t eval_batch_run(b200zk_ctx* ctx, const fe_t* const* h_polys, const host::HFr* h_points, size_t Q, size_t n, host::HFr* out) {
     if (Q == 0) return B200ZK_OK;
     if (n == 0) { for (size_t q = 0; q < Q; ++q) out[q] = host::HFr::zero(); return B200ZK_OK; }
+    const size_t CHUNK = chunk_for(n);
     const size_t C = (n + CHUNK - 1) / CHUNK;
     size_t bytes = 2 * Q * C * sizeof(fe_t) + Q * (sizeof(fe_t) + sizeof(void*)) + 512;
     ZK_TRY(ws_reserve(ctx, ctx->poly_batch, bytes));
@@ -155,6 +159,7 @@ int32_t powers_run(b200zk_ctx* ctx, const host::HFr& base, size_t n, fe_t* d_out
 // z[0] = z0, z[i] = z[i-1] * p[i-1] for i < n  (z may alias p)
 int32_t prefix_product_run(b200zk_ctx* ctx, const fe_t* d_p, fe_t* d_z, size_t n, const host::HFr& z0) {
     if (n == 0) return B200ZK_OK;
+    const size_t CHUNK = chunk_for(n);
     size_t C = (n + CHUNK - 1) / CHUNK;
     ZK_TRY(ws_reserve(ctx, ctx->poly_heads, 2 * C * sizeof(fe_t)));
     fe_t* prods = (fe_t*)ctx->poly_heads.p;
