@@ -246,19 +246,89 @@ template <class C> struct Field {
         for (int k = 1; k < 7; ++k) r[k] = ptx::addc_cc(E[2 + k], O[1 + k]);
         r[7] = ptx::addc(E[9], O[8]);
     }
-    ZK_D static T mul_shoup(const T& x, const T& w, const T& wq) {
-        const uint32_t P[8] = {C::p(0), C::p(1), C::p(2), C::p(3), C::p(4), C::p(5), C::p(6), C::p(7)};
-        uint32_t q[8], t1[8], t2[8];
-        mul_high_approx(q, x.l, wq.l);
-        mul_low(t1, P, q);                                     // q * p mod 2^256 (p's limbs are immediates)
-        mul_low(t2, x.l, w.l);                                 // x * w mod 2^256
-        T r;
-        r.l[0] = ptx::sub_cc(t2[0], t1[0]);
+    // low 8 limbs of a * b + c * d: the rows of both products go into the same pair of accumulators
+    ZK_D static void mul_low2(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d) {
+        uint32_t E[8], O[9];
 #pragma unroll
-        for (int i = 1; i < 7; ++i) r.l[i] = ptx::subc_cc(t2[i], t1[i]);
-        r.l[7] = ptx::subc(t2[7], t1[7]);
+        for (int i = 0; i < 8; ++i) E[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) O[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int je = i & 1, jo = (i & 1) ^ 1;
+            mad_chain(E, i, a, b[i], je, 8 - i, false, false);
+            mad_chain(O, i, a, b[i], jo, 8 - i, true, false);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int je = i & 1, jo = (i & 1) ^ 1;
+            mad_chain(E, i, c, d[i], je, 8 - i, false, false);
+            mad_chain(O, i, c, d[i], jo, 8 - i, true, false);
+        }
+        r[0] = E[0];
+        r[1] = ptx::add_cc(E[1], O[1]);
+#pragma unroll
+        for (int k = 2; k < 7; ++k) r[k] = ptx::addc_cc(E[k], O[k]);
+        r[7] = ptx::addc(E[7], O[7]);
+    }
+    ZK_D static constexpr uint32_t neg_p(int i) {             // limb i of 2^256 - p
+        return i == 0 ? 0u - C::p(0) : ~C::p(i);             // p(0) != 0: the borrow never propagates
+    }
+    ZK_D static constexpr uint32_t two_p(int i) {             // limb i of 2p (< 2^255)
+        return i == 0 ? C::p(0) << 1 : (C::p(i) << 1) | (C::p(i - 1) >> 31);
+    }
+    // x * w - q * p  (mod 2^256), in [0, 3p):  the subtraction is folded into the product as + q * (2^256 - p)
+    ZK_D static T mul_shoup_raw(const T& x, const T& w, const T& wq) {
+        const uint32_t NP[8] = {neg_p(0), neg_p(1), neg_p(2), neg_p(3), neg_p(4), neg_p(5), neg_p(6), neg_p(7)};
+        uint32_t q[8];
+        mul_high_approx(q, x.l, wq.l);
+        T r;
+        mul_low2(r.l, x.l, w.l, NP, q);                        // (2^256 - p)'s limbs are immediates
+        return r;
+    }
+    ZK_D static T mul_shoup(const T& x, const T& w, const T& wq) {
+        T r = mul_shoup_raw(x, w, wq);
         reduce_once(r);
         reduce_once(r);
+        return r;
+    }
+    // ---- the same with values kept in [0, 2p) between operations (the butterflies of a transform pass) ----------------
+    // Any x < 2^256 is a valid first operand of mul_shoup, and 4p < 2^256, so a pass can carry its values in [0, 2p): a
+    // product needs one conditional subtraction instead of two, a sum one (of 2p), a difference that goes straight into a
+    // product none; the pass that writes the final result reduces once more on the way out.
+    ZK_D static void reduce_2p(T& a) {                        // a - 2p if a >= 2p else a     (a < 4p)
+        uint32_t t[8];
+        t[0] = ptx::sub_cc(a.l[0], two_p(0));
+#pragma unroll
+        for (int i = 1; i < 8; ++i) t[i] = ptx::subc_cc(a.l[i], two_p(i));
+        uint32_t borrow = ptx::subc(0, 0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a.l[i] = borrow ? a.l[i] : t[i];
+    }
+    ZK_D static T mul_shoup_lazy(const T& x, const T& w, const T& wq) {   // x < 2^256 -> [0, 2p)
+        T r = mul_shoup_raw(x, w, wq);
+        reduce_once(r);
+        return r;
+    }
+    ZK_D static T add_lazy(const T& a, const T& b) {         // a, b in [0, 2p) -> [0, 2p)
+        T r;
+        r.l[0] = ptx::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) r.l[i] = ptx::addc_cc(a.l[i], b.l[i]);
+        r.l[7] = ptx::addc(a.l[7], b.l[7]);
+        reduce_2p(r);
+        return r;
+    }
+    ZK_D static T sub_raw(const T& a, const T& b) {          // a, b in [0, 2p) -> a - b + 2p in (0, 4p)
+        T r;
+        r.l[0] = ptx::sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) r.l[i] = ptx::subc_cc(a.l[i], b.l[i]);
+        r.l[7] = ptx::subc(a.l[7], b.l[7]);
+        r.l[0] = ptx::add_cc(r.l[0], two_p(0));
+#pragma unroll
+        for (int i = 1; i < 7; ++i) r.l[i] = ptx::addc_cc(r.l[i], two_p(i));
+        r.l[7] = ptx::addc(r.l[7], two_p(7));
         return r;
     }
 

@@ -41,11 +41,17 @@ template <int LAYOUT> __device__ __forceinline__ void ntt_warp_get(const half_t*
 #pragma unroll
     for (uint32_t e = 0; e < 4; ++e) x[e] = tile_ld(sm, 128, ntt_warp_slot(ntt_warp_u<LAYOUT>(lane, e)));
 }
-// d * (table entry ix): CIOS against the Montgomery-form table, or the constant-operand product against the {w, wq} table
+// d * (table entry ix): CIOS against the Montgomery-form table, or the constant-operand product against the {w, wq} table.
+// With the constant-operand multiplier the values of a pass live in [0, 2p) (Field::mul_shoup_lazy): LAZY butterflies.
 template <bool SHOUP> __device__ __forceinline__ fe_t ntt_warp_mul_root(const NttPassArgs& a, const fe_t& d, size_t ix) {
-    if (SHOUP) { const fe2_t t = a.roots_s[ix]; return Fr::mul_shoup(d, t.w, t.wq); }
+    if (SHOUP) { const fe2_t t = a.roots_s[ix]; return Fr::mul_shoup_lazy(d, t.w, t.wq); }
     return Fr::mul(d, a.roots[ix]);
 }
+template <bool LAZY> __device__ __forceinline__ fe_t ntt_bf_add(const fe_t& x, const fe_t& y) { return LAZY ? Fr::add_lazy(x, y) : Fr::add(x, y); }
+// difference that feeds a multiplication (LAZY: left in (0, 4p)) ...
+template <bool LAZY> __device__ __forceinline__ fe_t ntt_bf_sub_raw(const fe_t& x, const fe_t& y) { return LAZY ? Fr::sub_raw(x, y) : Fr::sub(x, y); }
+// ... and the same value when it is kept as it is
+template <bool LAZY> __device__ __forceinline__ fe_t ntt_bf_keep(fe_t d) { if (LAZY) Fr::reduce_2p(d); return d; }
 template <int LAYOUT, int B, int EB, bool SHOUP>
 __device__ __forceinline__ void ntt_warp_stage(const NttPassArgs& a, uint32_t lane, uint32_t log_tw, fe_t (&x)[4]) {
     if ((uint32_t)B < log_tw) return;
@@ -55,8 +61,9 @@ __device__ __forceinline__ void ntt_warp_stage(const NttPassArgs& a, uint32_t la
         if (e0 & (1u << EB)) continue;
         const uint32_t e1 = e0 | (1u << EB);
         const uint32_t j = (ntt_warp_u<LAYOUT>(lane, e0) >> log_tw) & ((1u << lh) - 1u);
-        fe_t s = Fr::add(x[e0], x[e1]), d = Fr::sub(x[e0], x[e1]);
+        fe_t s = ntt_bf_add<SHOUP>(x[e0], x[e1]), d = ntt_bf_sub_raw<SHOUP>(x[e0], x[e1]);
         if (j != 0) d = ntt_warp_mul_root<SHOUP>(a, d, (size_t)j << (a.log_roots - lh - 1));
+        else d = ntt_bf_keep<SHOUP>(d);
         x[e0] = s; x[e1] = d;
     }
 }
@@ -125,14 +132,15 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
         // multiplications with half its lanes idle.  The odd lane hands one of its differences to its even
         // neighbour instead: every lane multiplies exactly once.
         const bool odd = lane & 1u;
-        fe_t s0 = Fr::add(x[0], x[1]), d0 = Fr::sub(x[0], x[1]), s1 = Fr::add(x[2], x[3]), d1 = Fr::sub(x[2], x[3]);
+        fe_t s0 = ntt_bf_add<SHOUP>(x[0], x[1]), d0 = ntt_bf_sub_raw<SHOUP>(x[0], x[1]);
+        fe_t s1 = ntt_bf_add<SHOUP>(x[2], x[3]), d1 = ntt_bf_sub_raw<SHOUP>(x[2], x[3]);
         fe_t y;
 #pragma unroll
         for (int i = 0; i < 8; ++i) y.l[i] = __shfl_xor_sync(0xffffffffu, d1.l[i], 1);
         fe_t prod = ntt_warp_mul_root<SHOUP>(a, odd ? d0 : y, (size_t)1 << (a.log_roots - 2));
 #pragma unroll
         for (int i = 0; i < 8; ++i) y.l[i] = __shfl_xor_sync(0xffffffffu, prod.l[i], 1);
-        x[0] = s0; x[1] = odd ? prod : d0; x[2] = s1; x[3] = odd ? y : d1;
+        x[0] = s0; x[1] = odd ? prod : ntt_bf_keep<SHOUP>(d0); x[2] = s1; x[3] = odd ? y : ntt_bf_keep<SHOUP>(d1);
     } else {
         ntt_warp_stage<2, 1, 0, SHOUP>(a, lane, log_tw, x);
     }
@@ -143,7 +151,7 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
             fe_t y;
 #pragma unroll
             for (int i = 0; i < 8; ++i) y.l[i] = __shfl_xor_sync(0xffffffffu, x[e].l[i], 1);
-            x[e] = odd ? Fr::sub(y, x[e]) : Fr::add(x[e], y);
+            x[e] = odd ? ntt_bf_keep<SHOUP>(ntt_bf_sub_raw<SHOUP>(y, x[e])) : ntt_bf_add<SHOUP>(x[e], y);
         }
     }
     }   // live
@@ -159,11 +167,12 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
             g = ((size_t)h << (a.log_m + a.log_l)) + ((size_t)k << a.log_l) + l;
             uint64_t E = ((uint64_t)(l + a.l_offset) * k) << a.tw_shift;
             if (E && live) {
-                if (SHOUP) { const fe2_t t = a.tw_full_s[(uint32_t)E]; v = Fr::mul_shoup(v, t.w, t.wq); }
+                if (SHOUP) { const fe2_t t = a.tw_full_s[(uint32_t)E]; v = Fr::mul_shoup_lazy(v, t.w, t.wq); }
                 else v = Fr::mul(v, ntt_twiddle(a, (uint32_t)E));
             }
         } else {
             g = (size_t)(k1_0 + c) + ((size_t)rho_mid << a.log_m1) + ((size_t)k << (a.log_m1 + a.log_mid));
+            if (SHOUP) Fr::reduce_once(v);                     // [0, 2p) -> the canonical value leaves the transform
             if (a.use_post && live) v = Fr::mul(v, a.post[g % 3]);
             g += batch_base;
         }

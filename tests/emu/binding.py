@@ -149,3 +149,13 @@ def mul_shoup(which, x, w, wq):
     out = np.zeros_like(x)
     lib().emu_mul_shoup(which, _p(x), _p(w), _p(wq), _p(out), ctypes.c_size_t(x.shape[0]))
     return out
+
+
+def lazy_op(which, mode, x, w=None, wq=None):
+    """The [0, 2p) forms of a transform pass (Field::mul_shoup_lazy / add_lazy / sub_raw / reduce_2p); raw limb arrays."""
+    x = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1, 4)
+    w = x if w is None else np.ascontiguousarray(w, dtype=np.uint64).reshape(-1, 4)
+    wq = x if wq is None else np.ascontiguousarray(wq, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros_like(x)
+    lib().emu_lazy_op(which, {"mul": 0, "add": 1, "sub": 2, "reduce": 3}[mode], _p(x), _p(w), _p(wq), _p(out), ctypes.c_size_t(x.shape[0]))
+    return out

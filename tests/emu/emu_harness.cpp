@@ -51,6 +51,23 @@ void emu_mul_shoup(int which, const fe_t* x, const fe_t* w, const fe_t* wq, fe_t
     for (size_t i = 0; i < n; ++i) out[i] = which == 0 ? Fr::mul_shoup(x[i], w[i], wq[i]) : Fq::mul_shoup(x[i], w[i], wq[i]);
 }
 
+// the [0, 2p) forms used inside a transform pass: mode 0 mul_shoup_lazy(x, w, wq), 1 add_lazy(x, w), 2 sub_raw(x, w), 3 reduce_2p(x)
+void emu_lazy_op(int which, int mode, const fe_t* x, const fe_t* w, const fe_t* wq, fe_t* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        if (which == 0) {
+            if (mode == 0) out[i] = Fr::mul_shoup_lazy(x[i], w[i], wq[i]);
+            else if (mode == 1) out[i] = Fr::add_lazy(x[i], w[i]);
+            else if (mode == 2) out[i] = Fr::sub_raw(x[i], w[i]);
+            else { out[i] = x[i]; Fr::reduce_2p(out[i]); }
+        } else {
+            if (mode == 0) out[i] = Fq::mul_shoup_lazy(x[i], w[i], wq[i]);
+            else if (mode == 1) out[i] = Fq::add_lazy(x[i], w[i]);
+            else if (mode == 2) out[i] = Fq::sub_raw(x[i], w[i]);
+            else { out[i] = x[i]; Fq::reduce_2p(out[i]); }
+        }
+    }
+}
+
 void emu_field_consts(int which, fe_t* one, fe_t* r2) {
     if (which == 0) { *one = Fr::one(); *r2 = Fr::r2(); } else { *one = Fq::one(); *r2 = Fq::r2(); }
 }

@@ -52,6 +52,31 @@ def test_constant_operand_multiplication(orc, which):
 
 
 @pytest.mark.parametrize("which", [0, 1])
+def test_lazy_range_arithmetic(orc, which):
+    """The [0, 2p) arithmetic of a warp-level transform pass: mul_shoup_lazy takes ANY x < 2^256 and returns x w mod p as a
+    value below 2p; add_lazy keeps [0, 2p); sub_raw returns a - b + 2p (below 4p, fed to the multiplier unreduced);
+    reduce_2p brings [0, 4p) back below 2p."""
+    p = P.R_MOD if which == 0 else P.Q_MOD
+    rnd = random.Random(60 + which)
+    edge = [0, 1, p - 1, p, p + 1, 2 * p - 1, 2 * p, 4 * p - 1, (1 << 256) - 1, (1 << 255), 3 * p]
+    ws_e = [0, 1, 2, p - 1, p >> 1, (1 << 253) % p]
+    xs = [a for a in edge for _ in ws_e] + [rnd.randrange(1 << 256) for _ in range(3000)] + [rnd.randrange(4 * p) for _ in range(1000)]
+    ws = [b for _ in edge for b in ws_e] + [rnd.randrange(p) for _ in range(4000)]
+    wq = [(w << 256) // p for w in ws]
+    got = orc.raw_to_ints(emu.lazy_op(which, "mul", orc.ints_to_raw(xs), orc.ints_to_raw(ws), orc.ints_to_raw(wq)))
+    assert all(g < 2 * p for g in got)
+    assert [g % p for g in got] == [x * w % p for x, w in zip(xs, ws)]
+    a = [rnd.randrange(2 * p) for _ in range(2000)] + [0, 2 * p - 1, 0, 2 * p - 1, p, p]
+    b = [rnd.randrange(2 * p) for _ in range(2000)] + [0, 2 * p - 1, 2 * p - 1, 0, p, 0]
+    s = orc.raw_to_ints(emu.lazy_op(which, "add", orc.ints_to_raw(a), orc.ints_to_raw(b)))
+    assert all(v < 2 * p for v in s) and [v % p for v in s] == [(x + y) % p for x, y in zip(a, b)]
+    d = orc.raw_to_ints(emu.lazy_op(which, "sub", orc.ints_to_raw(a), orc.ints_to_raw(b)))
+    assert d == [x - y + 2 * p for x, y in zip(a, b)]
+    r = orc.raw_to_ints(emu.lazy_op(which, "reduce", orc.ints_to_raw(d)))
+    assert all(v < 2 * p for v in r) and [v % p for v in r] == [v % p for v in d]
+
+
+@pytest.mark.parametrize("which", [0, 1])
 def test_division_step_inversion(orc, which):
     """Field::inv_gcd (the inversion inside batch_invert): x^-1 in Montgomery form, identical to the Fermat chain Field::inv
     and to pow(x, p - 2); 0 -> 0.  Edge values sit at limb boundaries of the 9 x 30-bit state."""
