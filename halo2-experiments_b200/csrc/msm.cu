@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_reduce_bits_tree_kernel(c
     const uint32_t col = blockIdx.x / blocks_per_set;
     const uint32_t gid = (blockIdx.x % blocks_per_set) * blockDim.x + threadIdx.x;     // (bit t, chunk) inside the column
     const uint32_t t = gid >> a.log_t, chunk = gid & ((1u << a.log_t) - 1);
-    sm[threadIdx.x] = msm_reduce_bits_chunk(a.buckets + (size_t)col * a.set_buckets, a.c, a.log_t, t, chunk);
+    sm[threadIdx.x] = msm_reduce_bits_chunk(a.buckets + (size_t)col * a.set_buckets, a.counts + (size_t)col * a.set_buckets, a.c, a.log_t, t, chunk);
     __syncthreads();
     for (uint32_t s = MSM_ACC_THREADS >> 1; s > 0; s >>= 1) {
         if (threadIdx.x < s) { xyzz_t v = sm[threadIdx.x]; xyzz_add(v, sm[threadIdx.x + s]); sm[threadIdx.x] = v; }
@@ -247,7 +247,10 @@ int32_t msm_run_multi(b200zk_ctx* ctx, const fe_t* const* d_cols, uint32_t ncols
 
     uint32_t fast_max = MSM_FAST_MAX;
     if (const char* e = getenv("B200ZK_MSM_FAST_MAX")) fast_max = (uint32_t)strtoul(e, nullptr, 10);
-    uint32_t seg_min = n < ((size_t)1 << 18) ? 8 : 16;      // short columns are latency bound: shorter chains, one more level
+    // short columns are latency bound: shorter chains, one more level; long ones: 24 leaves a uniform 2^20 column (240 entries per
+    // bucket) with 10 partials per bucket, summed directly (16: 129.2 ms per k = 20 proof, 24: 128.7, 32: 129.0, 48: 130.0).
+    // (A warp per task of 256 entries with a shuffle tree was tried for the short columns: no gain, k = 14 proof 6.8 vs 6.4 ms.)
+    uint32_t seg_min = n < ((size_t)1 << 18) ? 8 : 24;
     if (const char* e = getenv("B200ZK_MSM_SEG_MIN")) seg_min = (uint32_t)strtoul(e, nullptr, 10);
     if (maxcnt <= fast_max) {
         msm_accumulate_kernel<<<nb(B, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, st>>>(a);

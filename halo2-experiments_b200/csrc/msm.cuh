@@ -292,7 +292,9 @@ ZK_D void msm_reduce_thread(const MsmArgs& a, uint32_t gid) {
 // 2^(c-2) of them below 2^(c-1) for t < c - 1, and the single v = 2^(c-1) for t = c - 1.  Chunk `chunk` of 2^log_t sums an equal
 // share of that list, so every lane of a warp has the same number of additions (walking all buckets and testing the bit left
 // half the lanes of a warp idle for every t above the chunk length).
-ZK_D xyzz_t msm_reduce_bits_chunk(const xyzz_t* B, uint32_t c, uint32_t log_t, uint32_t t, uint32_t chunk) {
+// `counts` (the histogram of the same bucket set) lets an empty bucket cost a 4-byte read instead of a 128-byte one: the witness
+// columns of a padded circuit fill a few hundred of the 2^(c-1) buckets.
+ZK_D xyzz_t msm_reduce_bits_chunk(const xyzz_t* B, const uint32_t* counts, uint32_t c, uint32_t log_t, uint32_t t, uint32_t chunk) {
     const uint32_t nset = t == c - 1 ? 1u : (1u << (c - 2));
     uint32_t per = c >= 2 ? ((1u << (c - 2)) >> log_t) : 1u;
     if (per == 0) per = 1;
@@ -300,6 +302,7 @@ ZK_D xyzz_t msm_reduce_bits_chunk(const xyzz_t* B, uint32_t c, uint32_t log_t, u
     xyzz_t acc = xyzz_identity();
     for (uint32_t s = s0; s < s0 + per && s < nset; ++s) {
         const uint32_t v = ((s >> t) << (t + 1)) + (1u << t) + (s & ((1u << t) - 1u));
+        if (counts[v - 1] == 0) continue;
         xyzz_add(acc, B[v - 1]);
     }
     return acc;
@@ -307,7 +310,7 @@ ZK_D xyzz_t msm_reduce_bits_chunk(const xyzz_t* B, uint32_t c, uint32_t log_t, u
 ZK_D void msm_reduce_bits_thread(const MsmArgs& a, uint32_t gid) {
     if (gid >= (a.c << a.log_t)) return;
     uint32_t t = gid >> a.log_t, chunk = gid & ((1u << a.log_t) - 1);
-    a.partials[gid] = msm_reduce_bits_chunk(a.buckets, a.c, a.log_t, t, chunk);
+    a.partials[gid] = msm_reduce_bits_chunk(a.buckets, a.counts, a.c, a.log_t, t, chunk);
 }
 
 // One block per window: sum the 2^log_t chunk results.  sm: nthreads xyzz_t.
