@@ -107,7 +107,7 @@ static int32_t build_plan(b200zk_ctx* ctx, uint32_t log_n, const host::HFr& omeg
         long v = strtol(e, nullptr, 10);
         return (v < (long)lo || v > (long)hi) ? dflt : (uint32_t)v;
     };
-    plan.warp = ntt_warp_eligible(log_n, tune("B200ZK_NTT_WARP_MAX", 21, 0, 24));
+    plan.warp = ntt_warp_eligible(log_n, tune("B200ZK_NTT_WARP_MAX", 26, 0, 28));
     plan.shape = plan.warp ? ntt_plan_shape_warp(log_n)
                            : ntt_plan_shape(log_n, tune("B200ZK_NTT_MAX_M", NTT_MAX_LOG_M, 2, 12),
                                             tune("B200ZK_NTT_MAX_TW", NTT_MAX_LOG_TW, 0, 5), tune("B200ZK_NTT_TILE_CAP", NTT_TILE_CAP_LOG, 6, 12));
@@ -201,7 +201,7 @@ static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, f
         a.in = p == 0 ? d_in : scratch;
         a.out = q.is_last ? d_out : scratch;
         a.log_n = log_n; a.log_m = q.log_m; a.log_l = q.log_l; a.log_tw = q.log_tw; a.is_last = q.is_last;
-        a.log_m1 = q.log_m1; a.log_mid = q.log_mid;
+        a.log_m1 = q.log_m1; a.log_mid = q.log_mid; a.log_m3 = q.log_m3;
         a.n_in = batch > 1 ? (uint32_t)(N * batch) : (p == 0 ? n_in : (uint32_t)N);
         a.batch_tiles = (batch > 1 && q.is_last) ? q.blocks : 0;
         a.use_pre = (p == 0 && pre) ? 1 : 0;

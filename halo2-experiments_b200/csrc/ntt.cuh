@@ -38,6 +38,7 @@ struct NttPassArgs {
     uint32_t is_last;
     // last pass only: digits of the row index.  log_m1 = slowest digit, log_mid = the rest.
     uint32_t log_m1, log_mid;
+    uint32_t log_m3;        // four-pass plans of the warp-level kernel: the third digit's size (faster half of the middle bits), else 0
     uint32_t n_in;          // first pass: elements beyond n_in read as zero (n_in = N otherwise)
     uint32_t use_pre, use_post;
     fe_t pre[3], post[3];   // multiplied by index mod 3 on load (first pass) / store (last pass)
@@ -181,7 +182,7 @@ ZK_D void ntt_pass_block(const NttPassArgs& a, uint32_t bid, uint32_t nthreads, 
             }
         } else {
             // out index = k_1 + M_1 * rev(rho') + (M_1 * mid) * k ; mid digit order is preserved
-            // because P <= 3 passes use a single middle digit (asserted on the host).
+            // (block plans have at most 3 passes: a single middle digit; the warp-level kernel handles two, ntt_warp.cuh)
             g = (size_t)(k1_0 + c) + ((size_t)rho_mid << a.log_m1) + ((size_t)k << (a.log_m1 + a.log_mid));
             if (a.use_post) v = Fr::mul(v, a.post[g % 3]);
             g += batch_base;

@@ -7,11 +7,12 @@ namespace b200zk {
 
 struct NttPassShape {
     uint32_t log_m, log_l, log_tw, is_last, log_m1, log_mid, blocks;
+    uint32_t log_m3;         // four passes: size of the third digit (the faster half of the log_mid middle bits); else 0
 };
 
 struct NttShape {
     uint32_t log_n, npass;
-    NttPassShape pass[3];
+    NttPassShape pass[4];
     uint32_t log_roots;      // roots table = w_R^j, j < R/2
     uint32_t tw_lo_bits;     // two-level twiddle split
 };
@@ -48,8 +49,8 @@ inline NttShape ntt_plan_shape(uint32_t log_n, uint32_t max_log_m, uint32_t max_
 }
 
 // Plan for the warp-level kernel (ntt_warp.cuh): every pass is a 2^4..2^7-point transform on
-// tiles of 128 elements (TW = 128 / M columns), at most three passes -> 12 <= log_n <= 21.
-inline bool ntt_warp_eligible(uint32_t log_n, uint32_t max_log = 21) { return log_n >= 12 && log_n <= 21 && log_n <= max_log; }
+// tiles of 128 elements (TW = 128 / M columns); three passes cover 2^21, four cover 2^28.
+inline bool ntt_warp_eligible(uint32_t log_n, uint32_t max_log = 26) { return log_n >= 12 && log_n <= 28 && log_n <= max_log; }
 
 inline NttShape ntt_plan_shape_warp(uint32_t log_n) {
     const uint32_t tile_log = 7;
@@ -57,7 +58,7 @@ inline NttShape ntt_plan_shape_warp(uint32_t log_n) {
     s.log_n = log_n;
     uint32_t P = (log_n + tile_log - 1) / tile_log;
     s.npass = P;
-    uint32_t base = log_n / P, rem = log_n % P, d[3] = {0, 0, 0};
+    uint32_t base = log_n / P, rem = log_n % P, d[4] = {0, 0, 0, 0};
     for (uint32_t p = 0; p < P; ++p) d[p] = base + (p < rem ? 1 : 0);
     uint32_t log_l = log_n;
     for (uint32_t p = 0; p < P; ++p) {
@@ -67,7 +68,9 @@ inline NttShape ntt_plan_shape_warp(uint32_t log_n) {
         q.log_l = log_l;
         q.is_last = (p + 1 == P);
         q.log_m1 = P > 1 ? d[0] : 0;
-        q.log_mid = P == 3 ? d[1] : 0;
+        // the last pass sees the middle digits as one index (second digit slower); it stores them digit-reversed
+        q.log_mid = P == 3 ? d[1] : P == 4 ? d[1] + d[2] : 0;
+        q.log_m3 = P == 4 ? d[2] : 0;
         q.log_tw = tile_log - d[p];
         q.blocks = 1u << (log_n - tile_log);            // warp tiles
     }

@@ -15,8 +15,11 @@
 //
 // No block-level barrier anywhere; 80 registers per thread, 24 resident warps per SM.  Measured on
 // B200 (profiles/r01_ntt_warp_vs_block.txt): 2^16 0.037 vs 0.064 ms, 2^20 0.235 vs 0.284 ms,
-// 2^21 0.478 vs 0.505 ms against the block kernel.  Three passes of at most 7 bits cover 2^21;
-// beyond that the block kernel runs.  (A variant with 8 elements per lane — 128 registers, 16
+// 2^21 0.478 vs 0.505 ms against the block kernel.  Three passes of at most 7 bits cover 2^21, four
+// cover 2^28 (round 2: the last pass then stores its two middle digits swapped, see the store phase): with
+// the constant-operand multiplier and the [0, 2p) butterflies this kernel outruns the block kernel at every
+// size — 2^22 0.81 vs 1.19 ms, 2^24 3.25 vs 3.85 ms, 2^26 15.7 vs 19.2 ms — so the block kernel is left with
+// the sizes below 2^12 and the column step of the sharded four-step.  (A variant with 8 elements per lane — 128 registers, 16
 // warps per SM, 288 KB of code — was slower than both from 2^21 up and is not kept.)
 #pragma once
 #include "ntt.cuh"
@@ -171,7 +174,9 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
                 else v = Fr::mul(v, ntt_twiddle(a, (uint32_t)E));
             }
         } else {
-            g = (size_t)(k1_0 + c) + ((size_t)rho_mid << a.log_m1) + ((size_t)k << (a.log_m1 + a.log_mid));
+            // natural output index k1 + M1 k2 (+ M1 M2 k3) + M1 M_mid k: with four passes the row index carries k2 above k3
+            g = (size_t)(k1_0 + c) + ((size_t)(rho_mid >> a.log_m3) << a.log_m1) +
+                ((size_t)(rho_mid & ((1u << a.log_m3) - 1u)) << (a.log_m1 + a.log_mid - a.log_m3)) + ((size_t)k << (a.log_m1 + a.log_mid));
             if (SHOUP) Fr::reduce_once(v);                     // [0, 2p) -> the canonical value leaves the transform
             if (a.use_post && live) v = Fr::mul(v, a.post[g % 3]);
             g += batch_base;
