@@ -299,7 +299,7 @@ def run_gpu(args):
             import torch
             sharded = importlib.import_module(zk.__name__ + ".sharded")
             dev = torch.device("cuda", local)
-            log_r = min(10, L // 2)
+            log_r = int(os.environ.get("B200ZK_FOURSTEP_LOG_R", min(7, L // 2)))   # R = 128: the column step is one warp-kernel pass
             # default: the exchange fused into the column-step kernel (NVLink peer stores, CUDA IPC);
             # B200ZK_NTT_NCCL=1 selects the NCCL all-to-all path
             fused = os.environ.get("B200ZK_NTT_NCCL", "0") != "1"
@@ -551,7 +551,7 @@ def sharded_sweep(zk, be, dist, rank, world, local, args):
 
     # ---- NTT: verify at Lv, time at L
     def ntt_at(L, reps, check):
-        log_r = min(10, L // 2)
+        log_r = int(os.environ.get("B200ZK_FOURSTEP_LOG_R", min(7, L // 2)))       # R = 128: the column step is one warp-kernel pass
         R, C = 1 << log_r, 1 << (L - log_r)
         omega = zk.EvaluationDomain(be, 2, L).omega
         if world == 1:

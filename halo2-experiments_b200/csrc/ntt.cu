@@ -264,6 +264,26 @@ int32_t ntt_colstep_run(b200zk_ctx* ctx, fe_t* d_block, uint32_t log_r, uint32_t
         ntt_pow_table_kernel<<<(unsigned)((n_lo + 127) / 128), 128, 0, ctx->stream>>>(plan.tw_lo, to_dev(omega_n), (uint32_t)n_lo, 0);
         ntt_pow_table_kernel<<<(unsigned)((n_hi + 127) / 128), 128, 0, ctx->stream>>>(plan.tw_hi, to_dev(omega_n), (uint32_t)n_hi, plan.shape.tw_lo_bits);
         ctx->launches += 3;
+        // R <= 128: the column step is ONE pass of the warp-level kernel (tiles of R points x 128 / R columns) and gets its
+        // constant-operand tables — the twiddle records of the whole transform, omega_n^E for E < N — when they fit
+        plan.warp = log_r >= 4 && log_r <= NTT_WARP_TILE_LOG;
+        const char* es = getenv("B200ZK_NTT_SHOUP");
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (plan.warp && !(es && es[0] == '0') && log_n <= 26 && (sizeof(fe_t) << log_n) * 8 < free_b) {
+            const size_t N = (size_t)1 << log_n;
+            if (cudaMalloc(&plan.tw_full, N * sizeof(fe_t)) == cudaSuccess && cudaMalloc(&plan.tw_full_s, N * sizeof(fe2_t)) == cudaSuccess &&
+                cudaMalloc(&plan.roots_s, n_roots * sizeof(fe2_t)) == cudaSuccess) {
+                ntt_tw_full_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(plan.tw_full, N, plan.tw_lo, plan.tw_hi, plan.shape.tw_lo_bits);
+                ntt_shoup_table_kernel<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(plan.tw_full, plan.tw_full_s, N);
+                ntt_shoup_table_kernel<<<(unsigned)((n_roots + 127) / 128), 128, 0, ctx->stream>>>(plan.roots, plan.roots_s, n_roots);
+                ctx->launches += 3;
+            } else {
+                cudaGetLastError();
+                cudaFree(plan.tw_full); cudaFree(plan.tw_full_s); cudaFree(plan.roots_s);
+                plan.tw_full = nullptr; plan.tw_full_s = nullptr; plan.roots_s = nullptr;
+            }
+        }
         it = ctx->ntt_plans.emplace(key, plan).first;
     }
     const NttPlan& plan = it->second;
@@ -280,16 +300,23 @@ int32_t ntt_colstep_run(b200zk_ctx* ctx, fe_t* d_block, uint32_t log_r, uint32_t
     a.n_in = 1u << (log_r + log_cg);
     a.roots = plan.roots; a.log_roots = log_r;
     a.tw_lo = plan.tw_lo; a.tw_hi = plan.tw_hi; a.tw_lo_bits = plan.shape.tw_lo_bits;
+    a.tw_full = plan.tw_full; a.roots_s = plan.roots_s; a.tw_full_s = plan.tw_full_s;
     a.tw_shift = 0; a.l_offset = col0;              // exponent (col0 + c) * k_r < C * R = N
+    a.canonical_out = 1;
     if (peer_rows) {                                // fused all-to-all: row k -> rank k / (R / world), see NttPassArgs
         if (world == 0 || world > 8 || (world & (world - 1)) || ((1u << log_r) % world)) return fail(ctx, B200ZK_EINVAL, "ntt_colstep", "world must be a power of two <= 8 dividing R");
         uint32_t lw = 0; while ((1u << lw) < world) ++lw;
         a.scatter = 1; a.log_rows_per_rank = log_r - lw; a.log_c_total = log_n - log_r;
         for (uint32_t j = 0; j < world; ++j) a.peers[j] = peer_rows[j];
     }
-    uint32_t tile = 1u << (a.log_m + a.log_tw);
-    uint32_t threads = tile / 2 < NTT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : NTT_THREADS;
-    ntt_pass_kernel<<<1u << (log_cg - a.log_tw), threads, sizeof(fe_t) << (a.log_m + a.log_tw), ctx->stream>>>(a);
+    if (plan.warp && log_cg >= NTT_WARP_TILE_LOG - log_r) {
+        a.log_tw = NTT_WARP_TILE_LOG - log_r;
+        ntt_warp_launch(ctx, a, 1u << (log_r + log_cg - NTT_WARP_TILE_LOG), false);
+    } else {
+        uint32_t tile = 1u << (a.log_m + a.log_tw);
+        uint32_t threads = tile / 2 < NTT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : NTT_THREADS;
+        ntt_pass_kernel<<<1u << (log_cg - a.log_tw), threads, sizeof(fe_t) << (a.log_m + a.log_tw), ctx->stream>>>(a);
+    }
     ctx->launches++;
     ZK_CUDA(ctx, cudaGetLastError());
     return B200ZK_OK;

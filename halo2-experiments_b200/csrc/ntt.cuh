@@ -57,6 +57,7 @@ struct NttPassArgs {
     // memory of the rank that owns it (peer pointers over NVLink / NVSwitch, CUDA IPC), at
     // [k mod rows_per_rank][global column]; no staging buffer, no separate exchange.
     uint32_t scatter, log_rows_per_rank, log_c_total;
+    uint32_t canonical_out; // warp-level kernel: this non-last pass is the end of a call (column step) — reduce its [0, 2p) values to [0, p)
     fe_t* peers[8];
     // Constant-operand (Shoup) form of the two twiddle tables — {plain value, floor(value * 2^256 / r)} records, see
     // Field::mul_shoup — used by the warp-level kernel when non-null: every multiplication of a pass is by a table entry.

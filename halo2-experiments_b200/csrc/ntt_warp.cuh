@@ -173,6 +173,12 @@ __device__ __forceinline__ void ntt_pass_warp(const NttPassArgs& a, uint32_t wid
                 if (SHOUP) { const fe2_t t = a.tw_full_s[(uint32_t)E]; v = Fr::mul_shoup_lazy(v, t.w, t.wq); }
                 else v = Fr::mul(v, ntt_twiddle(a, (uint32_t)E));
             }
+            if (SHOUP && a.canonical_out) Fr::reduce_once(v);  // column step: what leaves the call is canonical
+            if (a.scatter) {                                   // sharded four-step column step: row k to its owner (NttPassArgs::scatter)
+                const uint32_t dest = k >> a.log_rows_per_rank, row = k & ((1u << a.log_rows_per_rank) - 1u);
+                a.peers[dest][((size_t)row << a.log_c_total) + l + a.l_offset] = v;
+                continue;
+            }
         } else {
             // natural output index k1 + M1 k2 (+ M1 M2 k3) + M1 M_mid k: with four passes the row index carries k2 above k3
             g = (size_t)(k1_0 + c) + ((size_t)(rho_mid >> a.log_m3) << a.log_m1) +

@@ -331,7 +331,7 @@ def test_commit_many_matches_single_commits(zk, backend, orc, lagrange):
     params.close()
 
 
-@pytest.mark.parametrize("log_n,log_r,world", [(10, 4, 2), (12, 6, 4), (16, 8, 8), (20, 10, 8)])
+@pytest.mark.parametrize("log_n,log_r,world", [(10, 4, 2), (12, 6, 4), (16, 8, 8), (20, 10, 8), (16, 5, 2), (20, 7, 8)])
 def test_four_step_sharded_ntt_kernels(zk, backend, orc, log_n, log_r, world):
     """Column step / row step kernels of the sharded four-step NTT, with the `world` ranks emulated
     one after another on one GPU and the all-to-all done on the host; result = best_fft."""
@@ -357,7 +357,7 @@ def test_four_step_sharded_ntt_kernels(zk, backend, orc, log_n, log_r, world):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("log_n,log_r,world", [(10, 4, 2), (14, 6, 4), (18, 10, 8)])
+@pytest.mark.parametrize("log_n,log_r,world", [(10, 4, 2), (14, 6, 4), (18, 10, 8), (16, 5, 2), (20, 7, 8), (18, 7, 4)])
 def test_four_step_fused_scatter_kernel(zk, backend, orc, log_n, log_r, world):
     """b200zk_fft_colstep_scatter_dev: the column step that writes every transformed row into the
     owner's row buffer (NVLink peer stores between processes; here the `world` ranks are emulated
