@@ -159,3 +159,12 @@ def lazy_op(which, mode, x, w=None, wq=None):
     out = np.zeros_like(x)
     lib().emu_lazy_op(which, {"mul": 0, "add": 1, "sub": 2, "reduce": 3}[mode], _p(x), _p(w), _p(wq), _p(out), ctypes.c_size_t(x.shape[0]))
     return out
+
+
+def ntt_warp_plan(log_n):
+    """Pass plan of the warp-level NTT kernel: list of dicts (log_m, log_l, log_tw, is_last, log_m1, log_mid, log_m3, blocks), or None."""
+    out = np.zeros(1 + 8 * 4, dtype=np.uint32)
+    if not lib().emu_ntt_warp_plan(ctypes.c_uint32(log_n), _p(out)):
+        return None
+    keys = ("log_m", "log_l", "log_tw", "is_last", "log_m1", "log_mid", "log_m3", "blocks")
+    return [dict(zip(keys, (int(v) for v in out[1 + 8 * p: 9 + 8 * p]))) for p in range(int(out[0]))]

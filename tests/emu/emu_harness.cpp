@@ -106,6 +106,20 @@ void emu_ntt(const fe_t* in, uint32_t n_in, fe_t* out, uint32_t log_n, const fe_
 }
 
 
+// The warp-level kernel's pass plan (ntt_plan.hpp): out[0] = npass, then 8 words per pass:
+// log_m, log_l, log_tw, is_last, log_m1, log_mid, log_m3, blocks.  Returns 0 when log_n is not eligible.
+int emu_ntt_warp_plan(uint32_t log_n, uint32_t* out) {
+    if (!ntt_warp_eligible(log_n)) return 0;
+    NttShape s = ntt_plan_shape_warp(log_n);
+    out[0] = s.npass;
+    for (uint32_t p = 0; p < s.npass; ++p) {
+        const NttPassShape& q = s.pass[p];
+        uint32_t* o = out + 1 + 8 * p;
+        o[0] = q.log_m; o[1] = q.log_l; o[2] = q.log_tw; o[3] = q.is_last; o[4] = q.log_m1; o[5] = q.log_mid; o[6] = q.log_m3; o[7] = q.blocks;
+    }
+    return 1;
+}
+
 // Full MSM through the block programs of msm.cuh + the host finish of msm_plan.hpp.
 // out_affine: 64 bytes (x, y Montgomery).
 void emu_msm(const fe_t* scalars, const affine_t* bases, uint32_t n, int force_c, int fast_max, uint32_t seg_len, uint32_t* out_affine64) {
