@@ -391,3 +391,39 @@ def test_four_step_fused_scatter_kernel(zk, backend, orc, log_n, log_r, world):
     got = np.ascontiguousarray(np.transpose(Z, (1, 0, 2))).reshape(N, 4)
     want = orc.best_fft(a, omega_n, log_n) if log_n <= 16 else backend.best_fft(a, omega_n, log_n)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("env", [{"B200ZK_NTT_SHOUP": "0"}, {"B200ZK_NTT_FULL_TW": "0"}, {"B200ZK_NTT_WARP_MAX": "21"},
+                                 {"B200ZK_NTT_SHOUP": "0", "B200ZK_NTT_FULL_TW": "0"}])
+def test_ntt_fallback_plans_agree(zk, backend, orc, env):
+    """The plan switches of INTEGRATION.md §8 select other kernels / multipliers / twiddle tables for the same transform:
+    CIOS instead of the constant-operand multiplier in the warp-level kernel, two-level inter-pass twiddles, the block kernel
+    above 2^21.  They are what the library falls back to when the big tables do not fit, so each must give the bits of the
+    default plan (which the tests above and test_gpu_full_size.py pin to the oracle): sizes with 1, 2, 3 and 4 passes, plus the
+    coset extension (batched transforms, coset powers on load)."""
+    import os
+    from oracle import pyref
+    cases = [(k, orc.random_fr(1 << k, 70 + k), orc.ints_to_mont([pyref.omega_for_k(k)])[0]) for k in (7, 13, 16, 20, 22)]
+    want = [backend.best_fft(a, w, k) for k, a, w in cases]
+    dom = zk.EvaluationDomain(backend, 6, 16)
+    coeffs = orc.random_fr(1 << 16, 5)
+    want_ext = dom.coeff_to_extended(coeffs)
+    dom.close()
+    old = {name: os.environ.get(name) for name in env}
+    os.environ.update(env)
+    try:
+        be = zk.Backend(0)                                     # plans are built per context, with the switches read then
+        try:
+            for (k, a, w), ref in zip(cases, want):
+                assert np.array_equal(be.best_fft(a, w, k), ref), (env, k)
+            d2 = zk.EvaluationDomain(be, 6, 16)
+            assert np.array_equal(d2.coeff_to_extended(coeffs), want_ext), env
+            d2.close()
+        finally:
+            be.close()
+    finally:
+        for name, v in old.items():
+            if v is None:
+                os.environ.pop(name, None)
+            else:
+                os.environ[name] = v
