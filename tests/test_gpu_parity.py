@@ -58,7 +58,7 @@ def test_best_fft_sparse_inputs(zk, backend, orc, k, kind):
         d.close()
 
 
-@pytest.mark.parametrize("k", [18, 20, 21, 22, 23])
+@pytest.mark.parametrize("k", [18, 20, 21, 22, 23, 25])
 def test_best_fft_large_roundtrip_and_spot(backend, orc, k):
     from oracle import pyref
     n = 1 << k
