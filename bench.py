@@ -436,11 +436,13 @@ def run_gpu(args):
         line["roofline"] = {"bound": "imad", "kernel": f"ntt pass kernel, {q} transforms of 2^{k} per launch (the quotient cosets of one column: "
                                                         f"{ntt_passes(k)} launches of {q} x 2^{k - 7} warp tiles)",
                             "achieved": ach_b / 1e12, "peak": IMAD_WIDE_PEAK / 1e12, "unit": "T IMAD.WIDE.U32/s", "frac": ach_b / IMAD_WIDE_PEAK,
-                            # dram__bytes_read + write per pass launch of a 2^20 transform, ncu --set full
-                            # (profiles/r01_ncu_ntt_warp_summary.txt): the 32 MB transform and its 32 MB twiddle
-                            # table stay in L2, so traffic is below the 67 MB algorithmic bytes of a pass
-                            "traffic": ({"dram_bytes_per_launch": [67.7e6, 34.1e6, 35.0e6], "algorithmic_bytes_per_launch": 64 * n,
-                                         "source": "profiles/r01_ncu_ntt_warp_summary.txt (single 2^20 transform)"} if k == 20 else None),
+                            # dram__bytes_read + write of the three pass launches of one batched coset extension inside the proof
+                            # (5 transforms of 2^20 per launch), ncu --set full, profiles/r02_ncu_ntt_lazy_summary.txt: pass 1 also
+                            # streams the 160 MB coset-power table, every pass its 64-byte twiddle records (one use each)
+                            "traffic": ({"dram_bytes_per_launch": [672.2e6, 284.4e6, 293.9e6], "algorithmic_bytes_per_launch": 64 * n * 5,
+                                         "source": "profiles/r02_ncu_ntt_lazy_summary.txt (5 x 2^20 per launch; cold-cache capture)",
+                                         "single_2p20_dram_bytes_per_launch": [67.7e6, 34.1e6, 35.0e6],
+                                         "single_source": "profiles/r01_ncu_ntt_warp_summary.txt"} if k == 20 else None),
                             "ms_per_launch_group": ms_rows, "share_of_step": ph["ntt"] / max(sum(ph.values()), 1e-9),
                             "hbm_view": {"achieved": hbm_b, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_b / peaks["hbm_gbs"],
                                          "algorithmic_bytes": 64 * n * q, "peak_source": peak_src},
