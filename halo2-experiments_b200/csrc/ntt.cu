@@ -140,7 +140,7 @@ static int32_t build_plan(b200zk_ctx* ctx, uint32_t log_n, const host::HFr& omeg
     }
     // constant-operand tables for the warp-level kernel (B200ZK_NTT_SHOUP=0 keeps the CIOS multiplications)
     const char* es = getenv("B200ZK_NTT_SHOUP");
-    // (the block kernel of the sizes above 2^21 was tried with the same multiplier and lost: 2^24 3.85 -> 4.77 ms)
+    // (the block kernel was tried with the same multiplier while it still ran the sizes above 2^21, and lost: 2^24 3.85 -> 4.77 ms)
     if (plan.warp && !(es && es[0] == '0') && (s.npass == 1 || plan.tw_full)) {
         size_t N = (size_t)1 << log_n;
         if (cudaMalloc(&plan.roots_s, n_roots * sizeof(fe2_t)) == cudaSuccess) {
