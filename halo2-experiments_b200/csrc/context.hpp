@@ -117,7 +117,7 @@ int32_t ntt_run_cosets(b200zk_ctx* ctx, const fe_t* d_in, fe_t* d_out, uint32_t 
 // four-step sharded NTT building blocks (ntt.cu)
 int32_t ntt_colstep_run(b200zk_ctx* ctx, fe_t* d_block, uint32_t log_r, uint32_t log_cg, uint32_t col0,
                         const host::HFr& omega_n, uint32_t log_n, fe_t* const* peer_rows = nullptr, uint32_t world = 0);
-int32_t ntt_rows_run(b200zk_ctx* ctx, fe_t* d_rows, uint32_t nrows, const host::HFr& omega_c, uint32_t log_c);
+int32_t ntt_rows_run(b200zk_ctx* ctx, fe_t* d_rows, uint32_t nrows, const host::HFr& omega_c, uint32_t log_c, const host::HFr* post = nullptr);
 // a[i] *= m[i mod period]  (divide_by_vanishing_poly), m on device
 int32_t fr_scale_periodic(b200zk_ctx* ctx, fe_t* d_a, size_t n, const fe_t* d_m, uint32_t period);
 

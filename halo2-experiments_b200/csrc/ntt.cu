@@ -174,7 +174,8 @@ static int32_t ntt_run_batch(b200zk_ctx* ctx, const fe_t* d_in, uint32_t n_in, f
                              const fe_t* d_pre_tab, bool shared_input) {
     if (log_n > 3 * NTT_MAX_LOG_M) return fail(ctx, B200ZK_EINVAL, "ntt_run", "log_n too large");
     if (batch == 0) return B200ZK_OK;
-    if (batch > 1 && (pre || post || (d_pre_tab && !shared_input) || ((uint64_t)batch << log_n) > 0xFFFFFFFFull)) return fail(ctx, B200ZK_EINVAL, "ntt_run", "bad batch");
+    // (the post factors are indexed by the position inside a transform, so they work for a batch; the pre factors are not)
+    if (batch > 1 && (pre || (d_pre_tab && !shared_input) || ((uint64_t)batch << log_n) > 0xFFFFFFFFull)) return fail(ctx, B200ZK_EINVAL, "ntt_run", "bad batch");
     std::array<uint64_t, 5> key = {log_n, omega.v[0], omega.v[1], omega.v[2], omega.v[3]};
     auto it = ctx->ntt_plans.find(key);
     if (it == ctx->ntt_plans.end()) {
@@ -322,9 +323,10 @@ int32_t ntt_colstep_run(b200zk_ctx* ctx, fe_t* d_block, uint32_t log_r, uint32_t
     return B200ZK_OK;
 }
 
-// Row step: `nrows` independent natural-order transforms of size 2^log_c on contiguous rows, in place.
-int32_t ntt_rows_run(b200zk_ctx* ctx, fe_t* d_rows, uint32_t nrows, const host::HFr& omega_c, uint32_t log_c) {
-    return ntt_run_batch(ctx, d_rows, 1u << log_c, d_rows, log_c, omega_c, nullptr, nullptr, nrows);
+// Row step: `nrows` independent natural-order transforms of size 2^log_c on contiguous rows, in place; `post` (may be null):
+// three factors applied to the outputs by index mod 3 (the 1/n of an inverse transform: three equal factors).
+int32_t ntt_rows_run(b200zk_ctx* ctx, fe_t* d_rows, uint32_t nrows, const host::HFr& omega_c, uint32_t log_c, const host::HFr* post) {
+    return ntt_run_batch(ctx, d_rows, 1u << log_c, d_rows, log_c, omega_c, nullptr, post, nrows);
 }
 
 int32_t fr_scale_periodic(b200zk_ctx* ctx, fe_t* d_a, size_t n, const fe_t* d_m, uint32_t period) {

@@ -290,6 +290,15 @@ static int32_t commit_multi_dev(b200zk_pk* pk, const std::vector<const fe_t*>& c
     }
     return B200ZK_OK;
 }
+// `count` contiguous Lagrange columns to coefficient form in one launch per pass
+static int32_t lagrange_to_coeff_batch(b200zk_pk* pk, fe_t* d_a, uint32_t count) {
+    PhaseTimer t(pk, PH_NTT);
+    HFr post[3] = {pk->dom->ifft_divisor, pk->dom->ifft_divisor, pk->dom->ifft_divisor};
+    pk->ctx->ntt_sparse_hint = true;
+    int32_t rc = ntt_rows_run(pk->ctx, d_a, count, pk->dom->omega_inv, pk->dom->k, post);
+    pk->ctx->ntt_sparse_hint = false;
+    return rc;
+}
 static int32_t lagrange_to_coeff(b200zk_pk* pk, fe_t* d_a) {
     PhaseTimer t(pk, PH_NTT);
     HFr post[3] = {pk->dom->ifft_divisor, pk->dom->ifft_divisor, pk->dom->ifft_divisor};
@@ -722,10 +731,20 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
     }
     {
         SideStream side(ctx);
+        // columns that are already on the device arrive at once: all their inverse transforms as one batched launch per pass
+        // (columns from the host keep the per-column pipeline under the upload)
+        const bool batch_intt = advice_on_device && A > 1 && ((uint64_t)A << dom->k) <= 0xFFFFFFFFull;
+        if (batch_intt) {
+            ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pk->col_events[A - 1], 0));
+            ZK_CUDA(ctx, cudaMemcpyAsync(advice_polys, advice_values, (size_t)A * n * sizeof(fe_t), cudaMemcpyDeviceToDevice, ctx->stream));
+            ZK_TRY(lagrange_to_coeff_batch(pk, advice_polys, A));
+        }
         for (uint32_t c = 0; c < A; ++c) {
-            if (!split_upload) ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pk->col_events[c], 0));
-            ZK_CUDA(ctx, cudaMemcpyAsync(advice_polys + (size_t)c * n, advice_values + (size_t)c * n, n * sizeof(fe_t), cudaMemcpyDeviceToDevice, ctx->stream));
-            ZK_TRY(lagrange_to_coeff(pk, advice_polys + (size_t)c * n));
+            if (!batch_intt) {
+                if (!split_upload) ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pk->col_events[c], 0));
+                ZK_CUDA(ctx, cudaMemcpyAsync(advice_polys + (size_t)c * n, advice_values + (size_t)c * n, n * sizeof(fe_t), cudaMemcpyDeviceToDevice, ctx->stream));
+                ZK_TRY(lagrange_to_coeff(pk, advice_polys + (size_t)c * n));
+            }
             ZK_TRY(my_cosets(advice_polys + (size_t)c * n, advice_cosets + (size_t)c * ext, cj0, cj1));
         }
         for (uint32_t c = 0; c < I; ++c) ZK_TRY(my_cosets(inst_polys + (size_t)c * n, inst_cosets + (size_t)c * ext, cj0, cj1));
