@@ -892,9 +892,11 @@ static int32_t prove(b200zk_pk* pk, const fe_t* d_advice_in, bool advice_on_devi
         }
         {
             std::vector<CommPiece> pieces;
+            const bool batch_intt = !sh.on() && S > 1 && ((uint64_t)S << dom->k) <= 0xFFFFFFFFull;      // one rank: all sets in one launch per pass
+            if (batch_intt) ZK_TRY(lagrange_to_coeff_batch(pk, perm_polys, S));
             for (uint32_t s = 0; s < S; ++s) {
                 fe_t* z = perm_polys + (size_t)s * n;
-                if (sh.set_mine(s)) ZK_TRY(lagrange_to_coeff(pk, z));
+                if (!batch_intt && sh.set_mine(s)) ZK_TRY(lagrange_to_coeff(pk, z));
                 pieces.push_back({z, n * sizeof(fe_t), sh.set_owner(s)});
             }
             ZK_TRY(share(pieces));
